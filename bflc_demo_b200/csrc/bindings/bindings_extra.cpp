@@ -1,0 +1,218 @@
+// Bindings for the symmetric heap, the federated hot-path kernels, optimizers and
+// elementwise helpers.  (GEMM bindings: torch_bindings.cpp.)
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <cstring>
+#include <memory>
+#include <optional>
+
+#include "bflc_kernels.h"
+#include "symm_heap.hpp"
+
+namespace py = pybind11;
+using OptT = std::optional<at::Tensor>;
+
+namespace {
+
+void check(cudaError_t e, const char* what) {
+  TORCH_CHECK(e == cudaSuccess, "bflc::", what, " failed: ", cudaGetErrorString(e));
+}
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+template <typename T>
+T* P(int64_t addr) { return reinterpret_cast<T*>(static_cast<uintptr_t>(addr)); }
+
+bflc::FedArgs make_fed(const py::dict& d) {
+  bflc::FedArgs f;
+  std::memset(&f, 0, sizeof(f));
+  f.rank = d["rank"].cast<int>();
+  f.n_ranks = d["n_ranks"].cast<int>();
+  auto bases = d["peer_bases"].cast<std::vector<int64_t>>();
+  TORCH_CHECK((int)bases.size() == f.n_ranks && f.n_ranks <= bflc::kMaxRanks, "bad peer table");
+  for (int r = 0; r < f.n_ranks; ++r) f.peers.base[r] = P<char>(bases[r]);
+  f.peers.mc_base = P<char>(d["mc_base"].cast<int64_t>());
+  auto& l = f.lay;
+  l.flags_off = d["flags_off"].cast<int64_t>();
+  l.state_off = d["state_off"].cast<int64_t>();
+  l.plan_off = d["plan_off"].cast<int64_t>();
+  l.scores_off = d["scores_off"].cast<int64_t>();
+  l.meta_off = d["meta_off"].cast<int64_t>();
+  l.work_master_off = d["work_master_off"].cast<int64_t>();
+  l.work_shadow_off = d["work_shadow_off"].cast<int64_t>();
+  auto um = d["upload_master_off"].cast<std::vector<int64_t>>();
+  auto us = d["upload_shadow_off"].cast<std::vector<int64_t>>();
+  l.upload_master_off[0] = um.at(0); l.upload_master_off[1] = um.at(1);
+  l.upload_shadow_off[0] = us.at(0); l.upload_shadow_off[1] = us.at(1);
+  l.global_off = d["global_off"].cast<int64_t>();
+  l.global_shadow_off = d["global_shadow_off"].cast<int64_t>();
+  l.ring_off = d["ring_off"].cast<int64_t>();
+  l.n_params = d["n_params"].cast<int64_t>();
+  l.ring_slots = d["ring_slots"].cast<int>();
+  return f;
+}
+
+struct PyHeap {
+  std::unique_ptr<bflc::SymmHeap> h;
+};
+
+}  // namespace
+
+void bind_extra(py::module_& m) {
+  // ------------------------------------------------------------ symmetric heap
+  py::class_<PyHeap>(m, "SymmHeap")
+      .def(py::init([](int64_t bytes, int rank, int world, int device, const std::string& mode) {
+        bflc::SymmHeap::Mode md = mode == "vmm"   ? bflc::SymmHeap::Mode::VMM
+                                  : mode == "ipc" ? bflc::SymmHeap::Mode::IPC
+                                                  : bflc::SymmHeap::Mode::LOCAL;
+        auto p = std::make_unique<PyHeap>();
+        p->h = std::make_unique<bflc::SymmHeap>((size_t)bytes, rank, world, device, md);
+        return p;
+      }))
+      .def("export_handle", [](PyHeap& s) { return py::bytes(s.h->export_handle()); })
+      .def("import_handles",
+           [](PyHeap& s, const std::vector<py::bytes>& blobs) {
+             std::vector<std::string> v;
+             for (auto& b : blobs) v.emplace_back(static_cast<std::string>(b));
+             s.h->import_handles(v);
+           })
+      .def("mc_create_and_export", [](PyHeap& s) { return py::bytes(s.h->mc_create_and_export()); })
+      .def("mc_import_and_add",
+           [](PyHeap& s, const py::bytes& b) { return s.h->mc_import_and_add(std::string(b)); })
+      .def("mc_bind_and_map", [](PyHeap& s) { return s.h->mc_bind_and_map(); })
+      .def("local_ptr", [](PyHeap& s) { return reinterpret_cast<int64_t>(s.h->local_ptr()); })
+      .def("peer_ptr", [](PyHeap& s, int r) { return reinterpret_cast<int64_t>(s.h->peer_ptr(r)); })
+      .def("mc_ptr", [](PyHeap& s) { return reinterpret_cast<int64_t>(s.h->mc_ptr()); })
+      .def("bytes", [](PyHeap& s) { return (int64_t)s.h->bytes(); })
+      .def("last_error", [](PyHeap& s) { return s.h->last_error(); })
+      .def_static("multicast_supported", [](int dev) { return bflc::SymmHeap::multicast_supported(dev); });
+
+  // A torch tensor aliasing raw device memory (heap regions, peer-mapped regions).
+  m.def("tensor_from_ptr", [](int64_t ptr, std::vector<int64_t> shape, py::object dtype, int device) {
+    auto st = torch::python::detail::py_object_to_dtype(dtype);
+    auto opts = at::TensorOptions().dtype(st).device(at::kCUDA, device);
+    return at::from_blob(P<void>(ptr), shape, [](void*) {}, opts);
+  });
+
+  m.def("struct_sizes", [] {
+    py::dict d;
+    d["RoundState"] = sizeof(bflc::RoundState);
+    d["RoundPlan"] = sizeof(bflc::RoundPlan);
+    d["BlockRecord"] = sizeof(bflc::BlockRecord);
+    d["UploadMeta"] = sizeof(bflc::UploadMeta);
+    d["GemmDynamic"] = sizeof(bflc::GemmDynamic);
+    d["FLAG_COUNT"] = (int)bflc::FLAG_COUNT;
+    d["kMaxRanks"] = bflc::kMaxRanks;
+    d["plan_dyn_off"] = offsetof(bflc::RoundPlan, dyn);
+    d["plan_correct_off"] = offsetof(bflc::RoundPlan, correct);
+    d["plan_loss_sum_off"] = offsetof(bflc::RoundPlan, loss_sum);
+    d["plan_train_correct_off"] = offsetof(bflc::RoundPlan, train_correct);
+    d["plan_opt_step_off"] = offsetof(bflc::RoundPlan, opt_step);
+    d["plan_is_trainer_off"] = offsetof(bflc::RoundPlan, is_trainer);
+    d["plan_is_comm_off"] = offsetof(bflc::RoundPlan, is_comm);
+    d["state_epoch_off"] = offsetof(bflc::RoundState, epoch);
+    d["state_role_off"] = offsetof(bflc::RoundState, role);
+    d["state_global_loss_off"] = offsetof(bflc::RoundState, global_loss);
+    d["state_digest_off"] = offsetof(bflc::RoundState, model_digest);
+    d["CUtensorMap"] = sizeof(CUtensorMap);
+    return d;
+  });
+
+  // host-side init of the replicated ledger page
+  m.def("state_init_bytes", [](int n_ranks, int n_comm, int n_aggregate, std::vector<int> roles) {
+    bflc::RoundState st;
+    std::memset(&st, 0, sizeof(st));
+    st.epoch = 0; st.n_ranks = n_ranks; st.n_comm = n_comm; st.n_aggregate = n_aggregate;
+    for (int r = 0; r < n_ranks && r < bflc::kMaxRanks; ++r) st.role[r] = (uint32_t)roles.at(r);
+    return py::bytes(reinterpret_cast<const char*>(&st), sizeof(st));
+  });
+
+  // ------------------------------------------------------------ fed kernels
+  m.def("fed_plan_round", [](const py::dict& fd, std::vector<std::pair<int64_t, bool>> layers,
+                             int steps_per_round) {
+    bflc::FedArgs f = make_fed(fd);
+    bflc::PlanLayer pl[bflc::kMaxPlanLayers];
+    TORCH_CHECK((int)layers.size() <= bflc::kMaxPlanLayers, "too many plan layers");
+    for (size_t i = 0; i < layers.size(); ++i) {
+      pl[i].bias_off = layers[i].first;
+      pl[i].use_bias = layers[i].second ? 1 : 0;
+    }
+    check(bflc::fed_plan_round(f, pl, (int)layers.size(), steps_per_round, cur_stream()),
+          "fed_plan_round");
+  });
+  m.def("fed_upload", [](const py::dict& fd, int n_samples, int n_loss_terms, int byz_mode,
+                         double byz_scale) {
+    check(bflc::fed_upload(make_fed(fd), n_samples, n_loss_terms, byz_mode, (float)byz_scale,
+                           cur_stream()),
+          "fed_upload");
+  });
+  m.def("fed_consensus_aggregate", [](const py::dict& fd, int n_val, bool weight_by_score,
+                                      bool two_shot, bool use_mc) {
+    check(bflc::fed_consensus_aggregate(make_fed(fd), n_val, weight_by_score ? 1 : 0,
+                                        two_shot ? 1 : 0, use_mc ? 1 : 0, cur_stream()),
+          "fed_consensus_aggregate");
+  });
+  m.def("set_predicate", [](int64_t ptr) { bflc::set_predicate(P<const int>(ptr)); });
+  m.def("p2p_read_probe", [](int64_t src, int64_t dst, int64_t n_vec) {
+    check(bflc::p2p_read_probe(P<const float4>(src), P<float4>(dst), n_vec, cur_stream()),
+          "p2p_read_probe");
+  });
+  m.def("mc_store_probe", [](int64_t mc_dst, int64_t src, int64_t n_vec) {
+    check(bflc::mc_store_probe(P<float4>(mc_dst), P<const float4>(src), n_vec, cur_stream()),
+          "mc_store_probe");
+  });
+
+  // ------------------------------------------------------------ optimizers
+  m.def("optim_step",
+        [](bool adam, at::Tensor master, at::Tensor grad, const OptT& shadow, const OptT& mm,
+           const OptT& vv, double lr, double wd, double b1, double b2, double eps, int step,
+           int64_t step_dev_ptr, int64_t active_ptr, bool zero_grad) {
+          bflc::OptimArgs a;
+          a.master = master.data_ptr<float>();
+          a.grad = grad.data_ptr<float>();
+          a.shadow_bf16 = shadow.has_value() ? shadow->data_ptr() : nullptr;
+          a.n = master.numel();
+          a.lr = (float)lr; a.weight_decay = (float)wd;
+          a.m = mm.has_value() ? mm->data_ptr<float>() : nullptr;
+          a.v = vv.has_value() ? vv->data_ptr<float>() : nullptr;
+          a.beta1 = (float)b1; a.beta2 = (float)b2; a.eps = (float)eps;
+          a.step = step;
+          a.step_dev = P<const int>(step_dev_ptr);
+          a.active = active_ptr ? P<const int>(active_ptr) : bflc::current_predicate();
+          a.zero_grad = zero_grad ? 1 : 0;
+          check(adam ? bflc::adam_step(a, cur_stream()) : bflc::sgd_step(a, cur_stream()),
+                "optim_step");
+        });
+
+  // ------------------------------------------------------------ elementwise
+  m.def("cast_f32_to_bf16", [](at::Tensor src, at::Tensor dst) {
+    check(bflc::cast_f32_to_bf16(src.data_ptr<float>(), dst.data_ptr(), src.numel(), cur_stream()),
+          "cast_f32_to_bf16");
+  });
+  m.def("cast_bf16_to_f32", [](at::Tensor src, at::Tensor dst) {
+    check(bflc::cast_bf16_to_f32(src.data_ptr(), dst.data_ptr<float>(), src.numel(), cur_stream()),
+          "cast_bf16_to_f32");
+  });
+  m.def("cast_u8_to_bf16", [](at::Tensor src, at::Tensor dst, double scale) {
+    check(bflc::cast_u8_to_bf16(src.data_ptr<uint8_t>(), dst.data_ptr(), src.numel(), (float)scale,
+                                cur_stream()),
+          "cast_u8_to_bf16");
+  });
+  m.def("quantize_fp8", [](at::Tensor src, at::Tensor dst, double inv_scale) {
+    check(bflc::quantize_fp8(src.data_ptr(), reinterpret_cast<uint8_t*>(dst.data_ptr()),
+                             src.numel(), (float)inv_scale, cur_stream()),
+          "quantize_fp8");
+  });
+  m.def("amax_bf16", [](at::Tensor src, at::Tensor out) {
+    check(bflc::amax_bf16(src.data_ptr(), src.numel(), out.data_ptr<float>(), cur_stream()),
+          "amax_bf16");
+  });
+  m.def("fill_f32", [](at::Tensor dst, double v) {
+    check(bflc::fill_f32(dst.data_ptr<float>(), dst.numel(), (float)v, cur_stream()), "fill_f32");
+  });
+  m.def("add_bf16", [](at::Tensor a, at::Tensor b, at::Tensor out) {
+    check(bflc::add_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), cur_stream()),
+          "add_bf16");
+  });
+}

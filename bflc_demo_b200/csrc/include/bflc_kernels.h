@@ -1,0 +1,298 @@
+// Host-callable C++ API of the sm_100a kernel library (no torch dependency).
+// All launchers are asynchronous on `stream`.
+//
+// Parity map (reference = iammcy/BFLC-demo, CPU-only TensorFlow + C++ contract):
+//   gemm / linear       <- K1  x@W+b                 python-sdk/main.py:120,180,293
+//   xent epilogue       <- K2  softmax-xent mean     python-sdk/main.py:123
+//   backward + SGD/Adam <- K3  autodiff + optimizer  python-sdk/main.py:126-130
+//   accuracy epilogue   <- K6  argmax==argmax mean   python-sdk/main.py:182-183
+//   consensus kernel    <- K7-K10 median/top-K/FedAvg/apply
+//                              CommitteePrecompiled.cpp:349-456
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace bflc {
+
+enum class DType : int { F32 = 0, BF16 = 1, FP8_E4M3 = 2 };
+enum class Act : int { NONE = 0, RELU = 1, GELU = 2 };
+enum class EpiKind : int { GENERIC = 0, XENT = 1, ARGMAX_ACC = 2 };
+
+// D[b] (M x N) = alpha * A[b] (M x K) * B[b]^T (N x K)
+//   K-major operand : memory is [rows = M|N][K], K contiguous
+//   MN-major operand: memory is [K][M|N], M|N contiguous
+struct GemmOperand {
+  const void* ptr = nullptr;
+  int64_t ld = 0;            // row stride in elements
+  int64_t batch_stride = 0;  // in elements; 0 = shared across the batch
+  bool mn_major = false;
+};
+
+struct GemmEpilogue {
+  EpiKind kind = EpiKind::GENERIC;
+  // ---- generic ----
+  void* d = nullptr;  // output [batch][M][ldd]
+  DType d_dtype = DType::BF16;
+  int64_t ldd = 0;
+  int64_t d_batch_stride = 0;
+  float alpha = 1.f;
+  const float* bias = nullptr;              // [N] fp32, per output column
+  const float* const* bias_ptrs = nullptr;  // optional per-batch bias pointers (device array)
+  Act act = Act::NONE;
+  void* aux_out = nullptr;       // bf16 pre-activation copy (GELU backward needs it)
+  const void* aux_in = nullptr;  // bf16 [M][ldd]: act-backward mask source
+  int act_bwd = 0;               // 1: out *= (aux_in > 0)  2: out *= gelu'(aux_in)
+  float* colsum = nullptr;       // [N] fp32 += column sums of the stored values (bias grad)
+  int split_k = 1;               // >1: fp32 atomic accumulate into a zeroed d
+  int accumulate = 0;            // 1: d += result (fp32 d only, non-atomic)
+  // ---- xent / accuracy (row-wise over the N <= BN logits of a row) ----
+  const int32_t* labels = nullptr;  // [batch][M]
+  int64_t labels_batch_stride = 0;
+  float grad_scale = 1.f;         // dlogits = (softmax - onehot) * grad_scale
+  float* loss_sum = nullptr;      // += sum_rows (lse - z_label)
+  unsigned int* correct = nullptr;  // [batch] += #(argmax == label)
+};
+
+struct GemmDynamic;  // device-resident per-launch arguments, defined below
+
+struct GemmProblem {
+  int M = 0, N = 0, K = 0, batch = 1;
+  DType ab_dtype = DType::BF16;
+  GemmOperand a, b;
+  // optional: per-batch B tensor maps living in device memory (grouped GEMM whose
+  // B operands are in *different allocations*, e.g. peer GPUs' weights)
+  const CUtensorMap* b_maps_dev = nullptr;
+  // optional: batch count / map selection / bias / readiness flags read from device memory
+  const GemmDynamic* dyn = nullptr;
+  GemmEpilogue epi;
+  // debug overrides for descriptor bring-up (0 = use built-in)
+  uint32_t dbg_lbo_a = 0, dbg_sbo_a = 0, dbg_lbo_b = 0, dbg_sbo_b = 0;
+};
+
+// returns cudaSuccess or the failing status; throws nothing
+cudaError_t gemm_sm100(const GemmProblem& p, cudaStream_t stream);
+// Build the B-operand tensor map the kernel would use (for b_maps_dev arrays).
+cudaError_t gemm_make_b_map(const GemmProblem& p, CUtensorMap* out_host);
+int gemm_pick_bn(int N, EpiKind kind);
+// number of kernels launched by this library since process start (bench bookkeeping)
+unsigned long long launch_count();
+void note_launch();
+
+// ---------------------------------------------------------------- elementwise
+cudaError_t cast_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t s);
+cudaError_t cast_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t s);
+cudaError_t cast_u8_to_bf16(const uint8_t* src, void* dst, int64_t n, float scale, cudaStream_t s);
+cudaError_t quantize_fp8(const void* src_bf16, uint8_t* dst, int64_t n, float inv_scale,
+                         cudaStream_t s);
+cudaError_t amax_bf16(const void* src, int64_t n, float* amax_out, cudaStream_t s);
+cudaError_t fill_f32(float* dst, int64_t n, float v, cudaStream_t s);
+
+// ------------------------------------------------------------------ optimizers
+// Flat multi-tensor update. master fp32 is updated in place; shadow (bf16,
+// optional fp8 second shadow) is the compute copy the GEMMs read.  `active` (device
+// flag, may be null) lets a captured graph skip the update on non-trainer ranks.
+struct OptimArgs {
+  float* master = nullptr;
+  const float* grad = nullptr;
+  void* shadow_bf16 = nullptr;
+  int64_t n = 0;
+  float lr = 1e-3f, weight_decay = 0.f;
+  // adam
+  float* m = nullptr;
+  float* v = nullptr;
+  float beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
+  const int* step_dev = nullptr;  // device base step (steps before this round), may be null
+  int step = 1;                   // Adam t = (step_dev ? *step_dev : 0) + step
+  const int* active = nullptr;
+  int zero_grad = 1;  // clear grad after use (it is an accumulation target)
+};
+cudaError_t sgd_step(const OptimArgs& a, cudaStream_t s);
+cudaError_t adam_step(const OptimArgs& a, cudaStream_t s);
+
+// ------------------------------------------------------- NN support kernels
+cudaError_t im2col_bf16(const void* x, void* col, int N, int C, int H, int W, int KH, int KW,
+                        int stride, int pad, int OH, int OW, int64_t ld_col, cudaStream_t s);
+cudaError_t col2im_bf16(const void* col, void* dx, int N, int C, int H, int W, int KH, int KW,
+                        int stride, int pad, int OH, int OW, int64_t ld_col, cudaStream_t s);
+cudaError_t maxpool2d_fwd(const void* x, void* y, int32_t* idx, int N, int C, int H, int W, int k,
+                          int stride, int pad, int OH, int OW, cudaStream_t s);
+cudaError_t maxpool2d_bwd(const void* dy, const int32_t* idx, void* dx, int64_t n_out,
+                          int64_t n_in, cudaStream_t s);
+cudaError_t avgpool_global_fwd(const void* x, void* y, int N, int HW, int C, cudaStream_t s);
+cudaError_t avgpool_global_bwd(const void* dy, void* dx, int N, int HW, int C, cudaStream_t s);
+// channels-last batch norm over [rows][C]; train mode computes batch statistics
+cudaError_t batchnorm_fwd(const void* x, void* y, const float* gamma, const float* beta,
+                          float* mean, float* rstd, float* run_mean, float* run_var,
+                          int64_t rows, int C, float eps, float momentum, int training, int relu,
+                          const void* residual, cudaStream_t s);
+cudaError_t batchnorm_bwd(const void* dy, const void* x, const void* y, const float* gamma,
+                          const float* mean, const float* rstd, void* dx, float* dgamma,
+                          float* dbeta, void* dresidual, int64_t rows, int C, int relu,
+                          cudaStream_t s);
+cudaError_t layernorm_fwd(const void* x, const void* residual, void* y, const float* gamma,
+                          const float* beta, float* mean, float* rstd, int64_t rows, int C,
+                          float eps, cudaStream_t s);
+cudaError_t layernorm_bwd(const void* dy, const void* xin, const float* gamma, const float* mean,
+                          const float* rstd, void* dx, float* dgamma, float* dbeta, int64_t rows,
+                          int C, cudaStream_t s);
+cudaError_t softmax_rows_fwd(const void* x, void* y, int64_t rows, int cols, float scale,
+                             cudaStream_t s);
+cudaError_t softmax_rows_bwd(const void* dy, const void* y, void* dx, int64_t rows, int cols,
+                             float scale, cudaStream_t s);
+cudaError_t embedding_fwd(const int32_t* ids, const void* table_bf16, const void* pos_bf16,
+                          void* out, int64_t rows, int seq, int C, cudaStream_t s);
+cudaError_t embedding_bwd(const int32_t* ids, const void* dy, float* dtable, float* dpos,
+                          int64_t rows, int seq, int C, cudaStream_t s);
+cudaError_t add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStream_t s);
+cudaError_t transpose_0213_bf16(const void* x, void* y, int d0, int d1, int d2, int d3,
+                                cudaStream_t s);
+
+// -------------------------------------------------- federated hot-path kernels
+constexpr int kMaxRanks = 8;
+constexpr int kMaxPlanLayers = 4;
+
+// Per-launch dynamic GEMM arguments that live in device memory so one captured CUDA graph
+// serves every round even though committee membership changes ("roles as data").
+struct GemmDynamic {
+  int active_batches;                     // CTAs with batch index >= this exit immediately
+  int map_index[kMaxRanks];               // b_maps_dev[map_index[b]] is batch b's B operand
+  const float* bias[kMaxRanks];           // per-batch bias (may point into a peer's HBM)
+  const uint32_t* wait_flag[kMaxRanks];   // producer waits *wait_flag[b] >= wait_value first
+  uint32_t wait_value;
+};
+
+// Device-resident round state ("the ledger page"): one replica per rank inside its symmetric
+// heap, kept identical on all ranks by the consensus kernel.
+struct RoundState {
+  uint32_t epoch;                 // current federated round
+  uint32_t n_ranks, n_comm, n_aggregate;
+  uint32_t role[kMaxRanks];       // RoleBits (consensus_math.hpp)
+  float last_median[kMaxRanks];
+  uint32_t selected_mask;
+  float global_loss;
+  unsigned long long model_digest;
+  uint32_t blocks_appended;
+  uint32_t pad;
+};
+
+struct UploadMeta {
+  uint32_t n_samples;
+  float avg_cost;
+};
+
+// Scratch written by the plan kernel at the start of every round (local, not replicated).
+struct RoundPlan {
+  int is_trainer;                 // predicate flags consumed by captured kernels
+  int is_comm;
+  int n_cand;
+  int cand_rank[kMaxRanks];       // trainer rank of candidate slot z
+  uint32_t parity;
+  GemmDynamic dyn[kMaxPlanLayers];
+  unsigned int correct[kMaxRanks];  // validation hits per candidate slot (accuracy epilogue)
+  float loss_sum;                   // local-training loss accumulator (xent epilogue)
+  unsigned int train_correct;
+  int opt_step;                     // optimizer steps completed before this round (Adam t base)
+  int opt_total;                    // running total, advanced by the plan kernel on trainer ranks
+  unsigned int upload_blocks_done;
+  unsigned int consensus_blocks_done;
+  unsigned long long digest_acc;
+};
+
+struct PeerTable {
+  char* base[kMaxRanks];  // peer-mapped base pointer of each rank's symmetric heap
+  char* mc_base;          // NVLS multicast VA of the same heap (null if unavailable)
+};
+
+// Byte offsets of the regions inside every rank's symmetric heap (identical on all ranks).
+struct HeapLayout {
+  long long flags_off;         // uint32 [FLAG_COUNT]
+  long long state_off;         // RoundState
+  long long plan_off;          // RoundPlan
+  long long scores_off;        // float [2 parity][kMaxRanks committee][kMaxRanks trainer]
+  long long meta_off;          // UploadMeta [2 parity][kMaxRanks]
+  long long work_master_off;   // fp32 training weights (torch parameters alias this)
+  long long work_shadow_off;   // bf16 copy the GEMMs read
+  long long upload_master_off[2];  // fp32 uploaded local model, by epoch parity
+  long long upload_shadow_off[2];  // bf16 of the same (what the committee validates)
+  long long global_off;        // fp32 global model replica
+  long long global_shadow_off; // bf16
+  long long ring_off;          // BlockRecord [ring_slots]
+  long long n_params;          // elements (multiple of 8)
+  int ring_slots;
+  int pad;
+};
+
+// One record per finished round, written by the consensus kernel and drained by the host
+// C++ ledger, which re-executes the election from the raw score rows (state-machine
+// replication check) and chains the block hash.
+struct BlockRecord {
+  uint32_t epoch;
+  uint32_t n_ranks, n_comm, n_aggregate;
+  uint32_t role_before[kMaxRanks];
+  uint32_t role_after[kMaxRanks];
+  float score_rows[kMaxRanks][kMaxRanks];  // [committee][trainer]
+  uint32_t scored_mask[kMaxRanks];         // bit t of row c: score_rows[c][t] is valid
+  float median[kMaxRanks];
+  uint32_t n_samples[kMaxRanks];
+  float avg_cost[kMaxRanks];
+  float weight[kMaxRanks];
+  uint32_t admitted_mask;
+  uint32_t selected_mask;
+  float global_loss;
+  uint32_t weight_by_score;
+  unsigned long long model_digest;
+  uint32_t seq;  // epoch + 1, release-stored last: the record is complete when seq matches
+  uint32_t pad;
+};
+
+enum FlagSlot : int {
+  FLAG_TRAINED = 0,   // [kMaxRanks] trainer r's upload for epoch e is readable   -> e + 1
+  FLAG_SCORED = 8,    // [kMaxRanks] committee r's score row for epoch e landed   -> e + 1
+  FLAG_DONE = 16,     // [kMaxRanks] rank r finished aggregating epoch e           -> e + 1
+  FLAG_SLICE = 24,    // [kMaxRanks] two-shot: slice owner r published epoch e     -> e + 1
+  FLAG_COUNT = 64
+};
+
+struct FedArgs {
+  PeerTable peers;
+  HeapLayout lay;
+  int rank;
+  int n_ranks;
+};
+
+struct PlanLayer {
+  long long bias_off;   // element offset of this layer's bias in the flat parameter buffer
+  int use_bias;
+};
+
+// start of round: predicates, candidate list, per-layer GemmDynamic, accumulator reset,
+// and (safety) wait until every rank finished consuming the buffers about to be reused.
+cudaError_t fed_plan_round(const FedArgs& f, const PlanLayer* layers, int n_layers,
+                           int steps_per_round, cudaStream_t s);
+// trainer ("UploadLocalUpdate", CommitteePrecompiled.cpp:215-258): copy the trained weights
+// into the peer-readable upload buffers, push {n_samples, avg_cost} to every replica and
+// release FLAG_TRAINED on every peer.  byz_mode 1 = sign-flipped, scaled delta (fault
+// injection).
+cudaError_t fed_upload(const FedArgs& f, int n_samples, int n_loss_terms, int byz_mode,
+                       float byz_scale, cudaStream_t s);
+// everyone ("UploadScores" + "Aggregate", CommitteePrecompiled.cpp:259-298, 349-456):
+// committee ranks push their score row to every replica; all ranks wait for the rows, run
+// the consensus math, reduce the selected uploads over P2P loads in a fixed order, write
+// the new global model (+bf16, + next round's training buffers), append the BlockRecord,
+// re-elect, epoch++ and release FLAG_DONE.
+cudaError_t fed_consensus_aggregate(const FedArgs& f, int n_val, int weight_by_score,
+                                    int two_shot, int use_multicast, cudaStream_t s);
+
+// thread-local predicate: kernels launched while it is set start with
+// `if (*pred == 0) return;` (role predication inside a captured graph)
+void set_predicate(const int* pred);
+const int* current_predicate();
+
+// stand-alone P2P / multicast bandwidth probes (profiles/, substrate smoke test)
+cudaError_t p2p_read_probe(const float4* peer_src, float4* local_dst, int64_t n_vec,
+                           cudaStream_t s);
+cudaError_t mc_store_probe(float4* mc_dst, const float4* local_src, int64_t n_vec,
+                           cudaStream_t s);
+
+}  // namespace bflc

@@ -1,0 +1,244 @@
+// Bandwidth-bound helpers: dtype casts / fp8 quantisation, and the fused flat-buffer
+// optimizers.  Every kernel is vectorised to 16-byte accesses and sized as a grid-stride
+// loop over 148 SMs x 8 CTAs.
+//
+// Optimizer parity: the reference trains with tf.train.GradientDescentOptimizer(0.001)
+// and keeps Adam as a commented-out alternative (python-sdk/main.py:126-130); both are
+// first-class here.  The update also refreshes the bf16 "shadow" weights the tensor-core
+// GEMMs read, so no separate cast pass ever touches the parameters.
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+
+#include "bflc_kernels.h"
+
+namespace bflc {
+
+namespace {
+
+constexpr int kBlock = 256;
+inline int grid_for(int64_t n_vec) {
+  int64_t g = (n_vec + kBlock - 1) / kBlock;
+  const int64_t cap = 148 * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__global__ void k_cast_f32_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                int64_t n) {
+  const int64_t nv = n / 8;
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = tid; i < nv; i += stride) {
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i];
+    const float4 b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(dst)[i] = o;
+  }
+  for (int64_t i = nv * 8 + tid; i < n; i += stride) dst[i] = __float2bfloat16(src[i]);
+}
+
+__global__ void k_cast_bf16_f32(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
+                                int64_t n) {
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = tid; i < n; i += stride) dst[i] = __bfloat162float(src[i]);
+}
+
+__global__ void k_cast_u8_bf16(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                               int64_t n, float scale) {
+  const int64_t nv = n / 16;
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = tid; i < nv; i += stride) {
+    const uint4 in = reinterpret_cast<const uint4*>(src)[i];
+    const uint32_t w[4] = {in.x, in.y, in.z, in.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[2 * k] = pack_bf16x2((w[k] & 0xff) * scale, ((w[k] >> 8) & 0xff) * scale);
+      o[2 * k + 1] = pack_bf16x2(((w[k] >> 16) & 0xff) * scale, (w[k] >> 24) * scale);
+    }
+    reinterpret_cast<uint4*>(dst)[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<uint4*>(dst)[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+  for (int64_t i = nv * 16 + tid; i < n; i += stride) dst[i] = __float2bfloat16(src[i] * scale);
+}
+
+__global__ void k_quant_fp8(const __nv_bfloat16* __restrict__ src, uint8_t* __restrict__ dst,
+                            int64_t n, float inv_scale) {
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t nv = n / 8;
+  for (int64_t i = tid; i < nv; i += stride) {
+    const uint4 in = reinterpret_cast<const uint4*>(src)[i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&in);
+    uint8_t o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(h[k]);
+      o[2 * k] = __nv_cvt_float_to_fp8(f.x * inv_scale, __NV_SATFINITE, __NV_E4M3);
+      o[2 * k + 1] = __nv_cvt_float_to_fp8(f.y * inv_scale, __NV_SATFINITE, __NV_E4M3);
+    }
+    reinterpret_cast<uint2*>(dst)[i] = *reinterpret_cast<uint2*>(o);
+  }
+  for (int64_t i = nv * 8 + tid; i < n; i += stride)
+    dst[i] = __nv_cvt_float_to_fp8(__bfloat162float(src[i]) * inv_scale, __NV_SATFINITE, __NV_E4M3);
+}
+
+__global__ void k_amax_bf16(const __nv_bfloat16* __restrict__ src, int64_t n, float* out) {
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  float m = 0.f;
+  for (int64_t i = tid; i < n; i += stride) m = fmaxf(m, fabsf(__bfloat162float(src[i])));
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  // non-negative floats order like their bit patterns
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+
+__global__ void k_fill(float* dst, int64_t n, float v) {
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = tid; i < n; i += stride) dst[i] = v;
+}
+
+__global__ void k_add_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* o,
+                           int64_t n) {
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t nv = n / 8;
+  for (int64_t i = tid; i < nv; i += stride) {
+    const uint4 x = reinterpret_cast<const uint4*>(a)[i];
+    const uint4 y = reinterpret_cast<const uint4*>(b)[i];
+    const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&x);
+    const __nv_bfloat162* hy = reinterpret_cast<const __nv_bfloat162*>(&y);
+    uint4 r;
+    uint32_t* ro = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fx = __bfloat1622float2(hx[k]);
+      const float2 fy = __bfloat1622float2(hy[k]);
+      ro[k] = pack_bf16x2(fx.x + fy.x, fx.y + fy.y);
+    }
+    reinterpret_cast<uint4*>(o)[i] = r;
+  }
+  for (int64_t i = nv * 8 + tid; i < n; i += stride)
+    o[i] = __float2bfloat16(__bfloat162float(a[i]) + __bfloat162float(b[i]));
+}
+
+// ------------------------------------------------------------------ optimizers
+template <bool kAdam>
+__global__ void k_optim(OptimArgs a) {
+  if (a.active != nullptr && *a.active == 0) return;
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  float bc1 = 1.f, bc2 = 1.f;
+  if (kAdam) {
+    const int t = (a.step_dev ? *a.step_dev : 0) + a.step;
+    bc1 = 1.f - powf(a.beta1, static_cast<float>(t));
+    bc2 = 1.f - powf(a.beta2, static_cast<float>(t));
+  }
+  const int64_t nv = a.n / 4;
+  __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(a.shadow_bf16);
+  for (int64_t i = tid; i < nv; i += stride) {
+    float4 w = reinterpret_cast<float4*>(a.master)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(a.grad)[i];
+    float wv[4] = {w.x, w.y, w.z, w.w};
+    const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+    if (kAdam) {
+      float4 m4 = reinterpret_cast<float4*>(a.m)[i];
+      float4 v4 = reinterpret_cast<float4*>(a.v)[i];
+      float mv[4] = {m4.x, m4.y, m4.z, m4.w};
+      float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float g = gv[k] + a.weight_decay * wv[k];
+        mv[k] = a.beta1 * mv[k] + (1.f - a.beta1) * g;
+        vv[k] = a.beta2 * vv[k] + (1.f - a.beta2) * g * g;
+        wv[k] -= a.lr * (mv[k] / bc1) / (sqrtf(vv[k] / bc2) + a.eps);
+      }
+      reinterpret_cast<float4*>(a.m)[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
+      reinterpret_cast<float4*>(a.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) wv[k] -= a.lr * (gv[k] + a.weight_decay * wv[k]);
+    }
+    reinterpret_cast<float4*>(a.master)[i] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+    if (sh) {
+      uint2 o;
+      o.x = pack_bf16x2(wv[0], wv[1]);
+      o.y = pack_bf16x2(wv[2], wv[3]);
+      reinterpret_cast<uint2*>(sh)[i] = o;
+    }
+    if (a.zero_grad)
+      reinterpret_cast<float4*>(const_cast<float*>(a.grad))[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t i = nv * 4 + tid; i < a.n; i += stride) {
+    float w = a.master[i];
+    float g = a.grad[i] + a.weight_decay * w;
+    if (kAdam) {
+      const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
+      const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+      a.m[i] = m; a.v[i] = v;
+      w -= a.lr * (m / bc1) / (sqrtf(v / bc2) + a.eps);
+    } else {
+      w -= a.lr * g;
+    }
+    a.master[i] = w;
+    if (sh) sh[i] = __float2bfloat16(w);
+    if (a.zero_grad) const_cast<float*>(a.grad)[i] = 0.f;
+  }
+}
+
+}  // namespace
+
+#define BFLC_LAUNCH_1D(kernel, nvec, ...)                       \
+  do {                                                          \
+    kernel<<<grid_for(nvec), kBlock, 0, s>>>(__VA_ARGS__);      \
+    note_launch();                                              \
+    return cudaGetLastError();                                  \
+  } while (0)
+
+cudaError_t cast_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t s) {
+  BFLC_LAUNCH_1D(k_cast_f32_bf16, n / 8 + 1, src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+}
+cudaError_t cast_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t s) {
+  BFLC_LAUNCH_1D(k_cast_bf16_f32, n, reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+}
+cudaError_t cast_u8_to_bf16(const uint8_t* src, void* dst, int64_t n, float scale,
+                            cudaStream_t s) {
+  BFLC_LAUNCH_1D(k_cast_u8_bf16, n / 16 + 1, src, reinterpret_cast<__nv_bfloat16*>(dst), n, scale);
+}
+cudaError_t quantize_fp8(const void* src_bf16, uint8_t* dst, int64_t n, float inv_scale,
+                         cudaStream_t s) {
+  BFLC_LAUNCH_1D(k_quant_fp8, n / 8 + 1, reinterpret_cast<const __nv_bfloat16*>(src_bf16), dst, n,
+                 inv_scale);
+}
+cudaError_t amax_bf16(const void* src, int64_t n, float* amax_out, cudaStream_t s) {
+  BFLC_LAUNCH_1D(k_amax_bf16, n, reinterpret_cast<const __nv_bfloat16*>(src), n, amax_out);
+}
+cudaError_t fill_f32(float* dst, int64_t n, float v, cudaStream_t s) {
+  BFLC_LAUNCH_1D(k_fill, n, dst, n, v);
+}
+cudaError_t add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStream_t s) {
+  BFLC_LAUNCH_1D(k_add_bf16, n / 8 + 1, reinterpret_cast<const __nv_bfloat16*>(a),
+                 reinterpret_cast<const __nv_bfloat16*>(b), reinterpret_cast<__nv_bfloat16*>(out),
+                 n);
+}
+cudaError_t sgd_step(const OptimArgs& a, cudaStream_t s) {
+  BFLC_LAUNCH_1D(k_optim<false>, a.n / 4 + 1, a);
+}
+cudaError_t adam_step(const OptimArgs& a, cudaStream_t s) {
+  if (!a.m || !a.v) return cudaErrorInvalidValue;
+  BFLC_LAUNCH_1D(k_optim<true>, a.n / 4 + 1, a);
+}
+
+}  // namespace bflc

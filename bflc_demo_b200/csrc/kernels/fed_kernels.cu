@@ -1,0 +1,468 @@
+// The three communication-bound steps of a committee-consensus round as sm_100a kernels
+// that talk to peer GPUs themselves (ld/st/atom on peer-mapped HBM over NVLink 5 /
+// NVSwitch, optional NVLS multimem stores) -- no NCCL call on these paths.
+//
+//   fed_plan_round          X2  QueryState        -> local read of the HBM ledger page
+//   fed_upload              X4  UploadLocalUpdate -> publish + release flag on every peer
+//   (validation GEMM)       X5  QueryAllUpdates   -> TMA pulls of peers' weights (gemm_sm100.cu)
+//   fed_consensus_aggregate X6  UploadScores      -> score row pushed to every replica
+//                           X7  Aggregate         -> in-kernel median/top-K + FedAvg over P2P
+//                           X3  QueryGlobalModel  -> result written straight into the next
+//                                                    round's training buffers
+// (X-numbers: SURVEY.md 2.7b; reference semantics: CommitteePrecompiled.cpp:168-456.)
+//
+// Synchronisation is by monotonically increasing, epoch-tagged 32-bit flags written with
+// st.release.sys and polled with ld.acquire.sys; nothing is ever reset, so there is no
+// reuse race when committee membership changes between rounds.
+#include <cuda_bf16.h>
+
+#include "bflc_kernels.h"
+#include "consensus_math.hpp"
+#include "sm100_ptx.cuh"
+
+namespace bflc {
+
+namespace {
+
+constexpr int kFedThreads = 256;
+
+template <typename T>
+__device__ __forceinline__ T* at(char* base, long long off) {
+  return reinterpret_cast<T*>(base + off);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// ------------------------------------------------------------------ plan
+struct PlanLayers {
+  PlanLayer l[kMaxPlanLayers];
+  int n;
+  int steps_per_round;
+};
+
+__global__ void k_plan(FedArgs f, PlanLayers layers) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  char* me = f.peers.base[f.rank];
+  const RoundState* st = at<RoundState>(me, f.lay.state_off);
+  RoundPlan* plan = at<RoundPlan>(me, f.lay.plan_off);
+  uint32_t* flags = at<uint32_t>(me, f.lay.flags_off);
+  const uint32_t epoch = st->epoch;
+  const uint32_t par = epoch & 1u;
+  // Buffers of parity `par` were last read by peers while aggregating epoch - 2.
+  if (epoch >= 2) {
+    for (int r = 0; r < f.n_ranks; ++r) ptx::wait_flag_ge(flags + FLAG_DONE + r, epoch - 1);
+  }
+  plan->is_trainer = (st->role[f.rank] & ROLE_TRAINER) ? 1 : 0;
+  plan->is_comm = (st->role[f.rank] & ROLE_COMM) ? 1 : 0;
+  plan->parity = par;
+  int n_cand = 0;
+  for (int r = 0; r < f.n_ranks; ++r)
+    if (st->role[r] & ROLE_TRAINER) plan->cand_rank[n_cand++] = r;
+  plan->n_cand = n_cand;
+  for (int l = 0; l < layers.n; ++l) {
+    GemmDynamic& d = plan->dyn[l];
+    d.active_batches = plan->is_comm ? n_cand : 0;
+    d.wait_value = epoch + 1;
+    for (int z = 0; z < kMaxRanks; ++z) {
+      const int t = z < n_cand ? plan->cand_rank[z] : 0;
+      // tensor-map table is laid out [layer][parity][rank]
+      d.map_index[z] = (l * 2 + static_cast<int>(par)) * kMaxRanks + t;
+      d.bias[z] = layers.l[l].use_bias
+                      ? at<float>(f.peers.base[t], f.lay.upload_master_off[par]) +
+                            layers.l[l].bias_off
+                      : nullptr;
+      d.wait_flag[z] = flags + FLAG_TRAINED + t;
+    }
+  }
+  for (int z = 0; z < kMaxRanks; ++z) plan->correct[z] = 0;
+  plan->loss_sum = 0.f;
+  plan->train_correct = 0;
+  plan->upload_blocks_done = 0;
+  plan->consensus_blocks_done = 0;
+  plan->digest_acc = 0ull;
+  plan->opt_step = plan->opt_total;
+  if (plan->is_trainer) plan->opt_total += layers.steps_per_round;
+}
+
+// ------------------------------------------------------------------ upload
+__global__ void __launch_bounds__(kFedThreads)
+k_upload(FedArgs f, int n_samples, int n_loss_terms, int byz_mode, float byz_scale) {
+  char* me = f.peers.base[f.rank];
+  const RoundState* st = at<RoundState>(me, f.lay.state_off);
+  RoundPlan* plan = at<RoundPlan>(me, f.lay.plan_off);
+  if (!(st->role[f.rank] & ROLE_TRAINER)) return;
+  const uint32_t epoch = st->epoch;
+  const uint32_t par = epoch & 1u;
+  const float4* wm = at<const float4>(me, f.lay.work_master_off);
+  const float4* gm = at<const float4>(me, f.lay.global_off);
+  float4* um = at<float4>(me, f.lay.upload_master_off[par]);
+  uint2* us = at<uint2>(me, f.lay.upload_shadow_off[par]);
+  const long long nv = f.lay.n_params / 4;
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = tid; i < nv; i += stride) {
+    float4 w = wm[i];
+    if (byz_mode == 1) {
+      // Byzantine client: upload global - scale * (honest step) instead of the honest model
+      const float4 g = gm[i];
+      w.x = g.x - byz_scale * (w.x - g.x);
+      w.y = g.y - byz_scale * (w.y - g.y);
+      w.z = g.z - byz_scale * (w.z - g.z);
+      w.w = g.w - byz_scale * (w.w - g.w);
+    }
+    um[i] = w;
+    us[i] = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
+  }
+  // publish: all blocks' writes -> system scope, last block raises the flags
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(&plan->upload_blocks_done, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  if (threadIdx.x < f.n_ranks) {
+    const int r = threadIdx.x;
+    UploadMeta* meta = at<UploadMeta>(f.peers.base[r], f.lay.meta_off) + par * kMaxRanks + f.rank;
+    UploadMeta m;
+    m.n_samples = static_cast<uint32_t>(n_samples);
+    m.avg_cost = plan->loss_sum / static_cast<float>(n_loss_terms > 0 ? n_loss_terms : 1);
+    *meta = m;
+    __threadfence_system();
+    ptx::st_release_sys(at<uint32_t>(f.peers.base[r], f.lay.flags_off) + FLAG_TRAINED + f.rank,
+                        epoch + 1);
+  }
+}
+
+// --------------------------------------------------------------- consensus
+struct ConsShared {
+  ConsensusIn<kMaxRanks> in;
+  ConsensusOut<kMaxRanks> out;
+  int sel_rank[kMaxRanks];
+  float sel_w[kMaxRanks];
+  int n_sel;
+};
+
+__device__ __forceinline__ unsigned long long digest_term(float v, long long idx) {
+  // order-independent (sum of per-element terms) so any reduction schedule gives the same
+  // digest; odd multiplier keeps every bit of the float significant.
+  return static_cast<unsigned long long>(__float_as_uint(v)) *
+         (static_cast<unsigned long long>(2 * idx + 1) * 0x9E3779B97F4A7C15ull);
+}
+
+__global__ void __launch_bounds__(kFedThreads)
+k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc) {
+  __shared__ ConsShared sh;
+  __shared__ bool last;
+  char* me = f.peers.base[f.rank];
+  RoundState* st = at<RoundState>(me, f.lay.state_off);
+  RoundPlan* plan = at<RoundPlan>(me, f.lay.plan_off);
+  uint32_t* flags = at<uint32_t>(me, f.lay.flags_off);
+  const uint32_t epoch = st->epoch;
+  const uint32_t par = epoch & 1u;
+  const int n = f.n_ranks;
+  const bool i_am_comm = (st->role[f.rank] & ROLE_COMM) != 0;
+
+  // (a) committee: push my score row into every replica's ledger page, then release.
+  if (blockIdx.x == 0 && i_am_comm) {
+    if (threadIdx.x < n) {
+      const int r = threadIdx.x;  // destination replica
+      float* row = at<float>(f.peers.base[r], f.lay.scores_off) +
+                   (par * kMaxRanks + f.rank) * kMaxRanks;
+      for (int z = 0; z < plan->n_cand; ++z)
+        row[plan->cand_rank[z]] =
+            static_cast<float>(plan->correct[z]) / static_cast<float>(n_val > 0 ? n_val : 1);
+      __threadfence_system();
+      ptx::st_release_sys(at<uint32_t>(f.peers.base[r], f.lay.flags_off) + FLAG_SCORED + f.rank,
+                          epoch + 1);
+    }
+  }
+
+  // (b) every block: wait for all committee rows and all trainer uploads (local polls)
+  if (threadIdx.x < n) {
+    const int r = threadIdx.x;
+    if (st->role[r] & ROLE_COMM) ptx::wait_flag_ge(flags + FLAG_SCORED + r, epoch + 1);
+    if (st->role[r] & ROLE_TRAINER) ptx::wait_flag_ge(flags + FLAG_TRAINED + r, epoch + 1);
+  }
+  __syncthreads();
+
+  // (c) consensus math, redundantly per block (tiny), identical on every rank
+  if (threadIdx.x == 0) {
+    ConsensusIn<kMaxRanks>& in = sh.in;
+    in.n_ranks = n;
+    in.n_comm = static_cast<int>(st->n_comm);
+    in.n_aggregate = static_cast<int>(st->n_aggregate);
+    in.weight_by_score = weight_by_score;
+    const float* rows = at<float>(me, f.lay.scores_off) + par * kMaxRanks * kMaxRanks;
+    const UploadMeta* meta = at<UploadMeta>(me, f.lay.meta_off) + par * kMaxRanks;
+    for (int r = 0; r < kMaxRanks; ++r) {
+      in.role[r] = r < n ? st->role[r] : 0u;
+      in.admitted[r] = (r < n && (st->role[r] & ROLE_TRAINER)) ? 1 : 0;
+      in.n_samples[r] = r < n ? ptx::ld_relaxed_sys(&meta[r].n_samples) : 0u;
+      in.avg_cost[r] =
+          r < n ? __uint_as_float(ptx::ld_relaxed_sys(reinterpret_cast<const uint32_t*>(&meta[r].avg_cost)))
+                : 0.f;
+      for (int t = 0; t < kMaxRanks; ++t) {
+        const bool ok = r < n && t < n && (st->role[r] & ROLE_COMM) && (st->role[t] & ROLE_TRAINER);
+        in.scored[r][t] = ok ? 1 : 0;
+        in.score[r][t] =
+            ok ? __uint_as_float(ptx::ld_relaxed_sys(
+                     reinterpret_cast<const uint32_t*>(rows + r * kMaxRanks + t)))
+               : 0.f;
+      }
+    }
+    run_consensus<kMaxRanks>(in, sh.out);
+    int k = 0;
+    for (int r = 0; r < n; ++r)  // ascending rank = the fixed reduction order
+      if (sh.out.selected[r]) {
+        sh.sel_rank[k] = r;
+        sh.sel_w[k] = sh.out.weight[r];
+        ++k;
+      }
+    sh.n_sel = k;
+  }
+  __syncthreads();
+
+  // (d) FedAvg: new_global = sum_k w_k * upload_k   (reference C:373-414, with
+  //     delta = (w_old - w_new)/lr this is exactly global -= lr * weighted-mean(delta)).
+  const int n_sel = sh.n_sel;
+  const float4* src[kMaxRanks];
+  float w[kMaxRanks];
+#pragma unroll
+  for (int k = 0; k < kMaxRanks; ++k) {
+    const int r = k < n_sel ? sh.sel_rank[k] : f.rank;
+    src[k] = at<const float4>(f.peers.base[r], f.lay.upload_master_off[par]);
+    w[k] = k < n_sel ? sh.sel_w[k] : 0.f;
+  }
+  const long long nv = f.lay.n_params / 4;
+  long long lo = 0, hi = nv;
+  if (two_shot) {  // each rank reduces only its own slice, then publishes it to every peer
+    const long long per = (nv + n - 1) / n;
+    lo = per * f.rank;
+    hi = lo + per < nv ? lo + per : nv;
+    if (lo > nv) lo = nv;
+  }
+  float4* g_f32 = at<float4>(me, f.lay.global_off);
+  uint2* g_b16 = at<uint2>(me, f.lay.global_shadow_off);
+  float4* w_f32 = at<float4>(me, f.lay.work_master_off);
+  uint2* w_b16 = at<uint2>(me, f.lay.work_shadow_off);
+  const bool mc = two_shot && use_mc && f.peers.mc_base != nullptr;
+  unsigned long long dig = 0ull;
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = lo + tid; i < hi; i += stride) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n_sel == 0) {
+      acc = g_f32[i];  // nothing admitted: the global model is unchanged
+    } else {
+      float4 v[kMaxRanks];
+#pragma unroll
+      for (int k = 0; k < kMaxRanks; ++k)
+        if (k < n_sel) v[k] = ptx::ld_nc_f4(src[k] + i);  // all peer loads in flight first
+#pragma unroll
+      for (int k = 0; k < kMaxRanks; ++k)
+        if (k < n_sel) {
+          acc.x = fmaf(w[k], v[k].x, acc.x);
+          acc.y = fmaf(w[k], v[k].y, acc.y);
+          acc.z = fmaf(w[k], v[k].z, acc.z);
+          acc.w = fmaf(w[k], v[k].w, acc.w);
+        }
+    }
+    dig += digest_term(acc.x, 4 * i) + digest_term(acc.y, 4 * i + 1) +
+           digest_term(acc.z, 4 * i + 2) + digest_term(acc.w, 4 * i + 3);
+    const uint2 b = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+    if (!two_shot) {
+      g_f32[i] = acc; g_b16[i] = b; w_f32[i] = acc; w_b16[i] = b;
+    } else if (mc) {
+      // one NVLS store per destination buffer lands in all replicas
+      ptx::multimem_st_f4(at<float4>(f.peers.mc_base, f.lay.global_off) + i, acc);
+      ptx::multimem_st_f4(at<float4>(f.peers.mc_base, f.lay.work_master_off) + i, acc);
+      // bf16 copies: two uint2 make one 16-byte multimem store only when paired; keep P2P
+      for (int r = 0; r < n; ++r) {
+        at<uint2>(f.peers.base[r], f.lay.global_shadow_off)[i] = b;
+        at<uint2>(f.peers.base[r], f.lay.work_shadow_off)[i] = b;
+      }
+    } else {
+      for (int r = 0; r < n; ++r) {
+        char* pb = f.peers.base[r];
+        at<float4>(pb, f.lay.global_off)[i] = acc;
+        at<uint2>(pb, f.lay.global_shadow_off)[i] = b;
+        at<float4>(pb, f.lay.work_master_off)[i] = acc;
+        at<uint2>(pb, f.lay.work_shadow_off)[i] = b;
+      }
+    }
+  }
+  // block-level digest reduce
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) dig += __shfl_xor_sync(0xffffffffu, dig, off);
+  if ((threadIdx.x & 31) == 0 && dig) atomicAdd(&plan->digest_acc, dig);
+
+  // (e) last block: commit the round
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(&plan->consensus_blocks_done, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+
+  if (two_shot) {
+    // publish my slice (+ its digest) and wait for everyone else's
+    if (threadIdx.x < n) {
+      const int r = threadIdx.x;
+      unsigned long long* slot =
+          reinterpret_cast<unsigned long long*>(at<float>(f.peers.base[r], f.lay.scores_off) +
+                                                2 * kMaxRanks * kMaxRanks) +
+          par * kMaxRanks + f.rank;
+      *slot = *reinterpret_cast<volatile unsigned long long*>(&plan->digest_acc);
+      __threadfence_system();
+      ptx::st_release_sys(at<uint32_t>(f.peers.base[r], f.lay.flags_off) + FLAG_SLICE + f.rank,
+                          epoch + 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < n) ptx::wait_flag_ge(flags + FLAG_SLICE + threadIdx.x, epoch + 1);
+    __syncthreads();
+  }
+
+  if (threadIdx.x == 0) {
+    unsigned long long digest = 0ull;
+    if (two_shot) {
+      const unsigned long long* slots =
+          reinterpret_cast<const unsigned long long*>(at<float>(me, f.lay.scores_off) +
+                                                      2 * kMaxRanks * kMaxRanks) +
+          par * kMaxRanks;
+      for (int r = 0; r < n; ++r)
+        digest += *reinterpret_cast<const volatile unsigned long long*>(slots + r);
+    } else {
+      digest = *reinterpret_cast<volatile unsigned long long*>(&plan->digest_acc);
+    }
+    const ConsensusIn<kMaxRanks>& in = sh.in;
+    const ConsensusOut<kMaxRanks>& out = sh.out;
+    // append the block record (drained by the host ledger)
+    BlockRecord* rec =
+        at<BlockRecord>(me, f.lay.ring_off) + (epoch % static_cast<uint32_t>(f.lay.ring_slots));
+    rec->epoch = epoch;
+    rec->n_ranks = static_cast<uint32_t>(n);
+    rec->n_comm = st->n_comm;
+    rec->n_aggregate = st->n_aggregate;
+    uint32_t adm = 0, sel = 0;
+    for (int r = 0; r < kMaxRanks; ++r) {
+      rec->role_before[r] = in.role[r];
+      rec->role_after[r] = r < n ? out.role_after[r] : 0u;
+      uint32_t m = 0;
+      for (int t = 0; t < kMaxRanks; ++t) {
+        rec->score_rows[r][t] = in.score[r][t];
+        if (in.scored[r][t]) m |= 1u << t;
+      }
+      rec->scored_mask[r] = m;
+      rec->median[r] = r < n ? out.median[r] : 0.f;
+      rec->n_samples[r] = in.n_samples[r];
+      rec->avg_cost[r] = in.avg_cost[r];
+      rec->weight[r] = r < n ? out.weight[r] : 0.f;
+      if (in.admitted[r]) adm |= 1u << r;
+      if (r < n && out.selected[r]) sel |= 1u << r;
+    }
+    rec->admitted_mask = adm;
+    rec->selected_mask = sel;
+    rec->global_loss = out.global_loss;
+    rec->weight_by_score = static_cast<uint32_t>(weight_by_score);
+    rec->model_digest = digest;
+    __threadfence();
+    rec->seq = epoch + 1;
+    // advance the ledger page: re-election, epoch++
+    for (int r = 0; r < n; ++r) {
+      st->role[r] = out.role_after[r];
+      st->last_median[r] = out.median[r];
+    }
+    st->selected_mask = sel;
+    st->global_loss = out.global_loss;
+    st->model_digest = digest;
+    st->blocks_appended = st->blocks_appended + 1;
+    st->epoch = epoch + 1;
+    __threadfence_system();
+  }
+  __syncthreads();
+  // tell every peer that this rank no longer reads epoch `epoch` buffers
+  if (threadIdx.x < n)
+    ptx::st_release_sys(
+        at<uint32_t>(f.peers.base[threadIdx.x], f.lay.flags_off) + FLAG_DONE + f.rank, epoch + 1);
+}
+
+__global__ void k_p2p_read(const float4* __restrict__ src, float4* __restrict__ dst, long long n) {
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = tid; i + 3 * stride < n; i += 4 * stride) {
+    const float4 a = ptx::ld_nc_f4(src + i);
+    const float4 b = ptx::ld_nc_f4(src + i + stride);
+    const float4 c = ptx::ld_nc_f4(src + i + 2 * stride);
+    const float4 d = ptx::ld_nc_f4(src + i + 3 * stride);
+    dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+  }
+}
+__global__ void k_mc_store(float4* mc_dst, const float4* __restrict__ src, long long n) {
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = tid; i < n; i += stride) ptx::multimem_st_f4(mc_dst + i, src[i]);
+}
+
+int fed_grid(long long n_params) {
+  long long blocks = (n_params / 4 + kFedThreads * 4 - 1) / (kFedThreads * 4);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace
+
+cudaError_t fed_plan_round(const FedArgs& f, const PlanLayer* layers, int n_layers,
+                           int steps_per_round, cudaStream_t s) {
+  if (n_layers > kMaxPlanLayers) return cudaErrorInvalidValue;
+  PlanLayers pl{};
+  pl.n = n_layers;
+  pl.steps_per_round = steps_per_round;
+  for (int i = 0; i < n_layers; ++i) pl.l[i] = layers[i];
+  k_plan<<<1, 32, 0, s>>>(f, pl);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t fed_upload(const FedArgs& f, int n_samples, int n_loss_terms, int byz_mode,
+                       float byz_scale, cudaStream_t s) {
+  k_upload<<<fed_grid(f.lay.n_params), kFedThreads, 0, s>>>(f, n_samples, n_loss_terms, byz_mode,
+                                                            byz_scale);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t fed_consensus_aggregate(const FedArgs& f, int n_val, int weight_by_score,
+                                    int two_shot, int use_multicast, cudaStream_t s) {
+  const long long work = two_shot ? f.lay.n_params / (f.n_ranks > 0 ? f.n_ranks : 1)
+                                  : f.lay.n_params;
+  k_consensus<<<fed_grid(work), kFedThreads, 0, s>>>(f, n_val, weight_by_score, two_shot,
+                                                     use_multicast);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t p2p_read_probe(const float4* peer_src, float4* local_dst, int64_t n_vec,
+                           cudaStream_t s) {
+  k_p2p_read<<<148 * 4, 256, 0, s>>>(peer_src, local_dst, n_vec);
+  note_launch();
+  return cudaGetLastError();
+}
+cudaError_t mc_store_probe(float4* mc_dst, const float4* local_src, int64_t n_vec,
+                           cudaStream_t s) {
+  k_mc_store<<<148 * 4, 256, 0, s>>>(mc_dst, local_src, n_vec);
+  note_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace bflc
