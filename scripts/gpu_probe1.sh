@@ -6,6 +6,7 @@ LOG=gpurun_out/probe1.log
 : > $LOG
 nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv >> $LOG 2>&1
 export BFLC_NO_AUTOBUILD=1
+export PYTHONPATH=$PWD:$PYTHONPATH
 run() { echo "=== $1" >> $LOG; timeout 120 python scripts/gemm_case.py $1 >> $LOG 2>&1; echo "exit=$?" >> $LOG; }
 run kk_128_64_64
 run kk_256_256_512
