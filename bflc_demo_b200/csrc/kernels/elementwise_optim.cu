@@ -53,7 +53,8 @@ __global__ void k_cast_bf16_f32(const __nv_bfloat16* __restrict__ src, float* __
 }
 
 __global__ void k_cast_u8_bf16(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                               int64_t n, float scale) {
+                               int64_t n, float scale, const int* pred) {
+  if (pred != nullptr && *pred == 0) return;
   const int64_t nv = n / 16;
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -215,7 +216,8 @@ cudaError_t cast_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_
 }
 cudaError_t cast_u8_to_bf16(const uint8_t* src, void* dst, int64_t n, float scale,
                             cudaStream_t s) {
-  BFLC_LAUNCH_1D(k_cast_u8_bf16, n / 16 + 1, src, reinterpret_cast<__nv_bfloat16*>(dst), n, scale);
+  BFLC_LAUNCH_1D(k_cast_u8_bf16, n / 16 + 1, src, reinterpret_cast<__nv_bfloat16*>(dst), n, scale,
+                 current_predicate());
 }
 cudaError_t quantize_fp8(const void* src_bf16, uint8_t* dst, int64_t n, float inv_scale,
                          cudaStream_t s) {

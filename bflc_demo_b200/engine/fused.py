@@ -1,0 +1,292 @@
+"""The B200-native round engine: one process per GPU, every rank replays the SAME captured
+CUDA graph each round; who trains and who validates is decided by data in the HBM ledger
+page (role bits), not by launch topology.
+
+  round graph (all ranks):
+    fed_plan_round                     QueryState       (local read of the ledger page)
+    cast u8 -> bf16                    this round's inputs
+    [trainer]  steps x 6 kernels       local training   (models/mlp.py)
+    fed_upload                         UploadLocalUpdate (publish + release flags on peers)
+    [committee] 2 grouped GEMMs        QueryAllUpdates + validation: TMA pulls every
+                                       trainer's weights out of its HBM over NVLink
+    fed_consensus_aggregate            UploadScores + Aggregate + QueryGlobalModel
+
+No NCCL call and no host synchronisation inside a round.  The host C++ ledger drains the
+device block ring afterwards and re-executes every election (``Ledger.AppendDeviceRound``).
+
+Reference call stacks replaced: SURVEY.md 3.2 (trainer round) and 3.3 (committee round),
+i.e. python-sdk/main.py:103-169, 196-228 and CommitteePrecompiled.cpp:215-456.
+"""
+from __future__ import annotations
+
+import struct
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .._native import C, ledger as _ledger
+from ..config import FLConfig
+from ..data.synthetic import Shard
+from ..models.flat import ParamSpec
+from ..models.mlp import FlatMLP, mlp_spec
+from ..ops import gemm as G
+from ..parallel.layout import HeapLayout
+from ..parallel.symm import SymmetricHeap
+
+ROLE_TRAINER, ROLE_COMM = 1, 2
+
+
+def initial_roles(cfg: FLConfig) -> List[int]:
+    """Genesis committee (reference: first COMM_COUNT entries in unordered_map order,
+    C:176-182 -- arbitrary but deterministic): lowest ids, or a seeded permutation."""
+    n = cfg.clients
+    if cfg.solo:
+        return [ROLE_TRAINER | ROLE_COMM] * n
+    ids = list(range(n))
+    if cfg.seed:
+        rng = np.random.default_rng(cfg.seed)
+        rng.shuffle(ids)
+    roles = [ROLE_TRAINER] * n
+    for i in ids[: cfg.committee_size]:
+        roles[i] = ROLE_COMM
+    return roles
+
+
+class FusedEngine:
+    def __init__(self, cfg: FLConfig, shard: Shard, *, rank: int = 0, world: int = 1,
+                 device: int = 0, group=None, in_dim: Optional[int] = None):
+        assert cfg.clients == world, "one client per rank"
+        assert world <= 8
+        self.cfg, self.rank, self.world, self.device = cfg, rank, world, device
+        self.group = group
+        torch.cuda.set_device(device)
+        self.dev = torch.device("cuda", device)
+        self.mod = C()
+        sz = self.mod.struct_sizes()
+        self.sz = sz
+
+        # ---- model + heap --------------------------------------------------------------
+        x0 = shard.x.reshape(len(shard), -1)
+        self.in_dim = in_dim or x0.shape[1]
+        self.spec: ParamSpec = mlp_spec(self.in_dim, cfg.hidden, shard.n_classes)
+        self.n_params = self.spec.total
+        self.S = (len(shard) // cfg.batch_size) * cfg.batch_size  # drop remainder (M:141)
+        self.steps = (self.S // cfg.batch_size) * cfg.local_epochs
+        self.n_val = min(cfg.val_samples or len(shard), len(shard))
+        self.layout = HeapLayout(self.n_params, cfg.ring_slots)
+        self.heap = SymmetricHeap(self.layout.total_bytes, rank=rank, world=world, device=device,
+                                  group=group, want_multicast=cfg.use_multicast)
+        self.fed = self.layout.fed_dict(rank, world, self.heap.peer_ptrs, self.heap.mc_ptr)
+        o = self.layout.offsets
+        P = self.n_params
+        hv = self.heap.view
+        self.work_master = hv(o["work_master"], [P], torch.float32)
+        self.work_shadow = hv(o["work_shadow"], [P], torch.bfloat16)
+        self.global_master = hv(o["global"], [P], torch.float32)
+        self.global_shadow = hv(o["global_shadow"], [P], torch.bfloat16)
+        self.state_bytes = hv(o["state"], [sz["RoundState"]], torch.uint8)
+        self.plan_bytes = hv(o["plan"], [sz["RoundPlan"]], torch.uint8)
+        self.ring_bytes = hv(o["ring"], [cfg.ring_slots * sz["BlockRecord"]], torch.uint8)
+        plan_ptr = self.heap.local_ptr + o["plan"]
+        self.plan_ptr = plan_ptr
+        self.is_trainer_ptr = plan_ptr + sz["plan_is_trainer_off"]
+        self.is_comm_ptr = plan_ptr + sz["plan_is_comm_off"]
+        self.loss_sum = hv(o["plan"] + sz["plan_loss_sum_off"], [1], torch.float32)
+        self.train_correct = hv(o["plan"] + sz["plan_train_correct_off"], [1], torch.int32)
+        self.val_correct = hv(o["plan"] + sz["plan_correct_off"], [sz["kMaxRanks"]], torch.int32)
+        self.grad = torch.zeros(P, device=self.dev, dtype=torch.float32)
+
+        # genesis model: identical on every rank
+        init = torch.empty(P, dtype=torch.float32)
+        self.spec.init_(init, seed=cfg.seed + 1234)
+        for t in (self.work_master, self.global_master):
+            t.copy_(init)
+        for t in (self.work_shadow, self.global_shadow):
+            t.copy_(init.to(torch.bfloat16))
+
+        # ledger page + host chain
+        roles = initial_roles(cfg)
+        st = self.mod.state_init_bytes(world, cfg.committee_size, cfg.aggregate_count, roles)
+        self.state_bytes.copy_(torch.frombuffer(bytearray(st), dtype=torch.uint8))
+        self.host_ledger = _ledger().Ledger(cfg.to_ledger_config(P))
+        self.host_ledger.Bootstrap(roles)
+        self.drained = 0
+
+        # ---- model trainer over heap views -----------------------------------------------
+        self.trainer = FlatMLP(self.spec, self.work_master, self.work_shadow, self.grad,
+                               cfg.batch_size, optimizer=cfg.optimizer, lr=cfg.learning_rate,
+                               loss_sum=self.loss_sum, correct=self.train_correct,
+                               step_dev_ptr=plan_ptr + sz["plan_opt_step_off"])
+
+        # ---- data ------------------------------------------------------------------------
+        self.x_u8 = torch.empty(len(shard), self.in_dim, device=self.dev, dtype=torch.uint8)
+        self.x_bf = torch.empty(len(shard), self.in_dim, device=self.dev, dtype=torch.bfloat16)
+        self.y = torch.empty(len(shard), device=self.dev, dtype=torch.int32)
+        self.host_x = x0.contiguous().pin_memory()
+        self.host_y = shard.y.to(torch.int32).contiguous().pin_memory()
+        self.x_u8.copy_(self.host_x)
+        self.y.copy_(self.host_y)
+        self.h_val = torch.empty(world, self.n_val, cfg.hidden, device=self.dev, dtype=torch.bfloat16)
+        self.out_host = torch.empty(sz["RoundState"], dtype=torch.uint8).pin_memory()
+        self.rec_host = torch.empty(sz["BlockRecord"], dtype=torch.uint8).pin_memory()
+
+        # ---- validation tensor-map table [layer][parity][rank] (peers' upload shadows) ----
+        K = sz["kMaxRanks"]
+        blob = bytearray(2 * 2 * K * 128)
+        e1, e2 = self.spec.by_name["w1"], self.spec.by_name["w2"]
+        for layer, (e, kind) in enumerate(((e1, G.EPI_GENERIC), (e2, G.EPI_ARGMAX))):
+            for par in range(2):
+                for r in range(world):
+                    base = self.heap.peer_ptrs[r] + o[f"upload_shadow{par}"] + e.offset * 2
+                    m = self.mod.gemm_b_map(base, e.shape[0], e.shape[1], e.shape[1], False, False, kind)
+                    idx = (layer * 2 + par) * K + r
+                    blob[idx * 128:(idx + 1) * 128] = m
+        self.b_maps = torch.frombuffer(blob, dtype=torch.uint8).to(self.dev)
+        self.plan_layers = [(self.spec.offset("b1"), True), (self.spec.offset("b2"), True)]
+        self.dyn_ptr = [plan_ptr + sz["plan_dyn_off"] + i * sz["GemmDynamic"] for i in range(2)]
+        self.two_shot = cfg.two_shot if cfg.two_shot is not None else (P * 4 > (64 << 20) and world > 1)
+        self.byz = 1 if rank in cfg.byzantine_ranks else 0
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.launches_per_round = 0
+        if world > 1:
+            dist.barrier(group=group)
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ one round
+    def _enqueue_round(self):
+        m, cfg = self.mod, self.cfg
+        n0 = m.launch_count()
+        m.fed_plan_round(self.fed, self.plan_layers, self.steps)
+        m.cast_u8_to_bf16(self.x_u8, self.x_bf, 1.0 / 255.0)
+        # local training, predicated on the trainer role bit
+        m.set_predicate(self.is_trainer_ptr)
+        self.trainer.train_epoch(self.x_bf, self.y, self.steps)
+        m.set_predicate(0)
+        m.fed_upload(self.fed, self.S, self.steps * cfg.batch_size, self.byz, cfg.byzantine_scale)
+        # committee validation: grouped GEMMs whose B operands are the trainers' uploads
+        xv, yv = self.x_bf[: self.n_val], self.y[: self.n_val]
+        H = cfg.hidden
+        m.gemm(xv, self.work_shadow, self.h_val, self.n_val, H, self.in_dim, self.world,
+               self.in_dim, self.in_dim, 0, 0, False, False, False, G.EPI_GENERIC, 1, H,
+               self.n_val * H, 1.0, None, G.ACT_RELU, None, None, 0, None, 1, False, None, 0, 1.0,
+               None, None, self.b_maps, None, 0, 0, 0, 0, self.dyn_ptr[0])
+        m.gemm(self.h_val, self.work_shadow, None, self.n_val, self.spec.by_name["w2"].shape[0], H,
+               self.world, H, H, self.n_val * H, 0, False, False, False, G.EPI_ARGMAX, 1, 0, 0, 1.0,
+               None, 0, None, None, 0, None, 1, False, yv, 0, 1.0, None, self.val_correct,
+               self.b_maps, None, 0, 0, 0, 0, self.dyn_ptr[1])
+        m.fed_consensus_aggregate(self.fed, self.n_val, cfg.weight_by_score, self.two_shot,
+                                  cfg.use_multicast and self.heap.has_multicast)
+        self.launches_per_round = int(m.launch_count() - n0)
+
+    def capture(self):
+        """Warm up eagerly (lazy kernel attribute setup), then capture one round."""
+        with torch.cuda.stream(self.stream):
+            self._enqueue_round()
+        self.stream.synchronize()
+        if not self.cfg.cuda_graph:
+            return
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.stream):
+            self._enqueue_round()
+        self.graph = g
+
+    def run_round(self):
+        if self.graph is not None:
+            with torch.cuda.stream(self.stream):
+                self.graph.replay()
+        else:
+            with torch.cuda.stream(self.stream):
+                self._enqueue_round()
+
+    def run_round_e2e(self, host_x: Optional[torch.Tensor] = None,
+                      host_y: Optional[torch.Tensor] = None) -> dict:
+        """Public per-round call: stage this round's inputs from pinned host memory, run the
+        round, read the result (ledger page) back to the host."""
+        hx = self.host_x if host_x is None else host_x
+        hy = self.host_y if host_y is None else host_y
+        with torch.cuda.stream(self.stream):
+            self.x_u8.copy_(hx, non_blocking=True)
+            self.y.copy_(hy, non_blocking=True)
+        self.run_round()
+        with torch.cuda.stream(self.stream):
+            self.out_host.copy_(self.state_bytes, non_blocking=True)
+        self.stream.synchronize()
+        return self.read_state(self.out_host)
+
+    @property
+    def h2d_bytes_per_round(self) -> int:
+        return self.host_x.numel() * self.host_x.element_size() + self.host_y.numel() * 4
+
+    @property
+    def d2h_bytes_per_round(self) -> int:
+        return self.out_host.numel()
+
+    # ------------------------------------------------------------------ host views
+    def read_state(self, buf: Optional[torch.Tensor] = None) -> dict:
+        b = bytes((self.state_bytes.cpu() if buf is None else buf).numpy())
+        epoch, n_ranks, n_comm, n_agg = struct.unpack_from("<4I", b, 0)
+        roles = list(struct.unpack_from("<8I", b, 16))[: self.world]
+        med = list(struct.unpack_from("<8f", b, 48))[: self.world]
+        sel, = struct.unpack_from("<I", b, 80)
+        loss, = struct.unpack_from("<f", b, self.sz["state_global_loss_off"])
+        digest, = struct.unpack_from("<Q", b, self.sz["state_digest_off"])
+        return dict(epoch=epoch, roles=roles, median=med, selected_mask=sel, global_loss=loss,
+                    model_digest=digest)
+
+    def drain_blocks(self) -> List[str]:
+        """Pull finished BlockRecords off the device ring into the host C++ ledger, which
+        re-executes each election.  Returns the list of mismatches ([] = replicas agree)."""
+        torch.cuda.synchronize()
+        st = self.read_state()
+        ring = bytes(self.ring_bytes.cpu().numpy())
+        rs = self.sz["BlockRecord"]
+        errs = []
+        K = 8
+        while self.drained < st["epoch"]:
+            e = self.drained
+            off = (e % self.cfg.ring_slots) * rs
+            rec = ring[off:off + rs]
+            f = struct.unpack_from("<4I", rec, 0)
+            p = 16
+            role_before = list(struct.unpack_from("<8I", rec, p)); p += 32
+            role_after = list(struct.unpack_from("<8I", rec, p)); p += 32
+            rows = [list(struct.unpack_from("<8f", rec, p + 32 * c)) for c in range(K)]; p += 256
+            scored = list(struct.unpack_from("<8I", rec, p)); p += 32
+            p += 32  # median
+            n_samples = list(struct.unpack_from("<8I", rec, p)); p += 32
+            avg_cost = list(struct.unpack_from("<8f", rec, p)); p += 32
+            p += 32  # weight
+            adm, sel = struct.unpack_from("<2I", rec, p); p += 8
+            gl, = struct.unpack_from("<f", rec, p); p += 4
+            wbs, = struct.unpack_from("<I", rec, p); p += 4
+            digest, = struct.unpack_from("<Q", rec, p); p += 8
+            seq, = struct.unpack_from("<I", rec, p)
+            if f[0] != e or seq != e + 1:
+                errs.append(f"ring slot for epoch {e} holds epoch {f[0]} seq {seq}")
+                break
+            n = self.world
+            msg = self.host_ledger.AppendDeviceRound(dict(
+                epoch=e, role_before=role_before[:n], role_after=role_after[:n],
+                score_rows=[r[:n] for r in rows[:n]], scored_mask=scored[:n],
+                n_samples=n_samples[:n], avg_cost=avg_cost[:n], admitted_mask=adm,
+                selected_mask=sel, global_loss=gl, model_digest=digest, weight_by_score=wbs))
+            if msg:
+                errs.append(f"epoch {e}: {msg}")
+                break
+            self.drained += 1
+        return errs
+
+    def global_model(self) -> Dict[str, torch.Tensor]:
+        return {k: v.clone() for k, v in self.spec.views(self.global_master).items()}
+
+    def evaluate(self, shard: Shard) -> float:
+        """Sponsor-style test accuracy of the current global model (M:285-306)."""
+        x = shard.x.reshape(len(shard), -1).to(self.dev)
+        xb = torch.empty(x.shape, device=self.dev, dtype=torch.bfloat16)
+        self.mod.cast_u8_to_bf16(x.contiguous(), xb, 1.0 / 255.0)
+        cnt = self.trainer.accuracy_counts(xb, shard.y.to(self.dev, torch.int32),
+                                           shadow=self.global_shadow, master=self.global_master)
+        return float(cnt.item()) / len(shard)

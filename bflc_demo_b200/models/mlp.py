@@ -1,0 +1,123 @@
+"""2-layer MLP 784 -> hidden -> 62 (BASELINE.json configs #1/#2), hand-scheduled: every
+forward/backward GEMM is the tcgen05 kernel with a fused epilogue, the whole training step
+is six launches and is CUDA-graph capturable (no host syncs, no allocations).
+
+Reference parity: the reference's model is the degenerate single-layer case
+``pred = x @ W + b`` with softmax-cross-entropy and plain SGD, batch 100, one pass per
+round (python-sdk/main.py:109-148); ``SoftmaxRegression`` below is exactly that model.
+
+  step(x, y):
+    1. h       = relu(x @ W1^T + b1)                    GEMM  (bias+ReLU epilogue)
+    2. dlogits = softmax(h @ W2^T + b2) - onehot(y)     GEMM  (xent epilogue: loss, #correct,
+                                                              db2 column sums)
+    3. dW2     = dlogits^T @ h                          GEMM  (MN-major A and B, split-K)
+    4. dh      = (dlogits @ W2) * (h > 0)               GEMM  (MN-major B, ReLU-bwd mask, db1)
+    5. dW1     = dh^T @ x                               GEMM  (MN-major A and B, split-K)
+    6. SGD / Adam over the flat buffer (+ bf16 shadow refresh + grad zeroing)
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .._native import C
+from ..ops import gemm as G
+from .flat import ParamSpec
+
+
+def mlp_spec(in_dim: int = 784, hidden: int = 256, n_classes: int = 62) -> ParamSpec:
+    return ParamSpec([("w1", (hidden, in_dim)), ("b1", (hidden,)),
+                      ("w2", (n_classes, hidden)), ("b2", (n_classes,))])
+
+
+def softmax_regression_spec(n_features: int = 5, n_class: int = 2) -> ParamSpec:
+    """The reference model: W[n_features, n_class] stored [out, in] + b (H:7-8, M:113-120)."""
+    return ParamSpec([("w", (n_class, n_features)), ("b", (n_class,))])
+
+
+class FlatMLP:
+    """Fused-kernel trainer over flat buffers.  ``master``/``shadow``/``grad`` are 1-D tensors
+    of ``spec.total`` elements (fp32 / bf16 / fp32); they may live in the symmetric heap."""
+
+    def __init__(self, spec: ParamSpec, master: torch.Tensor, shadow: torch.Tensor,
+                 grad: torch.Tensor, batch: int, *, optimizer: str = "sgd", lr: float = 1e-3,
+                 loss_sum: Optional[torch.Tensor] = None, correct: Optional[torch.Tensor] = None,
+                 step_dev_ptr: int = 0):
+        self.spec, self.master, self.shadow, self.grad = spec, master, shadow, grad
+        self.p = spec.views(master)
+        self.s = spec.views(shadow)
+        self.g = spec.views(grad)
+        self.hidden, self.in_dim = spec.by_name["w1"].shape
+        self.n_classes = spec.by_name["w2"].shape[0]
+        self.batch = batch
+        dev = master.device
+        self.h = torch.empty(batch, self.hidden, device=dev, dtype=torch.bfloat16)
+        self.dh = torch.empty(batch, self.hidden, device=dev, dtype=torch.bfloat16)
+        self.ncp = (self.n_classes + 7) // 8 * 8          # dlogits row stride (TMA alignment)
+        self.dlogits = torch.zeros(batch, self.ncp, device=dev, dtype=torch.bfloat16)
+        self.loss_sum = loss_sum if loss_sum is not None else torch.zeros(1, device=dev)
+        self.correct = correct if correct is not None else torch.zeros(1, device=dev, dtype=torch.int32)
+        self.optimizer, self.lr = optimizer, lr
+        self.m = torch.zeros_like(master) if optimizer == "adam" else None
+        self.v = torch.zeros_like(master) if optimizer == "adam" else None
+        self.step_dev_ptr = step_dev_ptr
+        k_blocks = (batch + 63) // 64
+        self.split_k = max(1, min(8, k_blocks))
+
+    # -------------------------------------------------------------- training
+    def forward_backward(self, x: torch.Tensor, y: torch.Tensor) -> None:
+        """x: bf16 [batch, in_dim], y: int32 [batch].  Accumulates grads into ``grad``."""
+        B = x.shape[0]
+        s, g = self.s, self.g
+        h = self.h[:B]
+        G.gemm(x, s["w1"], out=h, bias=self.p["b1"], act=G.ACT_RELU)
+        dl = self.dlogits[:B]
+        G.gemm_xent(h, s["w2"], y, n_classes=self.n_classes, bias=self.p["b2"], dlogits=dl,
+                    grad_scale=1.0 / B, loss_sum=self.loss_sum, correct=self.correct,
+                    colsum=g["b2"])
+        # dW2[c, j] = sum_b dlogits[b, c] h[b, j]
+        G.gemm(dl[:, :self.n_classes], h, out=g["w2"], a_mn=True, b_mn=True,
+               split_k=self.split_k)
+        # dh = (dlogits @ W2) * relu'(h);  db1 = colsum(dh)
+        G.gemm(dl[:, :self.n_classes], s["w2"], out=self.dh[:B], b_mn=True, aux_in=h, act_bwd=1,
+               colsum=g["b1"])
+        # dW1 = dh^T @ x
+        G.gemm(self.dh[:B], x, out=g["w1"], a_mn=True, b_mn=True, split_k=self.split_k)
+
+    def optimizer_step(self, step_in_round: int = 1) -> None:
+        C().optim_step(self.optimizer == "adam", self.master, self.grad, self.shadow, self.m,
+                       self.v, self.lr, 0.0, 0.9, 0.999, 1e-8, step_in_round, self.step_dev_ptr, 0,
+                       True)
+
+    def train_epoch(self, X: torch.Tensor, Y: torch.Tensor, steps: int) -> None:
+        """One pass: ``steps`` mini-batches of ``batch`` rows, remainder dropped (M:141-148)."""
+        B = self.batch
+        for i in range(steps):
+            self.forward_backward(X[i * B:(i + 1) * B], Y[i * B:(i + 1) * B])
+            self.optimizer_step(i + 1)
+
+    # ------------------------------------------------------------ evaluation
+    def accuracy_counts(self, X: torch.Tensor, Y: torch.Tensor, shadow: Optional[torch.Tensor] = None,
+                        master: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """#correct of (optionally another model's) weights on (X, Y) -> int32 [1] (K6)."""
+        s = self.spec.views(shadow) if shadow is not None else self.s
+        p = self.spec.views(master) if master is not None else self.p
+        n = X.shape[0]
+        h = torch.empty(n, self.hidden, device=X.device, dtype=torch.bfloat16)
+        G.gemm(X, s["w1"], out=h, bias=p["b1"], act=G.ACT_RELU)
+        cnt = torch.zeros(1, device=X.device, dtype=torch.int32)
+        G.gemm_argmax_acc(h, s["w2"], Y, cnt, n_classes=self.n_classes, bias=p["b2"])
+        return cnt
+
+
+def torch_reference_step(params: dict, x: torch.Tensor, y: torch.Tensor, lr: float):
+    """Plain fp32 PyTorch version of one SGD step of the same MLP (numerics oracle)."""
+    w1, b1, w2, b2 = (params[k].detach().clone().requires_grad_(True) for k in ("w1", "b1", "w2", "b2"))
+    h = torch.relu(x.float() @ w1.t() + b1)
+    logits = h @ w2.t() + b2
+    loss = torch.nn.functional.cross_entropy(logits, y.long())
+    loss.backward()
+    new = {k: (t - lr * t.grad).detach() for k, t in (("w1", w1), ("b1", b1), ("w2", w2), ("b2", b2))}
+    grads = {"w1": w1.grad, "b1": b1.grad, "w2": w2.grad, "b2": b2.grad}
+    return loss.detach(), new, grads
