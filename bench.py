@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Headline benchmark: federated rounds/sec of the committee-consensus protocol on a 2-layer
+MLP over synthetic FEMNIST (BASELINE.json), one client per B200.
+
+  python bench.py --gpus N --steps K --warmup W            # fused engine (the product)
+  python bench.py --impl nccl ...                          # OUR NCCL+cuBLAS baseline arm
+  python bench.py --impl reference ...                     # the unmodified reference (cannot
+                                                           # be installed here -> "unavailable")
+
+A "step" is one full federated round: every trainer runs one local pass (steps x batch
+samples, forward+backward+optimizer), uploads; every committee member validates every
+candidate on its own shard; median / top-K / sample-weighted FedAvg; re-election.
+Per-GPU work is fixed as N grows (weak scaling).
+
+Timing: W >= 3 untimed rounds, then K rounds each bracketed by CUDA events on the launching
+stream; between timed rounds a 256 MiB buffer is written to flush the 126 MB L2 and the
+ranks re-synchronise (barrier + cudaDeviceSynchronize) OUTSIDE the timed interval; the
+per-round time is the max over ranks and the reported time is the sum over the K rounds.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+REFERENCE_UNAVAILABLE = (
+    "reference is a FISCO-BCOS precompiled contract + TF1 client with no setup.py/pyproject and "
+    "no GPU code; pip install of /root/reference fails (not a Python project) and it needs "
+    "FISCO-BCOS 2.x, nlohmann/json, the FISCO python-sdk, solc and TensorFlow, none available "
+    "offline (see DESIGN.md 'Reference arm')")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="fused", choices=["fused", "nccl", "reference"])
+    ap.add_argument("--hidden", type=int, default=256)
+    ap.add_argument("--samples", type=int, default=4096, help="samples per client per round")
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--optimizer", default="sgd")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--broadcast", action="store_true", help="nccl arm: literal average+broadcast")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.proc = None
+        self.path = f"/tmp/bflc_clocks_{os.getpid()}.csv"
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        print(json.dumps({"impl": "reference", "unavailable": REFERENCE_UNAVAILABLE}))
+        return 0
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: re-launch ourselves under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
+               os.environ.get("MASTER_PORT", "29531"), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n = max(world, 1)
+    assert n == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    import torch
+    import torch.distributed as dist
+
+    from bflc_demo_b200.config import FLConfig
+    from bflc_demo_b200.data.synthetic import femnist_like
+
+    torch.cuda.set_device(local_rank)
+    group = None
+    if n > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = FLConfig.for_world(n, model="mlp", dataset="femnist", hidden=args.hidden,
+                             batch_size=args.batch, samples_per_client=args.samples,
+                             optimizer=args.optimizer, learning_rate=0.05, dtype="bf16",
+                             cuda_graph=not args.no_graph, ring_slots=1024)
+    shard = femnist_like(n, args.samples, seed=7, only=rank)[0]
+    # a small pool of distinct pinned input sets the e2e loop cycles through
+    pool = [femnist_like(n, args.samples, seed=100 + i, only=rank)[0] for i in range(3)]
+
+    if args.impl == "fused":
+        from bflc_demo_b200.engine.fused import FusedEngine
+        eng = FusedEngine(cfg, shard, rank=rank, world=n, device=local_rank, group=group)
+    else:
+        from bflc_demo_b200.engine.nccl_baseline import NcclBaselineEngine
+        eng = NcclBaselineEngine(cfg, shard, rank=rank, world=n, device=local_rank, group=group,
+                                 broadcast=args.broadcast)
+    eng.capture()
+    pool_x = [p.x.reshape(len(p), -1).contiguous().pin_memory() for p in pool]
+    ydt = eng.host_y.dtype
+    pool_y = [p.y.to(ydt).contiguous().pin_memory() for p in pool]
+
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if n > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, k):
+        """k iterations of fn(i), each device-timed on the engine stream; L2 flush + barrier
+        between iterations, outside the timed interval.  -> list of per-iteration ms."""
+        out = []
+        for i in range(k):
+            if flush is not None:
+                flush.fill_(i & 0xFF)
+            sync_all()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(eng.stream):
+                e0.record()
+            fn(i)
+            with torch.cuda.stream(eng.stream):
+                e1.record()
+            e1.synchronize()
+            out.append(e0.elapsed_time(e1))
+        return out
+
+    def round_only(i):
+        eng.run_round()
+
+    def round_e2e(i):
+        eng.run_round_e2e(pool_x[i % len(pool_x)], pool_y[i % len(pool_y)])
+
+    W = max(args.warmup, 3)
+    for i in range(W):
+        round_e2e(i)
+    sync_all()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = _launch_count()
+    drain = (lambda: eng.drain_blocks()) if args.impl == "fused" else (lambda: [])
+    ledger_errs = list(drain())
+    t_dev = timed(round_only, args.steps)
+    ledger_errs += drain()
+    launches = _launch_count() - launches0
+    t_e2e = timed(round_e2e, args.steps)
+    ledger_errs += drain()
+    # back-to-back (no flush, no per-round barrier) for context
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(eng.stream):
+        e0.record()
+    for i in range(args.steps):
+        eng.run_round()
+    with torch.cuda.stream(eng.stream):
+        e1.record()
+    e1.synchronize()
+    pipelined_ms = e0.elapsed_time(e1) / args.steps
+    sync_all()
+    clocks = sampler.stop() if sampler else None
+
+    def reduce_max(vals):
+        t = torch.tensor(vals, device="cuda", dtype=torch.float64)
+        if n > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    dev_ms = sum(reduce_max(t_dev))
+    e2e_ms = sum(reduce_max(t_e2e))
+    pipe_ms = reduce_max([pipelined_ms])[0]
+
+    # consistency: the fused engine's host ledger re-executes every device election
+    extra = {}
+    if args.impl == "fused":
+        errs = ledger_errs + eng.drain_blocks()
+        st = eng.read_state()
+        extra = {"ledger_blocks": eng.host_ledger.n_blocks(), "ledger_mismatches": errs[:2],
+                 "chain_ok": eng.host_ledger.verify_chain(), "epoch": st["epoch"],
+                 "global_loss": st["global_loss"], "symm": eng.heap.describe(),
+                 "launches_per_round": eng.launches_per_round}
+        if n > 1:
+            digs = [None] * n
+            dist.all_gather_object(digs, st["model_digest"])
+            extra["replicas_bit_identical"] = len(set(digs)) == 1
+        gl = eng.launches_per_round * args.steps
+    else:
+        extra = {"epoch": eng.epoch, "global_loss": eng.global_loss}
+        gl = int(launches)
+
+    if rank == 0:
+        K = args.steps
+        trainers = cfg.n_trainers
+        line = {
+            "metric": "federated_rounds_per_sec",
+            "value": K / (dev_ms / 1e3),
+            "unit": "rounds/s",
+            "n_gpus": n, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic (class-conditional FEMNIST-like 28x28 uint8, 62 classes; random-init weights)",
+            "impl": args.impl if args.impl == "fused" else "nccl-baseline (ours, not a reference build)",
+            "config": {"model": f"mlp_784x{args.hidden}x62", "global_batch": trainers * eng.S,
+                       "seq_len": None, "parallelism": f"fed-dp{n} (committee {cfg.committee_size}, "
+                       f"trainers {trainers}, top-{cfg.aggregate_count})",
+                       "samples_per_client_per_round": eng.S, "local_batch": args.batch,
+                       "local_steps": eng.steps, "val_samples": eng.n_val,
+                       "optimizer": args.optimizer, "cuda_graph": not args.no_graph,
+                       "l2": "flushed between timed rounds (256 MiB write, outside the timed interval)"
+                             if flush is not None else "not flushed",
+                       "pipelined_ms_per_step_no_flush": pipe_ms},
+            "clocks": clocks,
+            "e2e": {"value": K / (e2e_ms / 1e3), "unit": "rounds/s", "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": eng.h2d_bytes_per_round,
+                    "d2h_bytes_per_step": eng.d2h_bytes_per_round},
+            "gpu_launches": gl,
+            "extra": extra,
+        }
+        print(json.dumps(line))
+    if n > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def _launch_count() -> int:
+    from bflc_demo_b200._native import C
+    return int(C().launch_count())
+
+
+if __name__ == "__main__":
+    sys.exit(main())
