@@ -107,6 +107,22 @@ class FLConfig:
         return cls(model="softmax", dataset="occupancy").validate()
 
     @classmethod
+    def reference_scaled(cls, clients: int, **kw) -> "FLConfig":
+        """The reference's 20/4/10/6 proportions scaled to another client count."""
+        if clients == 20:
+            base = dict()
+        else:
+            comm = max(1, clients // 5)
+            trainers = clients - comm
+            needed = max(comm, (trainers * 10 + 15) // 16)
+            agg = max(1, min(needed, max(comm, (needed * 6 + 9) // 10)))
+            base = dict(clients=clients, committee_size=comm, needed_updates=needed,
+                        aggregate_count=agg)
+        base.update(dict(model="softmax", dataset="occupancy"))
+        base.update(kw)
+        return cls(**base).validate()
+
+    @classmethod
     def for_world(cls, n: int, **kw) -> "FLConfig":
         """The benchmark family of BASELINE.json: n clients, committee 3 at n=8, 2 at n=4,
         1 at n=2, solo at n=1; every trainer's update is needed; top-(trainers-1) aggregated
