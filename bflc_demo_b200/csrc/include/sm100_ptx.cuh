@@ -248,6 +248,12 @@ __device__ __forceinline__ float4 ld_f4_relaxed(const float4* p) {
                : "memory");
   return v;
 }
+// 16-byte vector reduction (sm_90+): one L2 atomic transaction for four floats
+__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
 // NVLS multicast: one store lands in every replica bound to the multicast object
 __device__ __forceinline__ void multimem_st_f4(float4* mc_ptr, float4 v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_ptr),

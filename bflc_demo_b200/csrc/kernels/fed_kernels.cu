@@ -116,11 +116,12 @@ k_upload(FedArgs f, int n_samples, int n_loss_terms, int byz_mode, float byz_sca
     um[i] = w;
     us[i] = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
   }
-  // publish: all blocks' writes -> system scope, last block raises the flags
-  __threadfence_system();
+  // publish: the block barrier orders every thread's writes before thread 0's system-scope
+  // fence (release patterns are cumulative), the last block to arrive raises the flags
   __syncthreads();
   __shared__ bool last;
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned done = atomicAdd(&plan->upload_blocks_done, 1u);
     last = (done == gridDim.x - 1);
   }
@@ -304,9 +305,9 @@ k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc)
   if ((threadIdx.x & 31) == 0 && dig) atomicAdd(&plan->digest_acc, dig);
 
   // (e) last block: commit the round
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned done = atomicAdd(&plan->consensus_blocks_done, 1u);
     last = (done == gridDim.x - 1);
   }

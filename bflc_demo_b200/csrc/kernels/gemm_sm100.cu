@@ -273,9 +273,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (row_ok) {
           if (p.split_k > 1) {
             float* d = reinterpret_cast<float*>(p.d) + row_off + nc;
+            if (full && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full || nc + j < p.N) atomicAdd(d + j, v[j]);
+              for (int j = 0; j < 32; j += 4)
+                ptx::red_add_f32x4(d + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full || nc + j < p.N) atomicAdd(d + j, v[j]);
+            }
           } else if (p.d_dtype == 0) {
             float* d = reinterpret_cast<float*>(p.d) + row_off + nc;
             const bool vec = full && ((reinterpret_cast<uintptr_t>(d) & 15) == 0);

@@ -98,7 +98,7 @@ class NcclBaselineEngine:
             torch._foreach_add_([w["w1"], w["b1"], w["w2"], w["b2"]], [gw1, gb1, gw2, gb2], alpha=-lr)
         if self.byz:
             self.work.copy_(self.global_w - self.cfg.byzantine_scale * (self.work - self.global_w))
-        self.my_meta[0] = float(self.S)
+        self.my_meta[0:1].fill_(float(self.S))
         self.my_meta[1:2] = self.loss_acc / float(self.steps * B)
 
     def _val_pass(self):

@@ -100,6 +100,15 @@ def main():
             res[f"{M}x{N}x{K}"] = {"ours_ms": ms, "ours_tflops": 2 * M * N * K / ms / 1e9,
                                    "cublas_ms": ms_t, "cublas_tflops": 2 * M * N * K / ms_t / 1e9}
         out["perf"] = res
+    elif case == "perf_small":
+        a, b = mk(512, 784), mk(256, 784)
+        bias = torch.randn(256, device=dev)
+        o = torch.empty(512, 256, device=dev, dtype=torch.bfloat16)
+        for _ in range(36): G.gemm(a, b, out=o, bias=bias, act=G.ACT_RELU)
+    elif case == "perf_big":
+        a, b = mk(8192, 8192), mk(8192, 8192)
+        o = torch.empty(8192, 8192, device=dev, dtype=torch.bfloat16)
+        for _ in range(5): G.gemm(a, b, out=o)
     elif case == "elem":
         n = 100003
         x = torch.randn(n, device=dev)

@@ -162,5 +162,5 @@ def test_mlp_training_step_matches_torch():
     assert abs(tr.loss_sum.item() / B - loss_ref.item()) < 2e-3
     tr.optimizer_step(1)
     for k, v in spec.views(master).items():
-        assert rel(v, new_ref[k]) < 1e-3, k
+        assert rel(v, new_ref[k]) < 3e-3, k
     assert bool((grad == 0).all())
