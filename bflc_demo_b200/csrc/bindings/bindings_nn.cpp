@@ -1,0 +1,112 @@
+// Bindings for the non-GEMM NN kernels (csrc/kernels/nn_kernels.cu).
+#include <ATen/cuda/CUDAContext.h>
+#include <torch/extension.h>
+
+#include <optional>
+
+#include "bflc_kernels.h"
+
+namespace py = pybind11;
+using OptT = std::optional<at::Tensor>;
+
+namespace {
+void check(cudaError_t e, const char* what) {
+  TORCH_CHECK(e == cudaSuccess, "bflc::", what, " failed: ", cudaGetErrorString(e));
+}
+cudaStream_t st() { return at::cuda::getCurrentCUDAStream().stream(); }
+template <typename T>
+T* optp(const OptT& t) { return t.has_value() ? reinterpret_cast<T*>(t->data_ptr()) : nullptr; }
+}  // namespace
+
+void bind_nn(py::module_& m) {
+  m.def("im2col", [](at::Tensor x, at::Tensor col, int N, int C, int H, int W, int KH, int KW,
+                     int stride, int pad, int OH, int OW) {
+    check(bflc::im2col_bf16(x.data_ptr(), col.data_ptr(), N, C, H, W, KH, KW, stride, pad, OH, OW,
+                            col.stride(0), st()), "im2col");
+  });
+  m.def("col2im", [](at::Tensor col, at::Tensor dx, int N, int C, int H, int W, int KH, int KW,
+                     int stride, int pad, int OH, int OW) {
+    check(bflc::col2im_bf16(col.data_ptr(), dx.data_ptr(), N, C, H, W, KH, KW, stride, pad, OH, OW,
+                            col.stride(0), st()), "col2im");
+  });
+  m.def("maxpool_fwd", [](at::Tensor x, at::Tensor y, at::Tensor idx, int N, int C, int H, int W,
+                          int k, int stride, int pad, int OH, int OW) {
+    check(bflc::maxpool2d_fwd(x.data_ptr(), y.data_ptr(), idx.data_ptr<int32_t>(), N, C, H, W, k,
+                              stride, pad, OH, OW, st()), "maxpool_fwd");
+  });
+  m.def("maxpool_bwd", [](at::Tensor dy, at::Tensor idx, at::Tensor dx_f32, int64_t per_out,
+                          int64_t per_in) {
+    check(bflc::maxpool2d_bwd(dy.data_ptr(), idx.data_ptr<int32_t>(), dx_f32.data_ptr<float>(),
+                              dy.numel(), per_out, per_in, st()), "maxpool_bwd");
+  });
+  m.def("avgpool_fwd", [](at::Tensor x, at::Tensor y, int N, int HW, int C) {
+    check(bflc::avgpool_global_fwd(x.data_ptr(), y.data_ptr(), N, HW, C, st()), "avgpool_fwd");
+  });
+  m.def("avgpool_bwd", [](at::Tensor dy, at::Tensor dx, int N, int HW, int C) {
+    check(bflc::avgpool_global_bwd(dy.data_ptr(), dx.data_ptr(), N, HW, C, st()), "avgpool_bwd");
+  });
+  m.def("batchnorm_fwd", [](at::Tensor x, at::Tensor y, at::Tensor gamma, at::Tensor beta,
+                            at::Tensor mean, at::Tensor rstd, const OptT& run_mean,
+                            const OptT& run_var, int64_t rows, int C, double eps, double momentum,
+                            bool training, bool relu, const OptT& residual) {
+    check(bflc::batchnorm_fwd(x.data_ptr(), y.data_ptr(), gamma.data_ptr<float>(),
+                              beta.data_ptr<float>(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                              optp<float>(run_mean), optp<float>(run_var), rows, C, (float)eps,
+                              (float)momentum, training, relu,
+                              residual.has_value() ? residual->data_ptr() : nullptr, st()),
+          "batchnorm_fwd");
+  });
+  m.def("batchnorm_bwd", [](at::Tensor dy, at::Tensor x, at::Tensor y, at::Tensor gamma,
+                            at::Tensor mean, at::Tensor rstd, at::Tensor dx, at::Tensor dgamma,
+                            at::Tensor dbeta, const OptT& dres, int64_t rows, int C, bool relu) {
+    check(bflc::batchnorm_bwd(dy.data_ptr(), x.data_ptr(), y.data_ptr(), gamma.data_ptr<float>(),
+                              mean.data_ptr<float>(), rstd.data_ptr<float>(), dx.data_ptr(),
+                              dgamma.data_ptr<float>(), dbeta.data_ptr<float>(),
+                              dres.has_value() ? dres->data_ptr() : nullptr, rows, C, relu, st()),
+          "batchnorm_bwd");
+  });
+  m.def("layernorm_fwd", [](at::Tensor x, at::Tensor y, at::Tensor gamma, at::Tensor beta,
+                            at::Tensor mean, at::Tensor rstd, int64_t rows, int C, double eps) {
+    check(bflc::layernorm_fwd(x.data_ptr(), nullptr, y.data_ptr(), gamma.data_ptr<float>(),
+                              beta.data_ptr<float>(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                              rows, C, (float)eps, st()), "layernorm_fwd");
+  });
+  m.def("layernorm_bwd", [](at::Tensor dy, at::Tensor x, at::Tensor gamma, at::Tensor mean,
+                            at::Tensor rstd, at::Tensor dx, at::Tensor dgamma, at::Tensor dbeta,
+                            int64_t rows, int C) {
+    check(bflc::layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr<float>(),
+                              mean.data_ptr<float>(), rstd.data_ptr<float>(), dx.data_ptr(),
+                              dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), rows, C, st()),
+          "layernorm_bwd");
+  });
+  m.def("softmax_fwd", [](at::Tensor x, at::Tensor y, int64_t rows, int cols, double scale) {
+    check(bflc::softmax_rows_fwd(x.data_ptr(), y.data_ptr(), rows, cols, (float)scale, st()),
+          "softmax_fwd");
+  });
+  m.def("softmax_bwd", [](at::Tensor dy, at::Tensor y, at::Tensor dx, int64_t rows, int cols,
+                          double scale) {
+    check(bflc::softmax_rows_bwd(dy.data_ptr(), y.data_ptr(), dx.data_ptr(), rows, cols,
+                                 (float)scale, st()), "softmax_bwd");
+  });
+  m.def("embedding_fwd", [](at::Tensor ids, at::Tensor table, const OptT& pos, at::Tensor out,
+                            int64_t rows, int seq, int C) {
+    check(bflc::embedding_fwd(ids.data_ptr<int32_t>(), table.data_ptr(),
+                              pos.has_value() ? pos->data_ptr() : nullptr, out.data_ptr(), rows, seq,
+                              C, st()), "embedding_fwd");
+  });
+  m.def("embedding_bwd", [](at::Tensor ids, at::Tensor dy, at::Tensor dtable, const OptT& dpos,
+                            int64_t rows, int seq, int C) {
+    check(bflc::embedding_bwd(ids.data_ptr<int32_t>(), dy.data_ptr(), dtable.data_ptr<float>(),
+                              optp<float>(dpos), rows, seq, C, st()), "embedding_bwd");
+  });
+  m.def("act_bwd_colsum", [](at::Tensor dy, const OptT& aux, const OptT& dz, const OptT& colsum,
+                             int64_t rows, int C, int mode) {
+    check(bflc::act_bwd_colsum(dy.data_ptr(), aux.has_value() ? aux->data_ptr() : nullptr,
+                               dz.has_value() ? dz->data_ptr() : nullptr, optp<float>(colsum), rows,
+                               C, mode, st()), "act_bwd_colsum");
+  });
+  m.def("transpose_0213", [](at::Tensor x, at::Tensor y, int d0, int d1, int d2, int d3) {
+    check(bflc::transpose_0213_bf16(x.data_ptr(), y.data_ptr(), d0, d1, d2, d3, st()),
+          "transpose_0213");
+  });
+}

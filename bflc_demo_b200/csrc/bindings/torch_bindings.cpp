@@ -90,6 +90,7 @@ py::bytes gemm_b_map(int64_t ptr, int64_t N, int64_t K, int64_t ldb, bool b_mn, 
 }  // namespace
 
 void bind_extra(py::module_& m);  // defined in bindings_extra.cpp
+void bind_nn(py::module_& m);     // defined in bindings_nn.cpp
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "bflc_demo_b200 native kernels (sm_100a)";
@@ -111,4 +112,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
   m.def("launch_count", [] { return bflc::launch_count(); });
   bind_extra(m);
+  bind_nn(m);
 }

@@ -117,8 +117,8 @@ cudaError_t col2im_bf16(const void* col, void* dx, int N, int C, int H, int W, i
                         int stride, int pad, int OH, int OW, int64_t ld_col, cudaStream_t s);
 cudaError_t maxpool2d_fwd(const void* x, void* y, int32_t* idx, int N, int C, int H, int W, int k,
                           int stride, int pad, int OH, int OW, cudaStream_t s);
-cudaError_t maxpool2d_bwd(const void* dy, const int32_t* idx, void* dx, int64_t n_out,
-                          int64_t n_in, cudaStream_t s);
+cudaError_t maxpool2d_bwd(const void* dy, const int32_t* idx, float* dx_f32, int64_t n_out,
+                          int64_t per_out, int64_t per_in, cudaStream_t s);
 cudaError_t avgpool_global_fwd(const void* x, void* y, int N, int HW, int C, cudaStream_t s);
 cudaError_t avgpool_global_bwd(const void* dy, void* dx, int N, int HW, int C, cudaStream_t s);
 // channels-last batch norm over [rows][C]; train mode computes batch statistics
@@ -145,6 +145,9 @@ cudaError_t embedding_fwd(const int32_t* ids, const void* table_bf16, const void
 cudaError_t embedding_bwd(const int32_t* ids, const void* dy, float* dtable, float* dpos,
                           int64_t rows, int seq, int C, cudaStream_t s);
 cudaError_t add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStream_t s);
+// dz = dy * act'(aux), colsum += column sums of dz (bias gradient); mode 0 none, 1 ReLU, 2 GELU
+cudaError_t act_bwd_colsum(const void* dy, const void* aux, void* dz, float* colsum, int64_t rows,
+                           int C, int mode, cudaStream_t s);
 cudaError_t transpose_0213_bf16(const void* x, void* y, int d0, int d1, int d2, int d3,
                                 cudaStream_t s);
 
@@ -287,6 +290,7 @@ cudaError_t fed_consensus_aggregate(const FedArgs& f, int n_val, int weight_by_s
 // thread-local predicate: kernels launched while it is set start with
 // `if (*pred == 0) return;` (role predication inside a captured graph)
 void set_predicate(const int* pred);
+void set_debug_times(long long* dev_buf8);  // GEMM phase clock stamps of CTA (0,0,0)
 const int* current_predicate();
 
 // stand-alone P2P / multicast bandwidth probes (profiles/, substrate smoke test)

@@ -44,6 +44,7 @@ struct KParams {
   const CUtensorMap* b_maps_dev;
   const GemmDynamic* dyn;
   const int* pred;
+  long long* dbg_times;  // optional [8] clock64 stamps written by CTA (0,0,0) (bring-up only)
   // epilogue
   void* d;
   int d_dtype;
@@ -119,6 +120,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (p.dyn != nullptr && static_cast<int>(blockIdx.z) / p.split_k >= p.dyn->active_batches)
     return;
 
+  const long long t_entry = clock64();
+  const bool dbg = p.dbg_times != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
@@ -150,6 +153,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) { p.dbg_times[0] = t_entry; p.dbg_times[1] = clock64(); }
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -188,6 +192,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             ptx::tma_load_3d(sb + b * (block_k * 128), mapB, &full_bar[s], n0 + b * block_k, k0,
                              cb2);
         }
+        if (dbg && i == 0) p.dbg_times[2] = clock64();
       }
     }
   } else if (warp == 1) {
@@ -200,6 +205,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t ph = (i / L::kStages) & 1;
         ptx::mbar_wait(&full_bar[s], ph);
         ptx::tc_fence_after_sync();
+        if (dbg && i == 0) p.dbg_times[3] = clock64();
         const uint32_t sa = ptx::smem_u32(smem + s * L::kStageBytes);
         const uint32_t sb = sa + kABytes;
 #pragma unroll
@@ -215,6 +221,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         ptx::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
       }
       ptx::umma_commit(accum_bar);  // accumulator complete
+      if (dbg) p.dbg_times[4] = clock64();
     }
   } else {
     // --------------------------------------------------------------- epilogue
@@ -223,6 +230,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool row_ok = row < p.M;
     ptx::mbar_wait(accum_bar, 0);
     ptx::tc_fence_after_sync();
+    if (dbg && warp == 2 && lane == 0) p.dbg_times[5] = clock64();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const bool have_acc = n_kb > 0;
 
@@ -430,12 +438,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
+    if (dbg && warp == 2 && lane == 0) p.dbg_times[6] = clock64();
     ptx::tc_fence_before_sync();
   }
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, BN);
+    if (dbg && lane == 0) p.dbg_times[7] = clock64();
   }
 }
 
@@ -516,6 +526,8 @@ cudaError_t launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& 
 static unsigned long long g_launches = 0;
 unsigned long long launch_count() { return g_launches; }
 void note_launch() { ++g_launches; }
+static thread_local long long* g_dbg_times = nullptr;
+void set_debug_times(long long* p) { g_dbg_times = p; }
 static thread_local const int* g_pred = nullptr;
 void set_predicate(const int* pred) { g_pred = pred; }
 const int* current_predicate() { return g_pred; }
@@ -566,6 +578,7 @@ cudaError_t gemm_sm100(const GemmProblem& p, cudaStream_t stream) {
   kp.b_maps_dev = p.b_maps_dev;
   kp.dyn = p.dyn;
   kp.pred = current_predicate();
+  kp.dbg_times = g_dbg_times;
   kp.d = p.epi.d;
   kp.d_dtype = static_cast<int>(p.epi.d_dtype);
   kp.ldd = p.epi.ldd;

@@ -1,0 +1,579 @@
+// Non-GEMM layers for the CNN / transformer model families (LeNet-5, ResNet-18, BERT-base):
+// im2col / col2im (convolutions run as tcgen05 GEMMs over the column matrix), pooling,
+// batch-norm, layer-norm, row softmax, embeddings, head transposes.  All tensors are bf16,
+// channels-last (NHWC) for images so a convolution's GEMM output IS the next layer's input;
+// statistics and parameter gradients are fp32.
+//
+// The reference has none of these (its only model is x@W+b, python-sdk/main.py:113-120);
+// they exist because BASELINE.json names LeNet-5 / ResNet-18 / BERT-base configs.
+#include <cuda_bf16.h>
+
+#include "bflc_kernels.h"
+
+namespace bflc {
+
+namespace {
+
+constexpr int kT = 256;
+typedef __nv_bfloat16 bf16;
+
+inline int blocks_for(int64_t n, int per = kT, int cap = 148 * 16) {
+  int64_t g = (n + per - 1) / per;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum broadcast to all threads (blockDim.x == kT)
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < kT / 32) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) {
+    t = warp_sum(t);
+    if (l == 0) sh[0] = t;
+  }
+  __syncthreads();
+  return sh[0];
+}
+
+// ------------------------------------------------------------------ im2col / col2im
+// x: [N, H, W, C] -> col: [N*OH*OW, ld_col], column index = (kh*KW + kw)*C + c
+__global__ void k_im2col(const bf16* __restrict__ x, bf16* __restrict__ col, int N, int C, int H,
+                         int W, int KH, int KW, int stride, int pad, int OH, int OW,
+                         long long ld_col) {
+  const long long kcols = static_cast<long long>(KH) * KW * C;
+  const long long total = static_cast<long long>(N) * OH * OW * kcols;
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += step) {
+    const long long row = i / kcols;
+    const int kc = static_cast<int>(i - row * kcols);
+    const int c = kc % C;
+    const int kw = (kc / C) % KW;
+    const int kh = kc / (C * KW);
+    const int ow = static_cast<int>(row % OW);
+    const int oh = static_cast<int>((row / OW) % OH);
+    const int n = static_cast<int>(row / (static_cast<long long>(OW) * OH));
+    const int ih = oh * stride - pad + kh, iw = ow * stride - pad + kw;
+    bf16 v = __float2bfloat16(0.f);
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+      v = x[((static_cast<long long>(n) * H + ih) * W + iw) * C + c];
+    col[row * ld_col + kc] = v;
+  }
+}
+
+// gather form of the transpose: each dx element sums the col entries it was copied to
+__global__ void k_col2im(const bf16* __restrict__ col, bf16* __restrict__ dx, int N, int C, int H,
+                         int W, int KH, int KW, int stride, int pad, int OH, int OW,
+                         long long ld_col) {
+  const long long total = static_cast<long long>(N) * H * W * C;
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += step) {
+    const int c = static_cast<int>(i % C);
+    const int w = static_cast<int>((i / C) % W);
+    const int h = static_cast<int>((i / (static_cast<long long>(C) * W)) % H);
+    const int n = static_cast<int>(i / (static_cast<long long>(C) * W * H));
+    float acc = 0.f;
+    for (int kh = 0; kh < KH; ++kh) {
+      const int t = h + pad - kh;
+      if (t < 0 || t % stride) continue;
+      const int oh = t / stride;
+      if (oh >= OH) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int u = w + pad - kw;
+        if (u < 0 || u % stride) continue;
+        const int ow = u / stride;
+        if (ow >= OW) continue;
+        const long long row = (static_cast<long long>(n) * OH + oh) * OW + ow;
+        acc += __bfloat162float(col[row * ld_col + (kh * KW + kw) * C + c]);
+      }
+    }
+    dx[i] = __float2bfloat16(acc);
+  }
+}
+
+// ------------------------------------------------------------------ pooling (NHWC)
+__global__ void k_maxpool_fwd(const bf16* __restrict__ x, bf16* __restrict__ y,
+                              int32_t* __restrict__ idx, int N, int C, int H, int W, int k,
+                              int stride, int pad, int OH, int OW) {
+  const long long total = static_cast<long long>(N) * OH * OW * C;
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += step) {
+    const int c = static_cast<int>(i % C);
+    const int ow = static_cast<int>((i / C) % OW);
+    const int oh = static_cast<int>((i / (static_cast<long long>(C) * OW)) % OH);
+    const int n = static_cast<int>(i / (static_cast<long long>(C) * OW * OH));
+    float best = -INFINITY;
+    int bi = -1;
+    for (int a = 0; a < k; ++a)
+      for (int b = 0; b < k; ++b) {
+        const int ih = oh * stride - pad + a, iw = ow * stride - pad + b;
+        if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+        const long long src = ((static_cast<long long>(n) * H + ih) * W + iw) * C + c;
+        const float v = __bfloat162float(x[src]);
+        if (v > best) { best = v; bi = static_cast<int>(src % (static_cast<long long>(H) * W * C)); }
+      }
+    y[i] = __float2bfloat16(best);
+    idx[i] = bi;  // offset inside sample n
+  }
+}
+// dx must be zeroed by the caller; windows may overlap (ResNet stem: k=3, stride=2)
+__global__ void k_maxpool_bwd(const bf16* __restrict__ dy, const int32_t* __restrict__ idx,
+                              float* __restrict__ dx_f32, long long n_out, long long per_out,
+                              long long per_in) {
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_out;
+       i += step) {
+    const long long n = i / per_out;
+    const int j = idx[i];
+    if (j >= 0) atomicAdd(dx_f32 + n * per_in + j, __bfloat162float(dy[i]));
+  }
+}
+
+__global__ void k_avgpool_fwd(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int HW,
+                              int C) {
+  const long long total = static_cast<long long>(N) * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long n = i / C;
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += __bfloat162float(x[(n * HW + p) * C + c]);
+    y[i] = __float2bfloat16(s / HW);
+  }
+}
+__global__ void k_avgpool_bwd(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int HW,
+                              int C) {
+  const long long total = static_cast<long long>(N) * HW * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long n = i / (static_cast<long long>(HW) * C);
+    dx[i] = __float2bfloat16(__bfloat162float(dy[n * C + c]) / HW);
+  }
+}
+
+// ------------------------------------------------------------------ batch norm [rows][C]
+// stats: each block owns a slab of rows and a tile of 32 channels x 8 row-lanes
+__global__ void k_bn_stats(const bf16* __restrict__ x, float* __restrict__ sum,
+                           float* __restrict__ sumsq, long long rows, int C) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane_r = threadIdx.x >> 5;  // 0..7
+  float s = 0.f, q = 0.f;
+  if (c < C) {
+    for (long long r = blockIdx.y * 8 + lane_r; r < rows; r += static_cast<long long>(gridDim.y) * 8) {
+      const float v = __bfloat162float(x[r * C + c]);
+      s += v; q += v * v;
+    }
+  }
+  __shared__ float shs[8][33], shq[8][33];
+  shs[lane_r][threadIdx.x & 31] = s;
+  shq[lane_r][threadIdx.x & 31] = q;
+  __syncthreads();
+  if (lane_r == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { s += shs[k][threadIdx.x & 31]; q += shq[k][threadIdx.x & 31]; }
+    atomicAdd(sum + c, s);
+    atomicAdd(sumsq + c, q);
+  }
+}
+__global__ void k_bn_finalize(float* mean, float* rstd, float* run_mean, float* run_var,
+                              long long rows, int C, float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float m = mean[c] / rows;
+  float var = rstd[c] / rows - m * m;
+  var = fmaxf(var, 0.f);
+  mean[c] = m;
+  rstd[c] = rsqrtf(var + eps);
+  if (run_mean) {
+    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m;
+    const float unb = rows > 1 ? var * rows / (rows - 1) : var;
+    run_var[c] = (1.f - momentum) * run_var[c] + momentum * unb;
+  }
+}
+__global__ void k_bn_apply(const bf16* __restrict__ x, bf16* __restrict__ y,
+                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                           const bf16* __restrict__ residual, long long total, int C, int relu) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    float v = (__bfloat162float(x[i]) - mean[c]) * rstd[c] * gamma[c] + beta[c];
+    if (residual) v += __bfloat162float(residual[i]);
+    if (relu) v = fmaxf(v, 0.f);
+    y[i] = __float2bfloat16(v);
+  }
+}
+// backward pass 1: dgamma = sum g*xhat, dbeta = sum g   (g = dy masked by relu)
+__global__ void k_bn_bwd_reduce(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                const bf16* __restrict__ y, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, float* __restrict__ dgamma,
+                                float* __restrict__ dbeta, long long rows, int C, int relu) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane_r = threadIdx.x >> 5;
+  float sg = 0.f, sb = 0.f;
+  if (c < C) {
+    const float m = mean[c], rs = rstd[c];
+    for (long long r = blockIdx.y * 8 + lane_r; r < rows; r += static_cast<long long>(gridDim.y) * 8) {
+      float g = __bfloat162float(dy[r * C + c]);
+      if (relu && !(__bfloat162float(y[r * C + c]) > 0.f)) g = 0.f;
+      sg += g * (__bfloat162float(x[r * C + c]) - m) * rs;
+      sb += g;
+    }
+  }
+  __shared__ float s1[8][33], s2[8][33];
+  s1[lane_r][threadIdx.x & 31] = sg;
+  s2[lane_r][threadIdx.x & 31] = sb;
+  __syncthreads();
+  if (lane_r == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { sg += s1[k][threadIdx.x & 31]; sb += s2[k][threadIdx.x & 31]; }
+    atomicAdd(dgamma + c, sg);
+    atomicAdd(dbeta + c, sb);
+  }
+}
+__global__ void k_bn_bwd_apply(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                               const bf16* __restrict__ y, const float* __restrict__ gamma,
+                               const float* __restrict__ mean, const float* __restrict__ rstd,
+                               const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                               bf16* __restrict__ dx, bf16* __restrict__ dres, long long rows,
+                               int C, int relu) {
+  const long long total = rows * C;
+  const float inv = 1.f / rows;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    float g = __bfloat162float(dy[i]);
+    if (relu && !(__bfloat162float(y[i]) > 0.f)) g = 0.f;
+    if (dres) dres[i] = __float2bfloat16(g);
+    const float xhat = (__bfloat162float(x[i]) - mean[c]) * rstd[c];
+    dx[i] = __float2bfloat16(gamma[c] * rstd[c] * (g - inv * (dbeta[c] + xhat * dgamma[c])));
+  }
+}
+
+// ------------------------------------------------------------------ layer norm [rows][C]
+__global__ void __launch_bounds__(kT) k_ln_fwd(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                               const float* __restrict__ gamma,
+                                               const float* __restrict__ beta,
+                                               float* __restrict__ mean, float* __restrict__ rstd,
+                                               long long rows, int C, float eps) {
+  __shared__ float sh[kT / 32];
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const bf16* xr = x + r * C;
+    float s = 0.f;
+    for (int c = threadIdx.x; c < C; c += kT) s += __bfloat162float(xr[c]);
+    const float m = block_sum(s, sh) / C;
+    float q = 0.f;
+    for (int c = threadIdx.x; c < C; c += kT) {
+      const float d = __bfloat162float(xr[c]) - m;
+      q += d * d;
+    }
+    const float rs = rsqrtf(block_sum(q, sh) / C + eps);
+    if (threadIdx.x == 0) { mean[r] = m; rstd[r] = rs; }
+    for (int c = threadIdx.x; c < C; c += kT)
+      y[r * C + c] = __float2bfloat16((__bfloat162float(xr[c]) - m) * rs * gamma[c] + beta[c]);
+  }
+}
+// C <= 4 * kT.  Each block walks a strided set of rows and keeps per-column partial
+// dgamma/dbeta in registers -> one atomic per column per block.
+__global__ void __launch_bounds__(kT) k_ln_bwd(const bf16* __restrict__ dy,
+                                               const bf16* __restrict__ x,
+                                               const float* __restrict__ gamma,
+                                               const float* __restrict__ mean,
+                                               const float* __restrict__ rstd,
+                                               bf16* __restrict__ dx, float* __restrict__ dgamma,
+                                               float* __restrict__ dbeta, long long rows, int C) {
+  __shared__ float sh[kT / 32];
+  float pg[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float m = mean[r], rs = rstd[r];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = threadIdx.x + k * kT;
+      if (c < C) {
+        const float g = __bfloat162float(dy[r * C + c]);
+        const float xh = (__bfloat162float(x[r * C + c]) - m) * rs;
+        pg[k] += g * xh;
+        pb[k] += g;
+        const float gg = g * gamma[c];
+        s1 += gg;
+        s2 += gg * xh;
+      }
+    }
+    s1 = block_sum(s1, sh) / C;
+    s2 = block_sum(s2, sh) / C;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = threadIdx.x + k * kT;
+      if (c < C) {
+        const float g = __bfloat162float(dy[r * C + c]) * gamma[c];
+        const float xh = (__bfloat162float(x[r * C + c]) - m) * rs;
+        dx[r * C + c] = __float2bfloat16(rs * (g - s1 - xh * s2));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = threadIdx.x + k * kT;
+    if (c < C) { atomicAdd(dgamma + c, pg[k]); atomicAdd(dbeta + c, pb[k]); }
+  }
+}
+
+// ------------------------------------------------------------------ row softmax (one warp/row)
+__global__ void k_softmax_fwd(const bf16* __restrict__ x, bf16* __restrict__ y, long long rows,
+                              int cols, float scale) {
+  const long long r = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int l = threadIdx.x & 31;
+  if (r >= rows) return;
+  float mx = -INFINITY;
+  for (int c = l; c < cols; c += 32) mx = fmaxf(mx, __bfloat162float(x[r * cols + c]) * scale);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int c = l; c < cols; c += 32) s += __expf(__bfloat162float(x[r * cols + c]) * scale - mx);
+  s = 1.f / warp_sum(s);
+  for (int c = l; c < cols; c += 32)
+    y[r * cols + c] = __float2bfloat16(__expf(__bfloat162float(x[r * cols + c]) * scale - mx) * s);
+}
+__global__ void k_softmax_bwd(const bf16* __restrict__ dy, const bf16* __restrict__ y,
+                              bf16* __restrict__ dx, long long rows, int cols, float scale) {
+  const long long r = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int l = threadIdx.x & 31;
+  if (r >= rows) return;
+  float dot = 0.f;
+  for (int c = l; c < cols; c += 32)
+    dot += __bfloat162float(dy[r * cols + c]) * __bfloat162float(y[r * cols + c]);
+  dot = warp_sum(dot);
+  for (int c = l; c < cols; c += 32) {
+    const float p = __bfloat162float(y[r * cols + c]);
+    dx[r * cols + c] = __float2bfloat16(scale * p * (__bfloat162float(dy[r * cols + c]) - dot));
+  }
+}
+
+// ------------------------------------------------------------------ embeddings
+__global__ void k_embed_fwd(const int32_t* __restrict__ ids, const bf16* __restrict__ table,
+                            const bf16* __restrict__ pos, bf16* __restrict__ out, long long rows,
+                            int seq, int C) {
+  const long long total = rows * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C;
+    const int c = static_cast<int>(i - r * C);
+    float v = __bfloat162float(table[static_cast<long long>(ids[r]) * C + c]);
+    if (pos) v += __bfloat162float(pos[(r % seq) * C + c]);
+    out[i] = __float2bfloat16(v);
+  }
+}
+__global__ void k_embed_bwd(const int32_t* __restrict__ ids, const bf16* __restrict__ dy,
+                            float* __restrict__ dtable, float* __restrict__ dpos, long long rows,
+                            int seq, int C) {
+  const long long total = rows * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C;
+    const int c = static_cast<int>(i - r * C);
+    const float g = __bfloat162float(dy[i]);
+    atomicAdd(dtable + static_cast<long long>(ids[r]) * C + c, g);
+    if (dpos) atomicAdd(dpos + (r % seq) * C + c, g);
+  }
+}
+
+// [d0][d1][d2][d3] -> [d0][d2][d1][d3]
+__global__ void k_transpose_0213(const bf16* __restrict__ x, bf16* __restrict__ y, int d0, int d1,
+                                 int d2, int d3) {
+  const long long total = static_cast<long long>(d0) * d1 * d2 * d3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int e = static_cast<int>(i % d3);
+    const int b = static_cast<int>((i / d3) % d1);
+    const int c = static_cast<int>((i / (static_cast<long long>(d3) * d1)) % d2);
+    const long long a = i / (static_cast<long long>(d3) * d1 * d2);
+    // i indexes the OUTPUT [a][c][b][e]
+    y[i] = x[((a * d1 + b) * d2 + c) * d3 + e];
+  }
+}
+
+// dz = dy * act'(aux) and colsum[c] += sum_rows dz   (mode 0: identity, 1: ReLU with aux = y,
+// 2: GELU with aux = pre-activation).  Tile: 32 channels x 8 row-lanes per block.
+__global__ void k_act_bwd_colsum(const bf16* __restrict__ dy, const bf16* __restrict__ aux,
+                                 bf16* __restrict__ dz, float* __restrict__ colsum, long long rows,
+                                 int C, int mode) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane_r = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < C) {
+    for (long long r = blockIdx.y * 8 + lane_r; r < rows; r += static_cast<long long>(gridDim.y) * 8) {
+      float g = __bfloat162float(dy[r * C + c]);
+      if (mode == 1) {
+        if (!(__bfloat162float(aux[r * C + c]) > 0.f)) g = 0.f;
+      } else if (mode == 2) {
+        const float x = __bfloat162float(aux[r * C + c]);
+        const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+        g *= cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+      }
+      if (dz) dz[r * C + c] = __float2bfloat16(g);
+      s += g;
+    }
+  }
+  __shared__ float sh[8][33];
+  sh[lane_r][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (lane_r == 0 && c < C && colsum) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += sh[k][threadIdx.x & 31];
+    atomicAdd(colsum + c, s);
+  }
+}
+
+}  // namespace
+
+cudaError_t act_bwd_colsum(const void* dy, const void* aux, void* dz, float* colsum, int64_t rows,
+                           int C, int mode, cudaStream_t s) {
+  dim3 g((C + 31) / 32, static_cast<unsigned>(rows / 64 > 128 ? 128 : (rows / 64 > 0 ? rows / 64 : 1)));
+  k_act_bwd_colsum<<<g, kT, 0, s>>>(reinterpret_cast<const bf16*>(dy),
+                                    reinterpret_cast<const bf16*>(aux), reinterpret_cast<bf16*>(dz),
+                                    colsum, rows, C, mode);
+  note_launch();
+  return cudaGetLastError();
+}
+
+#define NN_LAUNCH(kernel, grid, ...)            \
+  do {                                          \
+    kernel<<<grid, kT, 0, s>>>(__VA_ARGS__);    \
+    note_launch();                              \
+    return cudaGetLastError();                  \
+  } while (0)
+
+cudaError_t im2col_bf16(const void* x, void* col, int N, int C, int H, int W, int KH, int KW,
+                        int stride, int pad, int OH, int OW, int64_t ld_col, cudaStream_t s) {
+  const int64_t total = static_cast<int64_t>(N) * OH * OW * KH * KW * C;
+  NN_LAUNCH(k_im2col, blocks_for(total), reinterpret_cast<const bf16*>(x),
+            reinterpret_cast<bf16*>(col), N, C, H, W, KH, KW, stride, pad, OH, OW, ld_col);
+}
+cudaError_t col2im_bf16(const void* col, void* dx, int N, int C, int H, int W, int KH, int KW,
+                        int stride, int pad, int OH, int OW, int64_t ld_col, cudaStream_t s) {
+  NN_LAUNCH(k_col2im, blocks_for(static_cast<int64_t>(N) * H * W * C),
+            reinterpret_cast<const bf16*>(col), reinterpret_cast<bf16*>(dx), N, C, H, W, KH, KW,
+            stride, pad, OH, OW, ld_col);
+}
+cudaError_t maxpool2d_fwd(const void* x, void* y, int32_t* idx, int N, int C, int H, int W, int k,
+                          int stride, int pad, int OH, int OW, cudaStream_t s) {
+  NN_LAUNCH(k_maxpool_fwd, blocks_for(static_cast<int64_t>(N) * OH * OW * C),
+            reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), idx, N, C, H, W, k, stride,
+            pad, OH, OW);
+}
+// dx_f32: fp32 scratch [N * per_in] zeroed by the caller (overlapping windows accumulate);
+// n_out = N * per_out
+cudaError_t maxpool2d_bwd(const void* dy, const int32_t* idx, float* dx_f32, int64_t n_out,
+                          int64_t per_out, int64_t per_in, cudaStream_t s) {
+  NN_LAUNCH(k_maxpool_bwd, blocks_for(n_out), reinterpret_cast<const bf16*>(dy), idx, dx_f32, n_out,
+            per_out, per_in);
+}
+cudaError_t avgpool_global_fwd(const void* x, void* y, int N, int HW, int C, cudaStream_t s) {
+  NN_LAUNCH(k_avgpool_fwd, blocks_for(static_cast<int64_t>(N) * C), reinterpret_cast<const bf16*>(x),
+            reinterpret_cast<bf16*>(y), N, HW, C);
+}
+cudaError_t avgpool_global_bwd(const void* dy, void* dx, int N, int HW, int C, cudaStream_t s) {
+  NN_LAUNCH(k_avgpool_bwd, blocks_for(static_cast<int64_t>(N) * HW * C),
+            reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dx), N, HW, C);
+}
+
+cudaError_t batchnorm_fwd(const void* x, void* y, const float* gamma, const float* beta,
+                          float* mean, float* rstd, float* run_mean, float* run_var,
+                          int64_t rows, int C, float eps, float momentum, int training, int relu,
+                          const void* residual, cudaStream_t s) {
+  if (training) {
+    cudaError_t e = cudaMemsetAsync(mean, 0, sizeof(float) * C, s);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(rstd, 0, sizeof(float) * C, s);
+    if (e != cudaSuccess) return e;
+    dim3 g((C + 31) / 32, static_cast<unsigned>(rows / 64 > 64 ? 64 : (rows / 64 > 0 ? rows / 64 : 1)));
+    k_bn_stats<<<g, kT, 0, s>>>(reinterpret_cast<const bf16*>(x), mean, rstd, rows, C);
+    note_launch();
+    k_bn_finalize<<<(C + 127) / 128, 128, 0, s>>>(mean, rstd, run_mean, run_var, rows, C, eps,
+                                                   momentum);
+    note_launch();
+  }
+  NN_LAUNCH(k_bn_apply, blocks_for(rows * C), reinterpret_cast<const bf16*>(x),
+            reinterpret_cast<bf16*>(y), gamma, beta, mean, rstd,
+            reinterpret_cast<const bf16*>(residual), rows * C, C, relu);
+}
+cudaError_t batchnorm_bwd(const void* dy, const void* x, const void* y, const float* gamma,
+                          const float* mean, const float* rstd, void* dx, float* dgamma,
+                          float* dbeta, void* dresidual, int64_t rows, int C, int relu,
+                          cudaStream_t s) {
+  // dgamma / dbeta are accumulation targets (flat gradient buffer): the statistics of THIS call
+  // must be isolated, so reduce into them only when they are zero on entry (the optimizer zeroes
+  // the gradient buffer every step) -- documented contract.
+  dim3 g((C + 31) / 32, static_cast<unsigned>(rows / 64 > 64 ? 64 : (rows / 64 > 0 ? rows / 64 : 1)));
+  k_bn_bwd_reduce<<<g, kT, 0, s>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x),
+                                   reinterpret_cast<const bf16*>(y), mean, rstd, dgamma, dbeta, rows,
+                                   C, relu);
+  note_launch();
+  NN_LAUNCH(k_bn_bwd_apply, blocks_for(rows * C), reinterpret_cast<const bf16*>(dy),
+            reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(y), gamma, mean, rstd,
+            dgamma, dbeta, reinterpret_cast<bf16*>(dx), reinterpret_cast<bf16*>(dresidual), rows, C,
+            relu);
+}
+
+cudaError_t layernorm_fwd(const void* x, const void* residual, void* y, const float* gamma,
+                          const float* beta, float* mean, float* rstd, int64_t rows, int C,
+                          float eps, cudaStream_t s) {
+  if (residual != nullptr) return cudaErrorNotSupported;  // add with add_bf16 first
+  const int grid = static_cast<int>(rows < 148 * 8 ? rows : 148 * 8);
+  NN_LAUNCH(k_ln_fwd, grid, reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), gamma, beta,
+            mean, rstd, rows, C, eps);
+}
+cudaError_t layernorm_bwd(const void* dy, const void* xin, const float* gamma, const float* mean,
+                          const float* rstd, void* dx, float* dgamma, float* dbeta, int64_t rows,
+                          int C, cudaStream_t s) {
+  if (C > 4 * kT) return cudaErrorInvalidValue;
+  const int grid = static_cast<int>(rows < 148 * 2 ? rows : 148 * 2);
+  NN_LAUNCH(k_ln_bwd, grid, reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(xin),
+            gamma, mean, rstd, reinterpret_cast<bf16*>(dx), dgamma, dbeta, rows, C);
+}
+cudaError_t softmax_rows_fwd(const void* x, void* y, int64_t rows, int cols, float scale,
+                             cudaStream_t s) {
+  NN_LAUNCH(k_softmax_fwd, static_cast<int>((rows * 32 + kT - 1) / kT),
+            reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), rows, cols, scale);
+}
+cudaError_t softmax_rows_bwd(const void* dy, const void* y, void* dx, int64_t rows, int cols,
+                             float scale, cudaStream_t s) {
+  NN_LAUNCH(k_softmax_bwd, static_cast<int>((rows * 32 + kT - 1) / kT),
+            reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(y),
+            reinterpret_cast<bf16*>(dx), rows, cols, scale);
+}
+cudaError_t embedding_fwd(const int32_t* ids, const void* table_bf16, const void* pos_bf16,
+                          void* out, int64_t rows, int seq, int C, cudaStream_t s) {
+  NN_LAUNCH(k_embed_fwd, blocks_for(rows * C), ids, reinterpret_cast<const bf16*>(table_bf16),
+            reinterpret_cast<const bf16*>(pos_bf16), reinterpret_cast<bf16*>(out), rows, seq, C);
+}
+cudaError_t embedding_bwd(const int32_t* ids, const void* dy, float* dtable, float* dpos,
+                          int64_t rows, int seq, int C, cudaStream_t s) {
+  NN_LAUNCH(k_embed_bwd, blocks_for(rows * C), ids, reinterpret_cast<const bf16*>(dy), dtable, dpos,
+            rows, seq, C);
+}
+cudaError_t transpose_0213_bf16(const void* x, void* y, int d0, int d1, int d2, int d3,
+                                cudaStream_t s) {
+  NN_LAUNCH(k_transpose_0213, blocks_for(static_cast<int64_t>(d0) * d1 * d2 * d3),
+            reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), d0, d1, d2, d3);
+}
+
+}  // namespace bflc
