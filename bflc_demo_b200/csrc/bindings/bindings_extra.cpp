@@ -153,6 +153,9 @@ void bind_extra(py::module_& m) {
                                         two_shot ? 1 : 0, use_mc ? 1 : 0, cur_stream()),
           "fed_consensus_aggregate");
   });
+  m.def("fed_wait_trained", [](const py::dict& fd) {
+    check(bflc::fed_wait_trained(make_fed(fd), cur_stream()), "fed_wait_trained");
+  });
   m.def("set_predicate", [](int64_t ptr) { bflc::set_predicate(P<const int>(ptr)); });
   m.def("set_debug_times", [](int64_t ptr) { bflc::set_debug_times(P<long long>(ptr)); });
   m.def("p2p_read_probe", [](int64_t src, int64_t dst, int64_t n_vec) {

@@ -34,7 +34,7 @@ void gemm(const at::Tensor& a, const at::Tensor& b, const OptT& d, int64_t M, in
           bool accumulate, const OptT& labels, int64_t labels_bs, double grad_scale,
           const OptT& loss_sum, const OptT& correct, const OptT& b_maps, const OptT& bias_ptrs,
           int64_t dbg_lbo_a, int64_t dbg_sbo_a, int64_t dbg_lbo_b, int64_t dbg_sbo_b,
-          int64_t dyn_ptr) {
+          int64_t dyn_ptr, int64_t force_bn) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda(), "gemm operands must be CUDA tensors");
   c10::cuda::CUDAGuard guard(a.device());
   bflc::GemmProblem p;
@@ -46,6 +46,7 @@ void gemm(const at::Tensor& a, const at::Tensor& b, const OptT& d, int64_t M, in
                      ? reinterpret_cast<const CUtensorMap*>(b_maps->data_ptr())
                      : nullptr;
   p.dyn = reinterpret_cast<const bflc::GemmDynamic*>(static_cast<uintptr_t>(dyn_ptr));
+  p.force_bn = (int)force_bn;
   auto& e = p.epi;
   e.kind = static_cast<bflc::EpiKind>(epi_kind);
   e.d = d.has_value() ? d->data_ptr() : nullptr;
@@ -76,12 +77,13 @@ void gemm(const at::Tensor& a, const at::Tensor& b, const OptT& d, int64_t M, in
 
 // Encode the B-operand tensor map for (ptr, N, K, ld, ...) and return its 128 raw bytes.
 py::bytes gemm_b_map(int64_t ptr, int64_t N, int64_t K, int64_t ldb, bool b_mn, bool is_fp8,
-                     int64_t epi_kind) {
+                     int64_t epi_kind, int64_t force_bn) {
   bflc::GemmProblem p;
   p.M = 128; p.N = (int)N; p.K = (int)K; p.batch = 1;
   p.ab_dtype = is_fp8 ? bflc::DType::FP8_E4M3 : bflc::DType::BF16;
   p.b = {reinterpret_cast<const void*>(ptr), ldb, 0, b_mn};
   p.epi.kind = static_cast<bflc::EpiKind>(epi_kind);
+  p.force_bn = (int)force_bn;
   CUtensorMap m;
   check(bflc::gemm_make_b_map(p, &m), "gemm_make_b_map");
   return py::bytes(reinterpret_cast<const char*>(&m), sizeof(m));
@@ -105,10 +107,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("labels_bs") = 0, py::arg("grad_scale") = 1.0, py::arg("loss_sum") = py::none(),
         py::arg("correct") = py::none(), py::arg("b_maps") = py::none(),
         py::arg("bias_ptrs") = py::none(), py::arg("dbg_lbo_a") = 0, py::arg("dbg_sbo_a") = 0,
-        py::arg("dbg_lbo_b") = 0, py::arg("dbg_sbo_b") = 0, py::arg("dyn_ptr") = 0);
+        py::arg("dbg_lbo_b") = 0, py::arg("dbg_sbo_b") = 0, py::arg("dyn_ptr") = 0,
+        py::arg("force_bn") = 0);
   m.def("gemm_b_map", &gemm_b_map);
-  m.def("gemm_pick_bn", [](int64_t N, int64_t kind) {
-    return bflc::gemm_pick_bn((int)N, static_cast<bflc::EpiKind>(kind));
+  m.def("gemm_pick_bn", [](int64_t N, int64_t kind, int64_t M, int64_t z) {
+    return bflc::gemm_pick_bn((int)N, static_cast<bflc::EpiKind>(kind), (int)M, (int)z);
   });
   m.def("launch_count", [] { return bflc::launch_count(); });
   bind_extra(m);

@@ -68,13 +68,15 @@ struct GemmProblem {
   GemmEpilogue epi;
   // debug overrides for descriptor bring-up (0 = use built-in)
   uint32_t dbg_lbo_a = 0, dbg_sbo_a = 0, dbg_lbo_b = 0, dbg_sbo_b = 0;
+  int force_bn = 0;  // 0 = heuristic; 64/128/256 pins the N-tile (must match pre-built b maps)
 };
 
 // returns cudaSuccess or the failing status; throws nothing
 cudaError_t gemm_sm100(const GemmProblem& p, cudaStream_t stream);
 // Build the B-operand tensor map the kernel would use (for b_maps_dev arrays).
 cudaError_t gemm_make_b_map(const GemmProblem& p, CUtensorMap* out_host);
-int gemm_pick_bn(int N, EpiKind kind);
+// N-tile width the launcher would choose for a problem (z = batch * split_k)
+int gemm_pick_bn(int N, EpiKind kind, int M, int z);
 // number of kernels launched by this library since process start (bench bookkeeping)
 unsigned long long launch_count();
 void note_launch();
@@ -286,6 +288,9 @@ cudaError_t fed_upload(const FedArgs& f, int n_samples, int n_loss_terms, int by
 // re-elect, epoch++ and release FLAG_DONE.
 cudaError_t fed_consensus_aggregate(const FedArgs& f, int n_val, int weight_by_score,
                                     int two_shot, int use_multicast, cudaStream_t s);
+
+// stream-blocking wait until every trainer of the current epoch released FLAG_TRAINED
+cudaError_t fed_wait_trained(const FedArgs& f, cudaStream_t s);
 
 // thread-local predicate: kernels launched while it is set start with
 // `if (*pred == 0) return;` (role predication inside a captured graph)

@@ -414,6 +414,17 @@ __global__ void k_mc_store(float4* mc_dst, const float4* __restrict__ src, long 
   for (long long i = tid; i < n; i += stride) ptx::multimem_st_f4(mc_dst + i, src[i]);
 }
 
+// Generic (non-captured) engines: block the stream until every trainer of the current epoch has
+// published its upload, so ordinary kernels launched afterwards may read the peers' buffers.
+__global__ void k_wait_trained(FedArgs f) {
+  char* me = f.peers.base[f.rank];
+  const RoundState* st = at<RoundState>(me, f.lay.state_off);
+  const uint32_t* flags = at<uint32_t>(me, f.lay.flags_off);
+  const int r = threadIdx.x;
+  if (r < f.n_ranks && (st->role[r] & ROLE_TRAINER))
+    ptx::wait_flag_ge(flags + FLAG_TRAINED + r, st->epoch + 1);
+}
+
 int fed_grid(long long n_params) {
   long long blocks = (n_params / 4 + kFedThreads * 4 - 1) / (kFedThreads * 4);
   if (blocks > 148 * 4) blocks = 148 * 4;
@@ -449,6 +460,12 @@ cudaError_t fed_consensus_aggregate(const FedArgs& f, int n_val, int weight_by_s
                                   : f.lay.n_params;
   k_consensus<<<fed_grid(work), kFedThreads, 0, s>>>(f, n_val, weight_by_score, two_shot,
                                                      use_multicast);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t fed_wait_trained(const FedArgs& f, cudaStream_t s) {
+  k_wait_trained<<<1, 32, 0, s>>>(f);
   note_launch();
   return cudaGetLastError();
 }

@@ -65,6 +65,7 @@ struct KParams {
   unsigned int* correct;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b;
   uint32_t kstep_a, kstep_b;  // descriptor start-address advance per UMMA_K step (bytes)
+  int vec_ok;                 // d / aux rows are 16-byte aligned -> vectorised global access
 };
 
 template <int BN>
@@ -74,8 +75,109 @@ struct SmemLayout {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTileBytes = kStages * kStageBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = kTileBytes + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kStgBytes = 4 * 32 * 36 * 4;  // per-epilogue-warp [32][36] fp32 staging
+  static constexpr int kBiasBytes = BN * 4;
+  static constexpr int kTotal = kTileBytes + kBarBytes + kStgBytes + kBiasBytes + 1024;
 };
+
+constexpr int kStgLd = 36;  // floats per staged row: 16-byte aligned, conflict-free both ways
+
+__device__ __forceinline__ void stage_put(float* stg, int lane, const float (&v)[32]) {
+  float4* rowp = reinterpret_cast<float4*>(stg + lane * kStgLd);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) rowp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void stage_get(const float* stg, int lane, float (&v)[32]) {
+  const float4* rowp = reinterpret_cast<const float4*>(stg + lane * kStgLd);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = rowp[j];
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// Staged [32][32] fp32 tile -> global.  Lane (cr, cg) moves 4 consecutive columns of row
+// it*4+cr, so one warp instruction covers 4 rows x 128 B.  DT: 0 fp32, 1 bf16, 2 fp8(e4m3).
+template <int DT, bool RED>
+__device__ __forceinline__ void tile_store(const float* stg, void* dptr, long long tile_off,
+                                           long long ldd, int row_base, int nc, int M, int N,
+                                           int cr, int cg, int vec_ok) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + cr;
+    const int row = row_base + rr;
+    const int col = nc + cg;
+    if (row >= M || col >= N) continue;
+    const float4 x = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cg);
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    const long long off = tile_off + static_cast<long long>(row) * ldd + col;
+    const bool vec = vec_ok && (col + 3 < N);
+    if constexpr (DT == 0) {
+      float* d = reinterpret_cast<float*>(dptr) + off;
+      if constexpr (RED) {
+        if (vec) ptx::red_add_f32x4(d, x.x, x.y, x.z, x.w);
+        else
+          for (int k = 0; k < 4; ++k) if (col + k < N) atomicAdd(d + k, xs[k]);
+      } else {
+        if (vec) *reinterpret_cast<float4*>(d) = x;
+        else
+          for (int k = 0; k < 4; ++k) if (col + k < N) d[k] = xs[k];
+      }
+    } else if constexpr (DT == 1) {
+      __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dptr) + off;
+      if (vec) *reinterpret_cast<uint2*>(d) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+      else
+        for (int k = 0; k < 4; ++k) if (col + k < N) d[k] = __float2bfloat16(xs[k]);
+    } else {
+      __nv_fp8_e4m3* d = reinterpret_cast<__nv_fp8_e4m3*>(dptr) + off;
+      for (int k = 0; k < 4; ++k) if (col + k < N) d[k] = __nv_fp8_e4m3(xs[k]);
+    }
+  }
+}
+__device__ __forceinline__ void tile_accumulate_f32(const float* stg, void* dptr, long long tile_off,
+                                                    long long ldd, int row_base, int nc, int M,
+                                                    int N, int cr, int cg) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + cr;
+    const int row = row_base + rr;
+    const int col = nc + cg;
+    if (row >= M || col >= N) continue;
+    const float4 x = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cg);
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    float* d = reinterpret_cast<float*>(dptr) + tile_off + static_cast<long long>(row) * ldd + col;
+    for (int k = 0; k < 4; ++k) if (col + k < N) d[k] += xs[k];
+  }
+}
+// global bf16 tile -> staged fp32 tile (zeros outside the matrix)
+__device__ __forceinline__ void tile_load_bf16(float* stg, const void* sptr, long long tile_off,
+                                               long long ldd, int row_base, int nc, int M, int N,
+                                               int cr, int cg, int vec_ok) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + cr;
+    const int row = row_base + rr;
+    const int col = nc + cg;
+    float xs[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < M && col < N) {
+      const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(sptr) + tile_off +
+                               static_cast<long long>(row) * ldd + col;
+      if (vec_ok && col + 3 < N) {
+        const uint2 u = *reinterpret_cast<const uint2*>(s);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        xs[0] = a.x; xs[1] = a.y; xs[2] = b.x; xs[3] = b.y;
+      } else {
+        for (int k = 0; k < 4; ++k) if (col + k < N) xs[k] = __bfloat162float(s[k]);
+      }
+    }
+    *reinterpret_cast<float4*>(stg + rr * kStgLd + cg) = make_float4(xs[0], xs[1], xs[2], xs[3]);
+  }
+}
 
 __device__ __forceinline__ float gelu_f(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
@@ -84,22 +186,6 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
   const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
-}
-
-// Sum v[j] over the 32 lanes of the warp for each j; lane j returns column j's total.
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int j = 0; j < off; ++j) {
-      // keep half of the columns: lanes with bit `off` set keep [off, 2*off), others [0, off)
-      const float send = upper ? v[j] : v[j + off];
-      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
-      v[j] = (upper ? v[j + off] : v[j]) + recv;
-    }
-  }
-  return v[0];
 }
 
 template <int BN, int EPI>
@@ -114,6 +200,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* empty_bar = full_bar + L::kStages;
   uint64_t* accum_bar = empty_bar + L::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  float* stage_base = reinterpret_cast<float*>(smem + L::kTileBytes + L::kBarBytes);
+  float* sbias = stage_base + 4 * 32 * kStgLd;
 
   // role predication / dynamic batch count: CTA-uniform early exits before any barrier
   if (p.pred != nullptr && *p.pred == 0) return;
@@ -224,21 +312,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (dbg) p.dbg_times[4] = clock64();
     }
   } else {
+
     // --------------------------------------------------------------- epilogue
+    // TMEM -> registers (thread = one accumulator row) -> fused math -> per-warp smem staging
+    // tile [32 rows][36 floats] -> global, so that every global instruction touches full
+    // 128-byte lines (4 rows x 128 B per warp instruction) instead of 32 scattered rows.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
+    const int ew = warp - 2; // epilogue warp index 0..3 (staging buffer owner)
+    const int row_base = m0 + q * 32;
+    const int row = row_base + lane;
     const bool row_ok = row < p.M;
+    float* stg = stage_base + ew * (32 * kStgLd);
+    const float* bias = p.dyn ? p.dyn->bias[bidx] : (p.bias_ptrs ? p.bias_ptrs[bidx] : p.bias);
+    {  // bias tile -> smem once per CTA (coalesced), shared by the four epilogue warps
+      const int et = threadIdx.x - 64;
+      for (int i = et; i < BN; i += 128)
+        sbias[i] = (bias != nullptr && n0 + i < p.N && split == 0) ? __ldg(bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     ptx::mbar_wait(accum_bar, 0);
     ptx::tc_fence_after_sync();
     if (dbg && warp == 2 && lane == 0) p.dbg_times[5] = clock64();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const bool have_acc = n_kb > 0;
+    const long long tile_off = static_cast<long long>(bidx) * p.d_batch_stride;
+    // coalesced-phase coordinates of this lane: 4 rows x 8 column groups per instruction
+    const int cr = lane >> 3, cg = (lane & 7) * 4;
 
     if constexpr (EPI == 0) {
-      const float* bias =
-          p.dyn ? p.dyn->bias[bidx] : (p.bias_ptrs ? p.bias_ptrs[bidx] : p.bias);
-      const long long row_off = static_cast<long long>(bidx) * p.d_batch_stride +
-                                static_cast<long long>(row) * p.ldd;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int nc = n0 + c * 32;
@@ -248,18 +349,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         ptx::tmem_ld_wait();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = have_acc ? __uint_as_float(r[j]) * p.alpha : 0.f;
-          const int n = nc + j;
-          if (bias != nullptr && n < p.N && split == 0) x += __ldg(bias + n);
-          v[j] = x;
-        }
-        const bool full = (nc + 32 <= p.N);
-        if (p.aux_out != nullptr && row_ok) {
-          __nv_bfloat16* ao = reinterpret_cast<__nv_bfloat16*>(p.aux_out) + row_off + nc;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || nc + j < p.N) ao[j] = __float2bfloat16(v[j]);
+        for (int j = 0; j < 32; ++j)
+          v[j] = (have_acc ? __uint_as_float(r[j]) * p.alpha : 0.f) + sbias[c * 32 + j];
+        if (p.aux_out != nullptr) {
+          stage_put(stg, lane, v);
+          __syncwarp();
+          tile_store<1, false>(stg, p.aux_out, tile_off, p.ldd, row_base, nc, p.M, p.N, cr, cg,
+                               p.vec_ok);
+          __syncwarp();
         }
         if (p.act == 1) {
 #pragma unroll
@@ -269,87 +366,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
         }
         if (p.act_bwd != 0) {
-          const __nv_bfloat16* ai =
-              reinterpret_cast<const __nv_bfloat16*>(p.aux_in) + row_off + nc;
+          tile_load_bf16(stg, p.aux_in, tile_off, p.ldd, row_base, nc, p.M, p.N, cr, cg, p.vec_ok);
+          __syncwarp();
+          float a[32];
+          stage_get(stg, lane, a);
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = 0.f;
-            if (row_ok && (full || nc + j < p.N)) a = __bfloat162float(ai[j]);
-            v[j] = (p.act_bwd == 1) ? (a > 0.f ? v[j] : 0.f) : v[j] * gelu_grad_f(a);
-          }
+          for (int j = 0; j < 32; ++j)
+            v[j] = (p.act_bwd == 1) ? (a[j] > 0.f ? v[j] : 0.f) : v[j] * gelu_grad_f(a[j]);
         }
-        if (row_ok) {
-          if (p.split_k > 1) {
-            float* d = reinterpret_cast<float*>(p.d) + row_off + nc;
-            if (full && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                ptx::red_add_f32x4(d + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (full || nc + j < p.N) atomicAdd(d + j, v[j]);
-            }
-          } else if (p.d_dtype == 0) {
-            float* d = reinterpret_cast<float*>(p.d) + row_off + nc;
-            const bool vec = full && ((reinterpret_cast<uintptr_t>(d) & 15) == 0);
-            if (vec && !p.accumulate) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (full || nc + j < p.N) d[j] = p.accumulate ? d[j] + v[j] : v[j];
-            }
-          } else if (p.d_dtype == 1) {
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.d) + row_off + nc;
-            const bool vec = full && ((reinterpret_cast<uintptr_t>(d) & 15) == 0);
-            if (vec) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&t0);
-                pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                pk.z = *reinterpret_cast<uint32_t*>(&t2);
-                pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                *reinterpret_cast<uint4*>(d + j) = pk;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (full || nc + j < p.N) d[j] = __float2bfloat16(v[j]);
-            }
-          } else {
-            // fp8 e4m3 output (already scaled by alpha)
-            __nv_fp8_e4m3* d = reinterpret_cast<__nv_fp8_e4m3*>(p.d) + row_off + nc;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full || nc + j < p.N) d[j] = __nv_fp8_e4m3(v[j]);
-          }
-        }
+        stage_put(stg, lane, v);
+        __syncwarp();
+        if (p.split_k > 1)
+          tile_store<0, true>(stg, p.d, tile_off, p.ldd, row_base, nc, p.M, p.N, cr, cg, p.vec_ok);
+        else if (p.d_dtype == 0)
+          (p.accumulate ? tile_accumulate_f32(stg, p.d, tile_off, p.ldd, row_base, nc, p.M, p.N, cr, cg)
+                        : tile_store<0, false>(stg, p.d, tile_off, p.ldd, row_base, nc, p.M, p.N,
+                                               cr, cg, p.vec_ok));
+        else if (p.d_dtype == 1)
+          tile_store<1, false>(stg, p.d, tile_off, p.ldd, row_base, nc, p.M, p.N, cr, cg, p.vec_ok);
+        else
+          tile_store<2, false>(stg, p.d, tile_off, p.ldd, row_base, nc, p.M, p.N, cr, cg, p.vec_ok);
         if (p.colsum != nullptr) {
-          if (!row_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          }
-          const float tot = warp_colsum32(v, lane);
+          // column sums straight from the staged tile: lane j adds up column j over valid rows
+          float tot = 0.f;
+          const int rmax = min(32, p.M - row_base);
+          for (int rr = 0; rr < rmax; ++rr) tot += stg[rr * kStgLd + lane];
           if (nc + lane < p.N) atomicAdd(p.colsum + nc + lane, tot);
         }
+        __syncwarp();
       }
     } else {
       // ---------------- row-wise epilogues: the whole logit row lives in this CTA's tile
-      static_assert(BN <= 256, "row epilogue needs N <= BN");
       const int32_t label =
           (row_ok && p.labels)
               ? p.labels[static_cast<long long>(bidx) * p.labels_batch_stride + row]
               : -1;
-      const float* bias =
-          p.dyn ? p.dyn->bias[bidx] : (p.bias_ptrs ? p.bias_ptrs[bidx] : p.bias);
       // pass 1: max / argmax (+ label logit)
       float vmax = -INFINITY, zlab = 0.f;
       int amax = -1;
@@ -364,7 +416,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int j = 0; j < 32; ++j) {
           const int n = nc + j;
           if (n < p.N) {
-            float x = __uint_as_float(r[j]) * p.alpha + (bias ? __ldg(bias + n) : 0.f);
+            const float x = __uint_as_float(r[j]) * p.alpha + sbias[n];
             if (x > vmax) { vmax = x; amax = n; }
             if (n == label) zlab = x;
           }
@@ -387,17 +439,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = nc + j;
-            if (n < p.N) {
-              float x = __uint_as_float(r[j]) * p.alpha + (bias ? __ldg(bias + n) : 0.f);
-              sum += __expf(x - vmax);
-            }
+            if (n < p.N) sum += __expf(__uint_as_float(r[j]) * p.alpha + sbias[n] - vmax);
           }
         }
         const float inv = 1.f / sum;
         float loss = row_ok ? (__logf(sum) + vmax - zlab) : 0.f;
-        // pass 3: dlogits
-        const long long row_off = static_cast<long long>(bidx) * p.d_batch_stride +
-                                  static_cast<long long>(row) * p.ldd;
+        // pass 3: dlogits (rows padded to ldd >= round_up(N, 8); pad columns get zeros)
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           const int nc = c * 32;
@@ -411,22 +458,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int n = nc + j;
             float g = 0.f;
             if (n < p.N && row_ok) {
-              float x = __uint_as_float(r[j]) * p.alpha + (bias ? __ldg(bias + n) : 0.f);
+              const float x = __uint_as_float(r[j]) * p.alpha + sbias[n];
               g = (__expf(x - vmax) * inv - (n == label ? 1.f : 0.f)) * p.grad_scale;
             }
             v[j] = g;
           }
-          if (row_ok && p.d != nullptr) {
-            // dlogits rows are padded to ldd (>= round_up(N, 8)); pad columns get zeros
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.d) + row_off + nc;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nc + j < p.ldd) d[j] = __float2bfloat16(v[j]);
-          }
+          stage_put(stg, lane, v);
+          __syncwarp();
+          if (p.d != nullptr)
+            tile_store<1, false>(stg, p.d, tile_off, p.ldd, row_base, nc, p.M,
+                                 static_cast<int>(p.ldd), cr, cg, p.vec_ok);
           if (p.colsum != nullptr) {
-            const float tot = warp_colsum32(v, lane);
+            float tot = 0.f;
+            for (int rr = 0; rr < 32; ++rr) tot += stg[rr * kStgLd + lane];
             if (nc + lane < p.N) atomicAdd(p.colsum + nc + lane, tot);
           }
+          __syncwarp();
         }
         // loss / correct reductions
 #pragma unroll
@@ -532,15 +579,23 @@ static thread_local const int* g_pred = nullptr;
 void set_predicate(const int* pred) { g_pred = pred; }
 const int* current_predicate() { return g_pred; }
 
-int gemm_pick_bn(int N, EpiKind kind) {
+int gemm_pick_bn(int N, EpiKind kind, int M, int z) {
   if (kind != EpiKind::GENERIC) return N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-  if (N <= 64) return 64;
-  if (N <= 128) return 128;
-  return 256;
+  // Largest tile that still yields ~a wave of CTAs; tiny problems take the narrowest tile so
+  // the fixed per-CTA latency (setup + first TMA + epilogue) is spread over more SMs.
+  const int mt = (M + kBM - 1) / kBM;
+  const int cand[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    if (bn > 64 && N <= bn / 2) continue;
+    const long long ctas = static_cast<long long>((N + bn - 1) / bn) * mt * (z < 1 ? 1 : z);
+    if (ctas >= 120 || bn == 64) return bn;
+  }
+  return 64;
 }
 
 cudaError_t gemm_make_b_map(const GemmProblem& p, CUtensorMap* out_host) {
-  const int BN = gemm_pick_bn(p.N, p.epi.kind);
+  const int BN = p.force_bn ? p.force_bn : gemm_pick_bn(p.N, p.epi.kind, p.M, p.batch);
   return make_map(out_host, p.b, p.ab_dtype, p.N, p.K, p.batch, BN);
 }
 
@@ -548,9 +603,12 @@ cudaError_t gemm_sm100(const GemmProblem& p, cudaStream_t stream) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.batch <= 0) return cudaErrorInvalidValue;
   const bool fp8 = p.ab_dtype == DType::FP8_E4M3;
   if (p.ab_dtype == DType::F32) return cudaErrorInvalidValue;
-  const int BN = gemm_pick_bn(p.N, p.epi.kind);
-  if (p.epi.kind != EpiKind::GENERIC && p.N > 256) return cudaErrorInvalidValue;
-  if (fp8 && p.b.mn_major && BN < 128) return cudaErrorInvalidValue;
+  int BN = p.force_bn ? p.force_bn
+                      : gemm_pick_bn(p.N, p.epi.kind, p.M,
+                                     p.batch * (p.epi.split_k < 1 ? 1 : p.epi.split_k));
+  if (BN != 64 && BN != 128 && BN != 256) return cudaErrorInvalidValue;
+  if (p.epi.kind != EpiKind::GENERIC && (p.N > 256 || BN < p.N)) return cudaErrorInvalidValue;
+  if (fp8 && p.b.mn_major && BN < 128) BN = 128;
   const int block_k = fp8 ? 128 : 64;
 
   CUtensorMap ta, tb;
@@ -597,6 +655,13 @@ cudaError_t gemm_sm100(const GemmProblem& p, cudaStream_t stream) {
   kp.grad_scale = p.epi.grad_scale;
   kp.loss_sum = p.epi.loss_sum;
   kp.correct = p.epi.correct;
+  {
+    // vector (16 B fp32 / 8 B bf16) global access needs 4-element aligned rows everywhere
+    auto al = [](const void* q, int bytes) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % bytes) == 0; };
+    const int eb = p.epi.d_dtype == DType::F32 ? 16 : (p.epi.d_dtype == DType::BF16 ? 8 : 4);
+    kp.vec_ok = (p.epi.ldd % 4 == 0) && (p.epi.d_batch_stride % 4 == 0) && al(p.epi.d, eb) &&
+                al(p.epi.aux_out, 8) && al(p.epi.aux_in, 8);
+  }
   // Canonical SWIZZLE_128B descriptors.
   //  K-major : rows of 128 B; 8-row groups every 1024 B (SBO); LBO unused (1 unit).
   //            one UMMA_K step = 32 B inside the swizzle span.

@@ -134,13 +134,17 @@ class FusedEngine:
 
         # ---- validation tensor-map table [layer][parity][rank] (peers' upload shadows) ----
         K = sz["kMaxRanks"]
-        blob = bytearray(2 * 2 * K * 128)
         e1, e2 = self.spec.by_name["w1"], self.spec.by_name["w2"]
+        # N-tile widths are pinned so the pre-encoded peer tensor maps match the launches
+        self.val_bn = [self.mod.gemm_pick_bn(e1.shape[0], G.EPI_GENERIC, self.n_val, world),
+                       self.mod.gemm_pick_bn(e2.shape[0], G.EPI_ARGMAX, self.n_val, world)]
+        blob = bytearray(2 * 2 * K * 128)
         for layer, (e, kind) in enumerate(((e1, G.EPI_GENERIC), (e2, G.EPI_ARGMAX))):
             for par in range(2):
                 for r in range(world):
                     base = self.heap.peer_ptrs[r] + o[f"upload_shadow{par}"] + e.offset * 2
-                    m = self.mod.gemm_b_map(base, e.shape[0], e.shape[1], e.shape[1], False, False, kind)
+                    m = self.mod.gemm_b_map(base, e.shape[0], e.shape[1], e.shape[1], False, False, kind,
+                                            self.val_bn[layer])
                     idx = (layer * 2 + par) * K + r
                     blob[idx * 128:(idx + 1) * 128] = m
         self.b_maps = torch.frombuffer(blob, dtype=torch.uint8).to(self.dev)
@@ -172,11 +176,11 @@ class FusedEngine:
         m.gemm(xv, self.work_shadow, self.h_val, self.n_val, H, self.in_dim, self.world,
                self.in_dim, self.in_dim, 0, 0, False, False, False, G.EPI_GENERIC, 1, H,
                self.n_val * H, 1.0, None, G.ACT_RELU, None, None, 0, None, 1, False, None, 0, 1.0,
-               None, None, self.b_maps, None, 0, 0, 0, 0, self.dyn_ptr[0])
+               None, None, self.b_maps, None, 0, 0, 0, 0, self.dyn_ptr[0], self.val_bn[0])
         m.gemm(self.h_val, self.work_shadow, None, self.n_val, self.spec.by_name["w2"].shape[0], H,
                self.world, H, H, self.n_val * H, 0, False, False, False, G.EPI_ARGMAX, 1, 0, 0, 1.0,
                None, 0, None, None, 0, None, 1, False, yv, 0, 1.0, None, self.val_correct,
-               self.b_maps, None, 0, 0, 0, 0, self.dyn_ptr[1])
+               self.b_maps, None, 0, 0, 0, 0, self.dyn_ptr[1], self.val_bn[1])
         m.fed_consensus_aggregate(self.fed, self.n_val, cfg.weight_by_score, self.two_shot,
                                   cfg.use_multicast and self.heap.has_multicast)
         self.launches_per_round = int(m.launch_count() - n0)
