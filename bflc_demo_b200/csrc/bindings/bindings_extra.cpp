@@ -77,6 +77,11 @@ void bind_extra(py::module_& m) {
              for (auto& b : blobs) v.emplace_back(static_cast<std::string>(b));
              s.h->import_handles(v);
            })
+      .def("fd_listen", [](PyHeap& s, const std::string& tag) { return s.h->fd_listen(tag); })
+      .def("import_via_sockets",
+           [](PyHeap& s, const std::vector<std::string>& names) { s.h->import_via_sockets(names); })
+      .def("mc_import_via_sockets",
+           [](PyHeap& s, const std::vector<std::string>& names) { return s.h->mc_import_via_sockets(names); })
       .def("mc_create_and_export", [](PyHeap& s) { return py::bytes(s.h->mc_create_and_export()); })
       .def("mc_import_and_add",
            [](PyHeap& s, const py::bytes& b) { return s.h->mc_import_and_add(std::string(b)); })

@@ -6,7 +6,9 @@
 #include <cuda_runtime.h>
 #include <cstring>
 #include <stdexcept>
+#include <sys/socket.h>
 #include <sys/syscall.h>
+#include <sys/un.h>
 #include <unistd.h>
 
 namespace bflc {
@@ -58,6 +60,54 @@ int steal_fd(int pid, int fd) {
 }
 
 size_t round_up(size_t x, size_t g) { return (x + g - 1) / g * g; }
+
+// --- SCM_RIGHTS helpers -------------------------------------------------------------------
+socklen_t abstract_addr(const std::string& name, sockaddr_un* a) {
+  std::memset(a, 0, sizeof(*a));
+  a->sun_family = AF_UNIX;
+  const size_t n = name.size() < sizeof(a->sun_path) - 2 ? name.size() : sizeof(a->sun_path) - 2;
+  std::memcpy(a->sun_path + 1, name.data(), n);  // leading NUL = abstract namespace
+  return static_cast<socklen_t>(offsetof(sockaddr_un, sun_path) + 1 + n);
+}
+bool send_fd(int sock, int fd) {
+  char tag = fd >= 0 ? 'F' : 'N';
+  iovec iov{&tag, 1};
+  msghdr msg{};
+  msg.msg_iov = &iov;
+  msg.msg_iovlen = 1;
+  alignas(cmsghdr) char ctl[CMSG_SPACE(sizeof(int))];
+  if (fd >= 0) {
+    std::memset(ctl, 0, sizeof(ctl));
+    msg.msg_control = ctl;
+    msg.msg_controllen = sizeof(ctl);
+    cmsghdr* c = CMSG_FIRSTHDR(&msg);
+    c->cmsg_level = SOL_SOCKET;
+    c->cmsg_type = SCM_RIGHTS;
+    c->cmsg_len = CMSG_LEN(sizeof(int));
+    std::memcpy(CMSG_DATA(c), &fd, sizeof(int));
+  }
+  return sendmsg(sock, &msg, 0) == 1;
+}
+int recv_fd(int sock) {  // -1: no fd sent, -2: error
+  char tag = 0;
+  iovec iov{&tag, 1};
+  msghdr msg{};
+  msg.msg_iov = &iov;
+  msg.msg_iovlen = 1;
+  alignas(cmsghdr) char ctl[CMSG_SPACE(sizeof(int))];
+  std::memset(ctl, 0, sizeof(ctl));
+  msg.msg_control = ctl;
+  msg.msg_controllen = sizeof(ctl);
+  if (recvmsg(sock, &msg, 0) != 1) return -2;
+  if (tag != 'F') return -1;
+  for (cmsghdr* c = CMSG_FIRSTHDR(&msg); c; c = CMSG_NXTHDR(&msg, c))
+    if (c->cmsg_level == SOL_SOCKET && c->cmsg_type == SCM_RIGHTS) {
+      int fd;
+      std::memcpy(&fd, CMSG_DATA(c), sizeof(int));
+      return fd;
+    }
+  return -2;
+}
 
 CUmemAllocationProp vmm_prop(int device) {
   CUmemAllocationProp prop;
@@ -164,6 +214,7 @@ SymmHeap::~SymmHeap() {
     if (export_fd_ >= 0) close(export_fd_);
     if (mc_fd_ >= 0) close(mc_fd_);
   }
+  if (listen_fd_ >= 0) close(listen_fd_);
 }
 
 std::string SymmHeap::export_handle() const {
@@ -218,6 +269,102 @@ void SymmHeap::import_handles(const std::vector<std::string>& blobs) {
       peers_[static_cast<size_t>(r)] = map_handle(h, bytes_, gran, device_);
     }
   }
+}
+
+std::string SymmHeap::fd_listen(const std::string& unique_tag) {
+  if (listen_fd_ >= 0) close(listen_fd_);
+  listen_fd_ = socket(AF_UNIX, SOCK_STREAM, 0);
+  if (listen_fd_ < 0) throw std::runtime_error("SymmHeap: socket() failed");
+  const std::string name = "bflc_symm_" + unique_tag + "_" + std::to_string(rank_);
+  sockaddr_un a;
+  const socklen_t len = abstract_addr(name, &a);
+  if (bind(listen_fd_, reinterpret_cast<sockaddr*>(&a), len) != 0 || listen(listen_fd_, 64) != 0)
+    throw std::runtime_error("SymmHeap: bind/listen on abstract socket failed");
+  return name;
+}
+
+// All-to-all exchange of one fd per rank (my_fd < 0 = nothing to share).  connect() completes
+// against the listen backlog, so [connect all] -> [accept all + send] -> [recv all] cannot
+// deadlock as long as every rank listened before the caller's barrier.
+std::vector<int> SymmHeap::exchange_fds(const std::vector<std::string>& names, int my_fd) {
+  if (listen_fd_ < 0) throw std::runtime_error("SymmHeap: fd_listen() was not called");
+  std::vector<int> out_sock(static_cast<size_t>(world_), -1), got(static_cast<size_t>(world_), -1);
+  for (int r = 0; r < world_; ++r) {
+    if (r == rank_) continue;
+    int s = socket(AF_UNIX, SOCK_STREAM, 0);
+    sockaddr_un a;
+    const socklen_t len = abstract_addr(names[static_cast<size_t>(r)], &a);
+    if (s < 0 || connect(s, reinterpret_cast<sockaddr*>(&a), len) != 0)
+      throw std::runtime_error("SymmHeap: connect to peer socket failed");
+    out_sock[static_cast<size_t>(r)] = s;
+  }
+  for (int i = 0; i < world_ - 1; ++i) {
+    int c = accept(listen_fd_, nullptr, nullptr);
+    if (c < 0 || !send_fd(c, my_fd)) throw std::runtime_error("SymmHeap: accept/send_fd failed");
+    close(c);
+  }
+  for (int r = 0; r < world_; ++r) {
+    if (r == rank_) continue;
+    const int fd = recv_fd(out_sock[static_cast<size_t>(r)]);
+    close(out_sock[static_cast<size_t>(r)]);
+    if (fd == -2) throw std::runtime_error("SymmHeap: recv_fd failed");
+    got[static_cast<size_t>(r)] = fd;
+  }
+  return got;
+}
+
+void SymmHeap::map_peer_fd(int r, int fd) {
+  DRV(cuMemImportFromShareableHandle);
+  DRV(cuMemGetAllocationGranularity);
+  CUmemGenericAllocationHandle h;
+  cu_check(p_cuMemImportFromShareableHandle(&h, reinterpret_cast<void*>(static_cast<intptr_t>(fd)),
+                                            CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR),
+           "cuMemImportFromShareableHandle");
+  close(fd);
+  peer_handles_[static_cast<size_t>(r)] = h;
+  CUmemAllocationProp prop = vmm_prop(device_);
+  size_t gran = 0;
+  cu_check(p_cuMemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED),
+           "granularity");
+  peers_[static_cast<size_t>(r)] = map_handle(h, bytes_, gran, device_);
+}
+
+void SymmHeap::import_via_sockets(const std::vector<std::string>& names) {
+  if (mode_ != Mode::VMM) throw std::runtime_error("SymmHeap: socket import needs VMM mode");
+  std::vector<int> fds = exchange_fds(names, export_fd_);
+  for (int r = 0; r < world_; ++r) {
+    if (r == rank_) continue;
+    if (fds[static_cast<size_t>(r)] < 0) throw std::runtime_error("SymmHeap: peer sent no fd");
+    map_peer_fd(r, fds[static_cast<size_t>(r)]);
+  }
+}
+
+bool SymmHeap::mc_import_via_sockets(const std::vector<std::string>& names) {
+  if (mode_ != Mode::VMM) return false;
+  DRV(cuMemImportFromShareableHandle);
+  DRV(cuMulticastAddDevice);
+  std::vector<int> fds = exchange_fds(names, rank_ == 0 ? mc_fd_ : -1);
+  if (rank_ != 0) {
+    const int fd = fds[0];
+    if (fd < 0) { err_ = "rank 0 has no multicast object: " + err_; return false; }
+    CUmemGenericAllocationHandle h;
+    CUresult r = p_cuMemImportFromShareableHandle(
+        &h, reinterpret_cast<void*>(static_cast<intptr_t>(fd)), CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+    close(fd);
+    if (r != CUDA_SUCCESS) {
+      err_ = "import multicast handle: CUresult " + std::to_string(static_cast<int>(r));
+      return false;
+    }
+    mc_handle_ = h;
+  } else if (!mc_handle_) {
+    return false;
+  }
+  CUresult r = p_cuMulticastAddDevice(mc_handle_, device_);
+  if (r != CUDA_SUCCESS) {
+    err_ = "cuMulticastAddDevice: CUresult " + std::to_string(static_cast<int>(r));
+    return false;
+  }
+  return true;
 }
 
 std::string SymmHeap::mc_create_and_export() {

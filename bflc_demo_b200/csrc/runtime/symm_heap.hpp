@@ -34,6 +34,14 @@ class SymmHeap {
   // blobs of all ranks, indexed by rank (own entry ignored)
   void import_handles(const std::vector<std::string>& blobs);
 
+  // VMM handle exchange over abstract unix sockets (SCM_RIGHTS) -- works where pidfd_getfd is
+  // denied (ptrace scope / seccomp).  Protocol: every rank calls fd_listen() and publishes the
+  // returned name; after a barrier every rank calls import_via_sockets(names).
+  std::string fd_listen(const std::string& unique_tag);
+  void import_via_sockets(const std::vector<std::string>& names);
+  // multicast over the same sockets: rank 0 must have called mc_create_and_export() first
+  bool mc_import_via_sockets(const std::vector<std::string>& names);
+
   // multicast (VMM mode only). Rank 0 creates and exports; everyone imports/binds/maps.
   // Returns empty string when the device or driver does not support multicast.
   std::string mc_create_and_export();
@@ -64,6 +72,9 @@ class SymmHeap {
   int mc_fd_ = -1;
   void* mc_va_ = nullptr;
   bool mc_bound_ = false;
+  int listen_fd_ = -1;
+  std::vector<int> exchange_fds(const std::vector<std::string>& names, int my_fd);
+  void map_peer_fd(int r, int fd);
   mutable std::string err_;
 };
 

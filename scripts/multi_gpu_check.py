@@ -1,0 +1,116 @@
+"""Multi-GPU protocol checks (run under torchrun, any world size 2..8). Rank 0 prints one
+``RESULT {json}`` line.  Used by tests/test_gpu_multi.py and the gpurun scripts.
+
+Checks:
+  fused       MLP fused engine: rounds advance, host ledgers verify, replicas bit-identical,
+              committee rotates, loss falls
+  byzantine   one sign-flipping rank is never aggregated nor elected
+  two_shot    two-shot (slice-reduce + publish) aggregation gives the same digest as one-shot
+  multicast   the same through NVLS multimem stores when the heap has a multicast mapping
+  generic     LeNet-5 through the model-agnostic engine (validation on peers' HBM)
+"""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+from bflc_demo_b200.config import FLConfig
+from bflc_demo_b200.data.synthetic import cifar_like, femnist_like
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    which = sys.argv[1:] or ["fused", "byzantine", "two_shot", "generic"]
+    out = {"world": world}
+
+    def gather(x):
+        box = [None] * world
+        dist.all_gather_object(box, x)
+        return box
+
+    from bflc_demo_b200.engine.fused import FusedEngine
+
+    def run_fused(rounds=6, **kw):
+        cfg = FLConfig.for_world(world, hidden=256, batch_size=128, samples_per_client=512,
+                                 learning_rate=0.05, **kw)
+        shard = femnist_like(world, 512, seed=3, only=rank)[0]
+        eng = FusedEngine(cfg, shard, rank=rank, world=world, device=lr)
+        eng.capture()
+        hist = [eng.run_round_e2e() for _ in range(rounds)]
+        errs = eng.drain_blocks()
+        st = eng.read_state()
+        info = dict(epoch=st["epoch"], digest=st["model_digest"], errs=errs,
+                    chain=eng.host_ledger.verify_chain(), blocks=eng.host_ledger.n_blocks(),
+                    last_hash=eng.host_ledger.blocks()[-1]["hash"], loss=[h["global_loss"] for h in hist],
+                    roles=[h["roles"] for h in hist], symm=eng.heap.describe())
+        blocks = eng.host_ledger.blocks()
+        torch.cuda.synchronize(); dist.barrier()   # nobody may still be reading my heap
+        del eng
+        torch.cuda.synchronize(); dist.barrier()
+        return info, blocks
+
+    if "fused" in which:
+        info, blocks = run_fused()
+        allinfo = gather(info)
+        out["fused"] = dict(
+            epochs=[i["epoch"] for i in allinfo], errs=sum((i["errs"] for i in allinfo), []),
+            identical_digest=len({i["digest"] for i in allinfo}) == 1,
+            identical_chain=len({i["last_hash"] for i in allinfo}) == 1,
+            chain_ok=all(i["chain"] for i in allinfo), loss=info["loss"],
+            committee_rotates=len({tuple(r) for r in info["roles"]}) > 1 if world > 2 else True,
+            symm=info["symm"])
+    if "byzantine" in which and world >= 4:
+        byz = world - 1
+        info, blocks = run_fused(rounds=6, byzantine_ranks=[byz], byzantine_scale=5.0)
+        sel = [b["selected"] for b in blocks]
+        elected = [b["role_after"][byz] for b in blocks]
+        admitted = [byz in b["admitted"] for b in blocks]
+        out["byzantine"] = dict(rank=byz, ever_selected=any(byz in s for s in sel),
+                                ever_elected=any(e == 2 for e in elected),
+                                times_admitted=sum(admitted),
+                                median_of_byz=[b["median"][b["admitted"].index(byz)] for b in blocks if byz in b["admitted"]][:3],
+                                median_best=[max(b["median"]) for b in blocks][:3])
+    if "two_shot" in which:
+        # (local training uses split-K atomics, so two separate runs are not bit-comparable;
+        #  what must hold in every mode is that all replicas of one run are bit-identical)
+        res = {}
+        for name, kw in (("two_shot_p2p", dict(two_shot=True, use_multicast=False)),
+                         ("two_shot_multicast", dict(two_shot=True, use_multicast=True))):
+            r, _ = run_fused(rounds=4, **kw)
+            g = gather(r)
+            res[name] = dict(identical=len({i["digest"] for i in g}) == 1,
+                             errs=sum((i["errs"] for i in g), []), chain_ok=all(i["chain"] for i in g),
+                             loss=r["loss"], multicast=r["symm"]["multicast"],
+                             multicast_error=r["symm"]["multicast_error"], notes=r["symm"]["notes"])
+        out["two_shot"] = res
+    if "generic" in which:
+        from bflc_demo_b200.engine.generic import GenericFedEngine
+        from bflc_demo_b200.models.nets import LeNet5
+        cfg = FLConfig.for_world(world, batch_size=64, samples_per_client=256, learning_rate=0.05,
+                                 model="lenet5", dataset="cifar10")
+        shard = cifar_like(world, 256, seed=2)[rank]
+        eng = GenericFedEngine(cfg, LeNet5(10), shard, rank=rank, world=world, device=lr)
+        acc0 = eng.evaluate(shard)
+        for _ in range(5):
+            eng.run_round()
+        errs = eng.drain_blocks()
+        st = eng.read_state()
+        g = gather(dict(digest=st["model_digest"], errs=errs, epoch=st["epoch"]))
+        out["generic_lenet5"] = dict(epoch=st["epoch"], acc_before=acc0, acc_after=eng.evaluate(shard),
+                                     identical=len({i["digest"] for i in g}) == 1,
+                                     errs=sum((i["errs"] for i in g), []), loss=st["global_loss"])
+        torch.cuda.synchronize(); dist.barrier()
+        del eng
+        torch.cuda.synchronize(); dist.barrier()
+    if rank == 0:
+        print("RESULT " + json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,49 @@
+"""Multi-GPU protocol tests: spawn torchrun over all visible GPUs (>= 2) and assert on the
+RESULT line of scripts/multi_gpu_check.py."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _run(which):
+    n = min(torch.cuda.device_count(), 8)
+    n = 8 if n >= 8 else (4 if n >= 4 else 2)
+    env = dict(os.environ, PYTHONPATH=ROOT + ":" + os.environ.get("PYTHONPATH", ""), BFLC_NO_AUTOBUILD="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port",
+                          str(_free_port()), os.path.join(ROOT, "scripts", "multi_gpu_check.py"), *which],
+                         capture_output=True, text=True, env=env, timeout=900)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
+    assert lines, out.stdout[-3000:] + out.stderr[-3000:]
+    return n, json.loads(lines[0][7:])
+
+
+def test_fused_engine_multi_gpu():
+    n, res = _run(["fused", "two_shot"])
+    f = res["fused"]
+    assert f["errs"] == [] and f["identical_digest"] and f["identical_chain"] and f["chain_ok"]
+    assert all(e == 7 for e in f["epochs"])
+    assert f["loss"][-1] < f["loss"][0]
+    for mode in res["two_shot"].values():
+        assert mode["identical"] and mode["errs"] == [] and mode["chain_ok"]
+
+
+def test_generic_engine_and_byzantine_multi_gpu():
+    n, res = _run(["generic", "byzantine"])
+    g = res["generic_lenet5"]
+    assert g["identical"] and g["errs"] == [] and g["epoch"] == 5
+    if n >= 4:
+        b = res["byzantine"]
+        assert not b["ever_selected"] and not b["ever_elected"]
