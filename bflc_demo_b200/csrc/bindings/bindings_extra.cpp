@@ -97,7 +97,13 @@ void bind_extra(py::module_& m) {
   m.def("tensor_from_ptr", [](int64_t ptr, std::vector<int64_t> shape, py::object dtype, int device) {
     auto st = torch::python::detail::py_object_to_dtype(dtype);
     auto opts = at::TensorOptions().dtype(st).device(at::kCUDA, device);
-    return at::from_blob(P<void>(ptr), shape, [](void*) {}, opts);
+    // target_device: a peer-mapped (VMM / IPC) pointer reports the OWNING GPU as its device;
+    // the view must still be a tensor of the local device so local kernels accept it.
+    return at::for_blob(P<void>(ptr), shape)
+        .deleter([](void*) {})
+        .options(opts)
+        .target_device(at::Device(at::kCUDA, static_cast<c10::DeviceIndex>(device)))
+        .make_tensor();
   });
 
   m.def("struct_sizes", [] {
