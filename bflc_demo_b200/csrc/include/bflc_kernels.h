@@ -295,6 +295,8 @@ cudaError_t fed_wait_trained(const FedArgs& f, cudaStream_t s);
 // thread-local predicate: kernels launched while it is set start with
 // `if (*pred == 0) return;` (role predication inside a captured graph)
 void set_predicate(const int* pred);
+void set_pdl(bool on);   // programmatic dependent launch for all library kernels (default on)
+bool pdl_enabled();
 void set_debug_times(long long* dev_buf8);  // GEMM phase clock stamps of CTA (0,0,0)
 const int* current_predicate();
 

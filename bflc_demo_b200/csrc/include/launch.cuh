@@ -1,0 +1,30 @@
+// Kernel launch helper: cudaLaunchKernelEx with the programmatic-stream-serialization attribute
+// (PDL).  A kernel launched this way may begin while its predecessor in the stream is still
+// running; it must execute ptx::pdl_wait() before touching memory the predecessor produces
+// (all kernels of this library do).  Works under stream capture (programmatic graph edges).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <utility>
+
+#include "bflc_kernels.h"
+
+namespace bflc {
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+}  // namespace bflc

@@ -36,6 +36,16 @@ __device__ __forceinline__ bool elect_one() {
 #endif
 
 // ----------------------------------------------------------------------------
+// programmatic dependent launch (PDL)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

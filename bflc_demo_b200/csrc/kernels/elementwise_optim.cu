@@ -10,6 +10,8 @@
 #include <cuda_fp8.h>
 
 #include "bflc_kernels.h"
+#include "launch.cuh"
+#include "sm100_ptx.cuh"
 
 namespace bflc {
 
@@ -54,6 +56,8 @@ __global__ void k_cast_bf16_f32(const __nv_bfloat16* __restrict__ src, float* __
 
 __global__ void k_cast_u8_bf16(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                int64_t n, float scale, const int* pred) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   if (pred != nullptr && *pred == 0) return;
   const int64_t nv = n / 16;
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -138,6 +142,8 @@ __global__ void k_add_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_
 // ------------------------------------------------------------------ optimizers
 template <bool kAdam>
 __global__ void k_optim(OptimArgs a) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   if (a.active != nullptr && *a.active == 0) return;
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -208,6 +214,12 @@ __global__ void k_optim(OptimArgs a) {
     return cudaGetLastError();                                  \
   } while (0)
 
+#define BFLC_LAUNCH_1D_PDL(kernel, nvec, ...)                                          \
+  do {                                                                                \
+    note_launch();                                                                    \
+    return launch_pdl(kernel, dim3(grid_for(nvec)), dim3(kBlock), 0, s, __VA_ARGS__); \
+  } while (0)
+
 cudaError_t cast_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t s) {
   BFLC_LAUNCH_1D(k_cast_f32_bf16, n / 8 + 1, src, reinterpret_cast<__nv_bfloat16*>(dst), n);
 }
@@ -216,8 +228,8 @@ cudaError_t cast_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_
 }
 cudaError_t cast_u8_to_bf16(const uint8_t* src, void* dst, int64_t n, float scale,
                             cudaStream_t s) {
-  BFLC_LAUNCH_1D(k_cast_u8_bf16, n / 16 + 1, src, reinterpret_cast<__nv_bfloat16*>(dst), n, scale,
-                 current_predicate());
+  BFLC_LAUNCH_1D_PDL(k_cast_u8_bf16, n / 16 + 1, src, reinterpret_cast<__nv_bfloat16*>(dst), n,
+                     scale, current_predicate());
 }
 cudaError_t quantize_fp8(const void* src_bf16, uint8_t* dst, int64_t n, float inv_scale,
                          cudaStream_t s) {
@@ -236,11 +248,11 @@ cudaError_t add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStr
                  n);
 }
 cudaError_t sgd_step(const OptimArgs& a, cudaStream_t s) {
-  BFLC_LAUNCH_1D(k_optim<false>, a.n / 4 + 1, a);
+  BFLC_LAUNCH_1D_PDL(k_optim<false>, a.n / 4 + 1, a);
 }
 cudaError_t adam_step(const OptimArgs& a, cudaStream_t s) {
   if (!a.m || !a.v) return cudaErrorInvalidValue;
-  BFLC_LAUNCH_1D(k_optim<true>, a.n / 4 + 1, a);
+  BFLC_LAUNCH_1D_PDL(k_optim<true>, a.n / 4 + 1, a);
 }
 
 }  // namespace bflc

@@ -18,6 +18,7 @@
 
 #include "bflc_kernels.h"
 #include "consensus_math.hpp"
+#include "launch.cuh"
 #include "sm100_ptx.cuh"
 
 namespace bflc {
@@ -44,6 +45,8 @@ struct PlanLayers {
 };
 
 __global__ void k_plan(FedArgs f, PlanLayers layers) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   char* me = f.peers.base[f.rank];
   const RoundState* st = at<RoundState>(me, f.lay.state_off);
@@ -90,6 +93,8 @@ __global__ void k_plan(FedArgs f, PlanLayers layers) {
 // ------------------------------------------------------------------ upload
 __global__ void __launch_bounds__(kFedThreads)
 k_upload(FedArgs f, int n_samples, int n_loss_terms, int byz_mode, float byz_scale) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   char* me = f.peers.base[f.rank];
   const RoundState* st = at<RoundState>(me, f.lay.state_off);
   RoundPlan* plan = at<RoundPlan>(me, f.lay.plan_off);
@@ -161,6 +166,8 @@ __global__ void __launch_bounds__(kFedThreads)
 k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc) {
   __shared__ ConsShared sh;
   __shared__ bool last;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   char* me = f.peers.base[f.rank];
   RoundState* st = at<RoundState>(me, f.lay.state_off);
   RoundPlan* plan = at<RoundPlan>(me, f.lay.plan_off);
@@ -441,27 +448,24 @@ cudaError_t fed_plan_round(const FedArgs& f, const PlanLayer* layers, int n_laye
   pl.n = n_layers;
   pl.steps_per_round = steps_per_round;
   for (int i = 0; i < n_layers; ++i) pl.l[i] = layers[i];
-  k_plan<<<1, 32, 0, s>>>(f, pl);
   note_launch();
-  return cudaGetLastError();
+  return launch_pdl(k_plan, dim3(1), dim3(32), 0, s, f, pl);
 }
 
 cudaError_t fed_upload(const FedArgs& f, int n_samples, int n_loss_terms, int byz_mode,
                        float byz_scale, cudaStream_t s) {
-  k_upload<<<fed_grid(f.lay.n_params), kFedThreads, 0, s>>>(f, n_samples, n_loss_terms, byz_mode,
-                                                            byz_scale);
   note_launch();
-  return cudaGetLastError();
+  return launch_pdl(k_upload, dim3(fed_grid(f.lay.n_params)), dim3(kFedThreads), 0, s, f, n_samples,
+                    n_loss_terms, byz_mode, byz_scale);
 }
 
 cudaError_t fed_consensus_aggregate(const FedArgs& f, int n_val, int weight_by_score,
                                     int two_shot, int use_multicast, cudaStream_t s) {
   const long long work = two_shot ? f.lay.n_params / (f.n_ranks > 0 ? f.n_ranks : 1)
                                   : f.lay.n_params;
-  k_consensus<<<fed_grid(work), kFedThreads, 0, s>>>(f, n_val, weight_by_score, two_shot,
-                                                     use_multicast);
   note_launch();
-  return cudaGetLastError();
+  return launch_pdl(k_consensus, dim3(fed_grid(work)), dim3(kFedThreads), 0, s, f, n_val,
+                    weight_by_score, two_shot, use_multicast);
 }
 
 cudaError_t fed_wait_trained(const FedArgs& f, cudaStream_t s) {

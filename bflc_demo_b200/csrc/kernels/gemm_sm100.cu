@@ -23,6 +23,7 @@
 #include <mutex>
 
 #include "bflc_kernels.h"
+#include "launch.cuh"
 #include "sm100_ptx.cuh"
 
 namespace bflc {
@@ -203,11 +204,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   float* stage_base = reinterpret_cast<float*>(smem + L::kTileBytes + L::kBarBytes);
   float* sbias = stage_base + 4 * 32 * kStgLd;
 
-  // role predication / dynamic batch count: CTA-uniform early exits before any barrier
-  if (p.pred != nullptr && *p.pred == 0) return;
-  if (p.dyn != nullptr && static_cast<int>(blockIdx.z) / p.split_k >= p.dyn->active_batches)
-    return;
-
+  // Programmatic dependent launch: let the next kernel of the stream get scheduled now; this
+  // CTA's own prologue (barrier init, TMEM alloc, descriptor prefetch) runs before it waits
+  // for its predecessors' memory.
+  ptx::pdl_launch_dependents();
   const long long t_entry = clock64();
   const bool dbg = p.dbg_times != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
   const int warp = threadIdx.x >> 5;
@@ -223,12 +223,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int n_kb = max(0, kb_end - kb_begin);
   const int block_k = p.is_fp8 ? 128 : 64;  // elements per 128-byte span
 
-  const CUtensorMap* mapB =
-      p.b_maps_dev ? (p.b_maps_dev + (p.dyn ? p.dyn->map_index[bidx] : bidx)) : &tmB;
-
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmA);
-    ptx::tma_prefetch_desc(mapB);
+    if (p.b_maps_dev == nullptr) ptx::tma_prefetch_desc(&tmB);
     for (int s = 0; s < L::kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -243,26 +240,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot;
   if (dbg && threadIdx.x == 0) { p.dbg_times[0] = t_entry; p.dbg_times[1] = clock64(); }
 
+  // Everything below touches memory produced by earlier kernels of the stream.
+  ptx::pdl_wait();
+  // role predication / dynamic batch count (device-resident, written by the plan kernel)
+  const bool inactive = (p.pred != nullptr && *p.pred == 0) ||
+                        (p.dyn != nullptr && bidx >= p.dyn->active_batches);
+  if (inactive) {  // CTA-uniform
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, BN);
+    return;
+  }
+  const CUtensorMap* mapB =
+      p.b_maps_dev ? (p.b_maps_dev + (p.dyn ? p.dyn->map_index[bidx] : bidx)) : &tmB;
+
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const int ca2 = p.a_batched ? bidx : 0;
-      const int cb2 = (p.b_batched && !p.b_maps_dev) ? bidx : 0;
-      const uint32_t stage_bytes = L::kStageBytes;
-      if (p.dyn != nullptr && p.dyn->wait_flag[bidx] != nullptr) {
-        // B lives in a peer's upload buffer: wait until that trainer released it, then make
-        // the acquired state visible to the async proxy before the first TMA pull.
-        ptx::wait_flag_ge(p.dyn->wait_flag[bidx], p.dyn->wait_value);
-        ptx::fence_proxy_async_all();
-      }
-      for (int i = 0; i < n_kb; ++i) {
-        const int s = i % L::kStages;
-        const uint32_t ph = (i / L::kStages) & 1;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-        ptx::mbar_expect_tx(&full_bar[s], stage_bytes);
-        uint8_t* sa = smem + s * L::kStageBytes;
-        uint8_t* sb = sa + kABytes;
-        const int k0 = (kb_begin + i) * block_k;
+    // The whole warp runs the loop (warp-uniform control flow keeps addresses / coordinates in
+    // uniform registers); one elected lane issues the copies.
+    const int ca2 = p.a_batched ? bidx : 0;
+    const int cb2 = (p.b_batched && !p.b_maps_dev) ? bidx : 0;
+    if (p.dyn != nullptr && p.dyn->wait_flag[bidx] != nullptr) {
+      // B lives in a peer's upload buffer: wait until that trainer released it, then make
+      // the acquired state visible to the async proxy before the first TMA pull.
+      if (lane == 0) ptx::wait_flag_ge(p.dyn->wait_flag[bidx], p.dyn->wait_value);
+      __syncwarp();
+      ptx::fence_proxy_async_all();
+    }
+    for (int i = 0; i < n_kb; ++i) {
+      const int s = i % L::kStages;
+      const uint32_t ph = (i / L::kStages) & 1;
+      ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* sa = smem + s * L::kStageBytes;
+      uint8_t* sb = sa + kABytes;
+      const int k0 = (kb_begin + i) * block_k;
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(&full_bar[s], L::kStageBytes);
         if (!p.a_mn) {
           ptx::tma_load_3d(sa, &tmA, &full_bar[s], k0, m0, ca2);
         } else {
@@ -282,35 +293,50 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (dbg && i == 0) p.dbg_times[2] = clock64();
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc =
-          ptx::make_idesc(p.is_fp8 ? 0u : 1u, p.a_mn ? 1u : 0u, p.b_mn ? 1u : 0u, kBM, BN);
-      for (int i = 0; i < n_kb; ++i) {
-        const int s = i % L::kStages;
-        const uint32_t ph = (i / L::kStages) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);
-        ptx::tc_fence_after_sync();
+    // Warp-uniform loop; descriptors are built from 32-bit uniform arithmetic (only the low
+    // word -- start address -- changes per stage / K step) and one elected lane issues.
+    const uint32_t idesc =
+        ptx::make_idesc(p.is_fp8 ? 0u : 1u, p.a_mn ? 1u : 0u, p.b_mn ? 1u : 0u, kBM, BN);
+    const uint32_t hi_a = ((p.sbo_a >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+    const uint32_t hi_b = ((p.sbo_b >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+    const uint32_t base_lo = (ptx::smem_u32(smem) >> 4);
+    const uint32_t lo_a0 = base_lo | (((p.lbo_a >> 4) & 0x3FFFu) << 16);
+    const uint32_t lo_b0 = (base_lo + (kABytes >> 4)) | (((p.lbo_b >> 4) & 0x3FFFu) << 16);
+    const uint32_t ks_a = p.kstep_a >> 4, ks_b = p.kstep_b >> 4;
+    const bool fp8 = p.is_fp8 != 0;
+    for (int i = 0; i < n_kb; ++i) {
+      const int s = i % L::kStages;
+      const uint32_t ph = (i / L::kStages) & 1;
+      ptx::mbar_wait(&full_bar[s], ph);
+      ptx::tc_fence_after_sync();
+      const uint32_t so = static_cast<uint32_t>(s) * (L::kStageBytes >> 4);
+      if (ptx::elect_one()) {
         if (dbg && i == 0) p.dbg_times[3] = clock64();
-        const uint32_t sa = ptx::smem_u32(smem + s * L::kStageBytes);
-        const uint32_t sb = sa + kABytes;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K (32 bytes of K) per 128-byte stage
-          const uint64_t ad = ptx::make_smem_desc_sw128(sa + k * p.kstep_a, p.lbo_a, p.sbo_a);
-          const uint64_t bd = ptx::make_smem_desc_sw128(sb + k * p.kstep_b, p.lbo_b, p.sbo_b);
+          const uint64_t ad =
+              (static_cast<uint64_t>(hi_a) << 32) | static_cast<uint64_t>(lo_a0 + so + k * ks_a);
+          const uint64_t bd =
+              (static_cast<uint64_t>(hi_b) << 32) | static_cast<uint64_t>(lo_b0 + so + k * ks_b);
           const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-          if (p.is_fp8)
+          if (fp8)
             ptx::umma_f8(tmem_base, ad, bd, idesc, acc);
           else
             ptx::umma_f16(tmem_base, ad, bd, idesc, acc);
         }
         ptx::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
       }
+      __syncwarp();
+    }
+    if (ptx::elect_one()) {
       ptx::umma_commit(accum_bar);  // accumulator complete
       if (dbg) p.dbg_times[4] = clock64();
     }
+    __syncwarp();
   } else {
 
     // --------------------------------------------------------------- epilogue
@@ -563,9 +589,8 @@ cudaError_t launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& 
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  gemm_kernel<BN, EPI><<<grid, kThreads, L::kTotal, stream>>>(ta, tb, kp);
   note_launch();
-  return cudaGetLastError();
+  return launch_pdl(gemm_kernel<BN, EPI>, grid, dim3(kThreads), L::kTotal, stream, ta, tb, kp);
 }
 
 }  // namespace
@@ -575,6 +600,9 @@ unsigned long long launch_count() { return g_launches; }
 void note_launch() { ++g_launches; }
 static thread_local long long* g_dbg_times = nullptr;
 void set_debug_times(long long* p) { g_dbg_times = p; }
+static bool g_pdl = true;
+void set_pdl(bool on) { g_pdl = on; }
+bool pdl_enabled() { return g_pdl; }
 static thread_local const int* g_pred = nullptr;
 void set_predicate(const int* pred) { g_pred = pred; }
 const int* current_predicate() { return g_pred; }
