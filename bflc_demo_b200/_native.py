@@ -37,7 +37,11 @@ def C():
     """The CUDA kernel module (imports torch first so libtorch symbols resolve)."""
     import torch  # noqa: F401
 
-    return _load("_C")
+    fresh = "_C" not in _cache
+    mod = _load("_C")
+    if fresh and os.environ.get("BFLC_PDL", "1") == "0":
+        mod.set_pdl(False)  # A/B switch: plain stream-ordered launches
+    return mod
 
 
 def ledger():

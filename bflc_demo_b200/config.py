@@ -45,6 +45,8 @@ class FLConfig:
     backend: str = "auto"             # auto | fused (P2P kernels) | nccl (baseline) | gloo
     two_shot: Optional[bool] = None   # None = by model size
     use_multicast: bool = True
+    stage_candidates: bool = True     # committee pulls each candidate's weights once (P2P) vs
+                                      # the validation GEMMs TMA-loading peers' HBM directly
     cuda_graph: bool = True
     ring_slots: int = 256
 

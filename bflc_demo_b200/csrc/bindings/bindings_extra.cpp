@@ -141,7 +141,7 @@ void bind_extra(py::module_& m) {
 
   // ------------------------------------------------------------ fed kernels
   m.def("fed_plan_round", [](const py::dict& fd, std::vector<std::pair<int64_t, bool>> layers,
-                             int steps_per_round) {
+                             int steps_per_round, bool staged) {
     bflc::FedArgs f = make_fed(fd);
     bflc::PlanLayer pl[bflc::kMaxPlanLayers];
     TORCH_CHECK((int)layers.size() <= bflc::kMaxPlanLayers, "too many plan layers");
@@ -149,7 +149,7 @@ void bind_extra(py::module_& m) {
       pl[i].bias_off = layers[i].first;
       pl[i].use_bias = layers[i].second ? 1 : 0;
     }
-    check(bflc::fed_plan_round(f, pl, (int)layers.size(), steps_per_round, cur_stream()),
+    check(bflc::fed_plan_round(f, pl, (int)layers.size(), steps_per_round, staged ? 1 : 0, cur_stream()),
           "fed_plan_round");
   });
   m.def("fed_upload", [](const py::dict& fd, int n_samples, int n_loss_terms, int byz_mode,
@@ -163,6 +163,12 @@ void bind_extra(py::module_& m) {
     check(bflc::fed_consensus_aggregate(make_fed(fd), n_val, weight_by_score ? 1 : 0,
                                         two_shot ? 1 : 0, use_mc ? 1 : 0, cur_stream()),
           "fed_consensus_aggregate");
+  });
+  m.def("fed_pull_candidates", [](const py::dict& fd, at::Tensor stage_shadow, const OptT& stage_master) {
+    check(bflc::fed_pull_candidates(make_fed(fd), stage_shadow.data_ptr(),
+                                    stage_master.has_value() ? stage_master->data_ptr<float>() : nullptr,
+                                    cur_stream()),
+          "fed_pull_candidates");
   });
   m.def("fed_wait_trained", [](const py::dict& fd) {
     check(bflc::fed_wait_trained(make_fed(fd), cur_stream()), "fed_wait_trained");

@@ -72,7 +72,13 @@ void gemm(const at::Tensor& a, const at::Tensor& b, const OptT& d, int64_t M, in
   e.correct = opt_ptr<unsigned int>(correct);
   p.dbg_lbo_a = (uint32_t)dbg_lbo_a; p.dbg_sbo_a = (uint32_t)dbg_sbo_a;
   p.dbg_lbo_b = (uint32_t)dbg_lbo_b; p.dbg_sbo_b = (uint32_t)dbg_sbo_b;
-  check(bflc::gemm_sm100(p, cur_stream()), "gemm_sm100");
+  const cudaError_t err = bflc::gemm_sm100(p, cur_stream());
+  TORCH_CHECK(err == cudaSuccess, "bflc::gemm_sm100 failed: ", cudaGetErrorString(err), " [M=", M,
+              " N=", N, " K=", K, " batch=", batch, " lda=", lda, " ldb=", ldb, " a_bs=", a_bs,
+              " b_bs=", b_bs, " a_mn=", a_mn, " b_mn=", b_mn, " fp8=", is_fp8, " epi=", epi_kind,
+              " d_dtype=", d_dtype, " ldd=", ldd, " split_k=", split_k, " a%16=",
+              reinterpret_cast<uintptr_t>(raw(a)) % 16, " b%16=",
+              reinterpret_cast<uintptr_t>(raw(b)) % 16, "]");
 }
 
 // Encode the B-operand tensor map for (ptr, N, K, ld, ...) and return its 128 raw bytes.

@@ -274,7 +274,7 @@ struct PlanLayer {
 // start of round: predicates, candidate list, per-layer GemmDynamic, accumulator reset,
 // and (safety) wait until every rank finished consuming the buffers about to be reused.
 cudaError_t fed_plan_round(const FedArgs& f, const PlanLayer* layers, int n_layers,
-                           int steps_per_round, cudaStream_t s);
+                           int steps_per_round, int staged, cudaStream_t s);
 // trainer ("UploadLocalUpdate", CommitteePrecompiled.cpp:215-258): copy the trained weights
 // into the peer-readable upload buffers, push {n_samples, avg_cost} to every replica and
 // release FLAG_TRAINED on every peer.  byz_mode 1 = sign-flipped, scaled delta (fault
@@ -289,6 +289,11 @@ cudaError_t fed_upload(const FedArgs& f, int n_samples, int n_loss_terms, int by
 cudaError_t fed_consensus_aggregate(const FedArgs& f, int n_val, int weight_by_score,
                                     int two_shot, int use_multicast, cudaStream_t s);
 
+// committee ranks: pull every candidate's uploaded weights (bf16 shadow, optionally the fp32
+// master) out of the trainers' HBM into local staging [slot z][n_params], each as soon as its
+// trainer's flag is up.  stage_master may be null.
+cudaError_t fed_pull_candidates(const FedArgs& f, void* stage_shadow, float* stage_master,
+                                cudaStream_t s);
 // stream-blocking wait until every trainer of the current epoch released FLAG_TRAINED
 cudaError_t fed_wait_trained(const FedArgs& f, cudaStream_t s);
 

@@ -42,6 +42,7 @@ struct PlanLayers {
   PlanLayer l[kMaxPlanLayers];
   int n;
   int steps_per_round;
+  int staged;  // 1: validation B operands are the local staging slots filled by k_pull
 };
 
 __global__ void k_plan(FedArgs f, PlanLayers layers) {
@@ -71,13 +72,15 @@ __global__ void k_plan(FedArgs f, PlanLayers layers) {
     d.wait_value = epoch + 1;
     for (int z = 0; z < kMaxRanks; ++z) {
       const int t = z < n_cand ? plan->cand_rank[z] : 0;
-      // tensor-map table is laid out [layer][parity][rank]
-      d.map_index[z] = (l * 2 + static_cast<int>(par)) * kMaxRanks + t;
+      // tensor-map table: staged -> [layer][slot] over local staging; direct -> [layer][parity]
+      // [rank] over the trainers' upload buffers (TMA pulls across NVLink)
+      d.map_index[z] = layers.staged ? (l * kMaxRanks + z)
+                                     : ((l * 2 + static_cast<int>(par)) * kMaxRanks + t);
       d.bias[z] = layers.l[l].use_bias
                       ? at<float>(f.peers.base[t], f.lay.upload_master_off[par]) +
                             layers.l[l].bias_off
                       : nullptr;
-      d.wait_flag[z] = flags + FLAG_TRAINED + t;
+      d.wait_flag[z] = layers.staged ? nullptr : flags + FLAG_TRAINED + t;
     }
   }
   for (int z = 0; z < kMaxRanks; ++z) plan->correct[z] = 0;
@@ -432,6 +435,47 @@ __global__ void k_wait_trained(FedArgs f) {
     ptx::wait_flag_ge(flags + FLAG_TRAINED + r, st->epoch + 1);
 }
 
+// Committee-side gather ("QueryAllUpdates", C:299-311) without NCCL: block (x, z) waits for
+// candidate z's trainer flag, then streams that trainer's uploaded bf16 weights (and optionally
+// the fp32 master) out of the peer's HBM into a local staging slot with 16-byte P2P loads.
+// Every candidate is pulled exactly once per committee rank and as soon as ITS trainer is
+// done -- the validation GEMMs then read local memory instead of re-fetching each weight tile
+// over NVLink once per M-tile.
+__global__ void __launch_bounds__(256)
+k_pull(FedArgs f, uint4* stage_shadow, float4* stage_master) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  char* me = f.peers.base[f.rank];
+  const RoundState* st = at<RoundState>(me, f.lay.state_off);
+  const RoundPlan* plan = at<RoundPlan>(me, f.lay.plan_off);
+  if (!(st->role[f.rank] & ROLE_COMM)) return;
+  const int z = blockIdx.y;
+  if (z >= plan->n_cand) return;
+  const int t = plan->cand_rank[z];
+  const uint32_t epoch = st->epoch;
+  const uint32_t par = epoch & 1u;
+  if (threadIdx.x == 0)
+    ptx::wait_flag_ge(at<uint32_t>(me, f.lay.flags_off) + FLAG_TRAINED + t, epoch + 1);
+  __syncthreads();
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  {
+    const long long nv = f.lay.n_params / 8;  // 8 bf16 per 16 bytes
+    const uint4* src = at<const uint4>(f.peers.base[t], f.lay.upload_shadow_off[par]);
+    uint4* dst = stage_shadow + static_cast<long long>(z) * nv;
+    for (long long i = tid; i < nv; i += stride) {
+      const float4 v = ptx::ld_nc_f4(reinterpret_cast<const float4*>(src) + i);
+      dst[i] = *reinterpret_cast<const uint4*>(&v);
+    }
+  }
+  if (stage_master != nullptr) {
+    const long long nv = f.lay.n_params / 4;
+    const float4* src = at<const float4>(f.peers.base[t], f.lay.upload_master_off[par]);
+    float4* dst = stage_master + static_cast<long long>(z) * nv;
+    for (long long i = tid; i < nv; i += stride) dst[i] = ptx::ld_nc_f4(src + i);
+  }
+}
+
 int fed_grid(long long n_params) {
   long long blocks = (n_params / 4 + kFedThreads * 4 - 1) / (kFedThreads * 4);
   if (blocks > 148 * 4) blocks = 148 * 4;
@@ -442,11 +486,12 @@ int fed_grid(long long n_params) {
 }  // namespace
 
 cudaError_t fed_plan_round(const FedArgs& f, const PlanLayer* layers, int n_layers,
-                           int steps_per_round, cudaStream_t s) {
+                           int steps_per_round, int staged, cudaStream_t s) {
   if (n_layers > kMaxPlanLayers) return cudaErrorInvalidValue;
   PlanLayers pl{};
   pl.n = n_layers;
   pl.steps_per_round = steps_per_round;
+  pl.staged = staged;
   for (int i = 0; i < n_layers; ++i) pl.l[i] = layers[i];
   note_launch();
   return launch_pdl(k_plan, dim3(1), dim3(32), 0, s, f, pl);
@@ -466,6 +511,17 @@ cudaError_t fed_consensus_aggregate(const FedArgs& f, int n_val, int weight_by_s
   note_launch();
   return launch_pdl(k_consensus, dim3(fed_grid(work)), dim3(kFedThreads), 0, s, f, n_val,
                     weight_by_score, two_shot, use_multicast);
+}
+
+cudaError_t fed_pull_candidates(const FedArgs& f, void* stage_shadow, float* stage_master,
+                                cudaStream_t s) {
+  long long blocks = (f.lay.n_params / 8 + 256 * 4 - 1) / (256 * 4);
+  if (blocks > 74) blocks = 74;  // x kMaxRanks candidates in flight
+  if (blocks < 1) blocks = 1;
+  note_launch();
+  return launch_pdl(k_pull, dim3(static_cast<unsigned>(blocks), kMaxRanks), dim3(256), 0, s, f,
+                    reinterpret_cast<uint4*>(stage_shadow),
+                    reinterpret_cast<float4*>(stage_master));
 }
 
 cudaError_t fed_wait_trained(const FedArgs& f, cudaStream_t s) {

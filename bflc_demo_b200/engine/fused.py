@@ -138,8 +138,25 @@ class FusedEngine:
         # N-tile widths are pinned so the pre-encoded peer tensor maps match the launches
         self.val_bn = [self.mod.gemm_pick_bn(e1.shape[0], G.EPI_GENERIC, self.n_val, world),
                        self.mod.gemm_pick_bn(e2.shape[0], G.EPI_ARGMAX, self.n_val, world)]
+        # Two ways to feed the candidates' weights to the validation GEMMs:
+        #  staged (default): fed_pull_candidates streams each trainer's bf16 weights out of its
+        #    HBM once (as soon as that trainer's flag is up); the GEMM B maps cover the local
+        #    staging slots [layer][slot].
+        #  direct: the B maps cover the trainers' upload buffers [layer][parity][rank] and the
+        #    GEMM's TMA producer pulls tiles across NVLink itself -- no staging pass, but every
+        #    M-tile CTA re-reads the weights remotely (good only for few M-tiles).
+        self.staged = bool(cfg.stage_candidates) and world > 1
+        self.cand_shadow = torch.zeros(world, P, device=self.dev, dtype=torch.bfloat16)
         blob = bytearray(2 * 2 * K * 128)
         for layer, (e, kind) in enumerate(((e1, G.EPI_GENERIC), (e2, G.EPI_ARGMAX))):
+            if self.staged:
+                for zslot in range(world):
+                    base = self.cand_shadow.data_ptr() + (zslot * P + e.offset) * 2
+                    m = self.mod.gemm_b_map(base, e.shape[0], e.shape[1], e.shape[1], False, False,
+                                            kind, self.val_bn[layer])
+                    idx = layer * K + zslot
+                    blob[idx * 128:(idx + 1) * 128] = m
+                continue
             for par in range(2):
                 for r in range(world):
                     base = self.heap.peer_ptrs[r] + o[f"upload_shadow{par}"] + e.offset * 2
@@ -163,7 +180,7 @@ class FusedEngine:
     def _enqueue_round(self):
         m, cfg = self.mod, self.cfg
         n0 = m.launch_count()
-        m.fed_plan_round(self.fed, self.plan_layers, self.steps)
+        m.fed_plan_round(self.fed, self.plan_layers, self.steps, self.staged)
         m.cast_u8_to_bf16(self.x_u8, self.x_bf, 1.0 / 255.0)
         # local training, predicated on the trainer role bit
         m.set_predicate(self.is_trainer_ptr)
@@ -171,6 +188,8 @@ class FusedEngine:
         m.set_predicate(0)
         m.fed_upload(self.fed, self.S, self.steps * cfg.batch_size, self.byz, cfg.byzantine_scale)
         # committee validation: grouped GEMMs whose B operands are the trainers' uploads
+        if self.staged:
+            m.fed_pull_candidates(self.fed, self.cand_shadow, None)
         xv, yv = self.x_bf[: self.n_val], self.y[: self.n_val]
         H = cfg.hidden
         m.gemm(xv, self.work_shadow, self.h_val, self.n_val, H, self.in_dim, self.world,

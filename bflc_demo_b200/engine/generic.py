@@ -83,6 +83,7 @@ class GenericFedEngine:
         self.two_shot = cfg.two_shot if cfg.two_shot is not None else (P * 4 > (64 << 20) and world > 1)
         self.byz = 1 if rank in cfg.byzantine_ranks else 0
         self._peer_bounds = {}
+        self._stage = None
         if world > 1:
             dist.barrier(group=group)
         torch.cuda.synchronize()
@@ -109,16 +110,30 @@ class GenericFedEngine:
                                 0.999, 1e-8, i + 1, self.opt_step_ptr, 0, True)
 
     def validate(self, trainers: List[int], parity: int):
-        self.mod.fed_wait_trained(self.fed)
         xv, yv = self.x[: self.n_val], self.y[: self.n_val]
-        for z, t in enumerate(trainers):
-            cnt = self.net.correct(self.peer_bound(t, parity), xv, yv)
+        if self.cfg.stage_candidates and self.world > 1:
+            # one P2P pass per candidate (weights + fp32 master) into local staging, started per
+            # candidate as soon as its trainer's flag is up; the forward passes then read local HBM
+            if self._stage is None:
+                P = self.n_params
+                self._stage = (torch.empty(self.world, P, device=self.dev, dtype=torch.bfloat16),
+                               torch.empty(self.world, P, device=self.dev, dtype=torch.float32))
+                self._stage_bounds = [self.net.bind(self._stage[1][z], self._stage[0][z], None)
+                                      for z in range(self.world)]
+            self.mod.fed_pull_candidates(self.fed, self._stage[0], self._stage[1])
+            bounds = [self._stage_bounds[z] for z in range(len(trainers))]
+        else:
+            # direct: every GEMM of the forward pass TMA-loads its weight tiles from the peer
+            self.mod.fed_wait_trained(self.fed)
+            bounds = [self.peer_bound(t, parity) for t in trainers]
+        for z, b in enumerate(bounds):
+            cnt = self.net.correct(b, xv, yv)
             self.val_correct[z:z + 1].copy_(cnt)
 
     # ------------------------------------------------------------------ one round
     def run_round(self) -> dict:
         m, cfg = self.mod, self.cfg
-        m.fed_plan_round(self.fed, [], self.steps)
+        m.fed_plan_round(self.fed, [], self.steps, False)
         st = self.read_state()  # host learns roles/epoch (D2H of the 104-byte ledger page)
         role = st["roles"][self.rank]
         trainers = [r for r in range(self.world) if st["roles"][r] & ROLE_TRAINER]
