@@ -203,6 +203,29 @@ void Ledger::log(std::string s) {
   if (log_.size() < 4096) log_.push_back(std::move(s));
 }
 
+const MethodInfo* method_table(int* n) {
+  static const MethodInfo kTable[] = {
+      {Method::RegisterNode, "RegisterNode()", false},
+      {Method::QueryState, "QueryState()", true},
+      {Method::QueryGlobalModel, "QueryGlobalModel()", true},
+      {Method::UploadLocalUpdate, "UploadLocalUpdate(string,int256)", false},
+      {Method::UploadScores, "UploadScores(int256,string)", false},
+      {Method::QueryAllUpdates, "QueryAllUpdates()", true},
+  };
+  if (n) *n = 6;
+  return kTable;
+}
+
+Method method_from_signature(const std::string& s) {
+  int n = 0;
+  const MethodInfo* t = method_table(&n);
+  for (int i = 0; i < n; ++i) {
+    const std::string sig = t[i].signature;
+    if (s == sig || s == sig.substr(0, sig.find('('))) return t[i].id;
+  }
+  return Method::Unknown;
+}
+
 Status Ledger::RegisterNode(int client) {
   std::lock_guard<std::mutex> g(mu_);
   ++ctr_.calls;

@@ -96,6 +96,27 @@ struct OpCounters {  // replaces the gas meter (C:143,151,468-469,...) as plain 
            scores_rejected = 0, aggregations = 0, queries = 0;
 };
 
+// The contract's method table (reference: six Solidity signatures -> 4-byte selectors,
+// CommitteePrecompiled.cpp:46-52,122-130; interface stub python-sdk/contracts/
+// CommitteePrecompiled.sol:3-10).  Signatures are kept verbatim so external tooling written
+// against the reference ABI can address the same methods by name.
+enum class Method : int {
+  RegisterNode = 0,
+  QueryState = 1,
+  QueryGlobalModel = 2,
+  UploadLocalUpdate = 3,
+  UploadScores = 4,
+  QueryAllUpdates = 5,
+  Unknown = -1,  // C:312-318: unknown selector -> error
+};
+struct MethodInfo {
+  Method id;
+  const char* signature;  // e.g. "UploadLocalUpdate(string,int256)"
+  bool is_view;           // client.call (view) vs sendRawTransactionGetReceipt (tx)
+};
+const MethodInfo* method_table(int* n);
+Method method_from_signature(const std::string& signature_or_name);
+
 class Ledger {
  public:
   explicit Ledger(const LedgerConfig& cfg);

@@ -144,6 +144,17 @@ PYBIND11_MODULE(_ledger, m) {
       .def_static("restore", [](const py::bytes& b) { return Ledger::restore(std::string(b)); })
       .def("config", [](Ledger& L) { return L.config(); });
 
+  // ABI-style method table + dispatcher-by-signature (reference C:46-52, C:132-167, C:312-318)
+  m.def("method_table", [] {
+    int n = 0;
+    const MethodInfo* t = method_table(&n);
+    py::list out;
+    for (int i = 0; i < n; ++i)
+      out.append(py::make_tuple((int)t[i].id, std::string(t[i].signature), t[i].is_view));
+    return out;
+  });
+  m.def("method_from_signature", [](const std::string& s) { return (int)method_from_signature(s); });
+
   m.def("sha256_hex", [](const py::bytes& b) {
     std::string s = b;
     return hex(sha256(s.data(), s.size()));

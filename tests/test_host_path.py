@@ -158,3 +158,58 @@ def test_config_object():
         assert FLConfig.from_env(clients=8, needed_updates=5, aggregate_count=4).committee_size == 2
     finally:
         del os.environ["BFLC_COMMITTEE_SIZE"]
+
+
+def test_reference_call_surface_and_json_payloads():
+    """client.call / sendRawTransactionGetReceipt with the reference's JSON formats (M:106-228)."""
+    from bflc_demo_b200._native import ledger as _ledger
+    from bflc_demo_b200.protocol import abi
+    L = _ledger()
+    sigs = [s for _, s, _ in abi.methods()]
+    assert sigs == ["RegisterNode()", "QueryState()", "QueryGlobalModel()",
+                    "UploadLocalUpdate(string,int256)", "UploadScores(int256,string)", "QueryAllUpdates()"]
+    assert L.method_from_signature("NoSuch()") == -1
+    cfg = FLConfig.for_world(4)
+    led = L.Ledger(cfg.to_ledger_config(12))
+    cl = [abi.ContractClient(led, i) for i in range(4)]
+    for c in cl:
+        assert c.sendRawTransactionGetReceipt(abi.CONTRACT_ADDRESS, None, "RegisterNode", [])["status"] == "OK"
+    role, ep = cl[0].call(abi.CONTRACT_ADDRESS, None, "QueryState")
+    assert (role, ep) == ("comm", 0) and cl[3].call("", None, "QueryState")[0] == "trainer"
+    model, ep = cl[2].call("", None, "QueryGlobalModel")
+    m = abi.deserialize(model)
+    assert np.asarray(m["ser_W"]).shape == (5, 2) and len(m["ser_b"]) == 2     # H:31-34
+    assert cl[0].call("", None, "QueryAllUpdates")[0] == ""                    # C:304-307
+    for t in (2, 3):
+        upd = abi.pack_update(np.full((5, 2), t, np.float32), np.full(2, -t, np.float32), 100 * t, 0.5)
+        r = cl[t].sendRawTransactionGetReceipt("", None, "UploadLocalUpdate", [upd, 0])
+        assert r["status"] == "OK"
+    ups = abi.deserialize(cl[0].call("", None, "QueryAllUpdates")[0])
+    W, b, n, c = abi.unpack_update(ups["3"])
+    assert W.shape == (5, 2) and float(W[0, 0]) == 3 and float(b[0]) == -3 and n == 300
+    for c_ in (0, 1):
+        r = cl[c_].sendRawTransactionGetReceipt("", None, "UploadScores", [0, abi.serialize({"2": 0.9, "3": 0.4})])
+    assert r["status"] == "AGGREGATED"
+    model, ep = cl[0].call("", None, "QueryGlobalModel")
+    assert ep == 1
+    Wn = np.asarray(abi.deserialize(model)["ser_W"])
+    # global -= lr * sample-weighted mean of the top-2 deltas: (200*2 + 300*3)/500 = 2.6
+    np.testing.assert_allclose(Wn, -cfg.learning_rate * 2.6 * np.ones((5, 2)), rtol=1e-5)
+    with pytest.raises(ValueError):
+        cl[0].call("", None, "UploadScores")
+
+
+def test_account_generation_and_signed_requests(tmp_path):
+    from bflc_demo_b200.host import identity as I
+    addrs = I.generate_accounts(3, str(tmp_path))
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["node_0.pem", "node_1.pem", "node_2.pem"]
+    reg = I.AccountRegistry()
+    keys = [I.load_account(str(tmp_path), i) for i in range(3)]
+    for i, k in enumerate(keys):
+        assert reg.enroll(i, k.public_key()) == addrs[i]
+    msg = b"UploadScores|0|{...}"
+    assert reg.authenticate(addrs[1], msg, I.sign(keys[1], msg)) == 1
+    with pytest.raises(PermissionError):
+        reg.authenticate(addrs[1], msg, I.sign(keys[2], msg))       # wrong signer
+    with pytest.raises(PermissionError):
+        reg.authenticate("0xdead", msg, I.sign(keys[0], msg))
