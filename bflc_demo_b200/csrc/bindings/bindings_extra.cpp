@@ -175,6 +175,7 @@ void bind_extra(py::module_& m) {
   });
   m.def("set_predicate", [](int64_t ptr) { bflc::set_predicate(P<const int>(ptr)); });
   m.def("set_pdl", [](bool on) { bflc::set_pdl(on); });
+  m.def("pdl_fallbacks", [] { return bflc::pdl_fallbacks(); });
   m.def("set_debug_times", [](int64_t ptr) { bflc::set_debug_times(P<long long>(ptr)); });
   m.def("p2p_read_probe", [](int64_t src, int64_t dst, int64_t n_vec) {
     check(bflc::p2p_read_probe(P<const float4>(src), P<float4>(dst), n_vec, cur_stream()),

@@ -302,6 +302,7 @@ cudaError_t fed_wait_trained(const FedArgs& f, cudaStream_t s);
 void set_predicate(const int* pred);
 void set_pdl(bool on);   // programmatic dependent launch for all library kernels (default on)
 bool pdl_enabled();
+unsigned long long pdl_fallbacks();  // launches retried without the PDL attribute
 void set_debug_times(long long* dev_buf8);  // GEMM phase clock stamps of CTA (0,0,0)
 const int* current_predicate();
 

@@ -601,6 +601,9 @@ void note_launch() { ++g_launches; }
 static thread_local long long* g_dbg_times = nullptr;
 void set_debug_times(long long* p) { g_dbg_times = p; }
 static bool g_pdl = true;
+static unsigned long long g_pdl_fallbacks = 0;
+void note_pdl_fallback() { ++g_pdl_fallbacks; }
+unsigned long long pdl_fallbacks() { return g_pdl_fallbacks; }
 void set_pdl(bool on) { g_pdl = on; }
 bool pdl_enabled() { return g_pdl; }
 static thread_local const int* g_pred = nullptr;
