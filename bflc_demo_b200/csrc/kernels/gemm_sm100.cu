@@ -575,7 +575,17 @@ cudaError_t make_map(CUtensorMap* out, const GemmOperand& op, DType dt, int rows
   CUresult r = enc(out, cdt, 3, const_cast<void*>(op.ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+  if (r != CUDA_SUCCESS) {
+    std::fprintf(stderr,
+                 "[bflc] cuTensorMapEncodeTiled failed (CUresult %d): ptr=%p mn=%d dims={%llu,%llu,%llu} "
+                 "strides={%llu,%llu} box={%u,%u,%u} es=%d\n",
+                 static_cast<int>(r), op.ptr, op.mn_major ? 1 : 0,
+                 static_cast<unsigned long long>(dims[0]), static_cast<unsigned long long>(dims[1]),
+                 static_cast<unsigned long long>(dims[2]), static_cast<unsigned long long>(strides[0]),
+                 static_cast<unsigned long long>(strides[1]), box[0], box[1], box[2], es);
+    return cudaErrorInvalidValue;
+  }
+  return cudaSuccess;
 }
 
 template <int BN, int EPI>
@@ -626,11 +636,20 @@ int gemm_pick_bn(int N, EpiKind kind, int M, int z) {
 }
 
 cudaError_t gemm_make_b_map(const GemmProblem& p, CUtensorMap* out_host) {
+  (void)cudaFree(nullptr);  // make the primary context current on this thread
   const int BN = p.force_bn ? p.force_bn : gemm_pick_bn(p.N, p.epi.kind, p.M, p.batch);
   return make_map(out_host, p.b, p.ab_dtype, p.N, p.K, p.batch, BN);
 }
 
 cudaError_t gemm_sm100(const GemmProblem& p, cudaStream_t stream) {
+  // cuTensorMapEncodeTiled is a driver call and needs a context current on THIS thread; worker
+  // threads (e.g. PyTorch's autograd thread) may never have made a runtime call that binds the
+  // primary context (observed: CUDA_ERROR_INVALID_CONTEXT).  Bind it once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    (void)cudaFree(nullptr);
+    ctx_bound = true;
+  }
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.batch <= 0) return cudaErrorInvalidValue;
   const bool fp8 = p.ab_dtype == DType::FP8_E4M3;
   if (p.ab_dtype == DType::F32) return cudaErrorInvalidValue;
