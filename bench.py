@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--optimizer", default="sgd")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-fused-step", action="store_true", help="fused arm: one launch per GEMM instead of the persistent training kernel")
+    ap.add_argument("--no-stage", action="store_true", help="fused arm: validation GEMMs TMA-load peers' HBM directly")
     ap.add_argument("--broadcast", action="store_true", help="nccl arm: literal average+broadcast")
     return ap.parse_args()
 
@@ -132,7 +134,8 @@ def main():
     cfg = FLConfig.for_world(n, model="mlp", dataset="femnist", hidden=args.hidden,
                              batch_size=args.batch, samples_per_client=args.samples,
                              optimizer=args.optimizer, learning_rate=0.05, dtype="bf16",
-                             cuda_graph=not args.no_graph, ring_slots=1024)
+                             cuda_graph=not args.no_graph, ring_slots=1024,
+                             fused_step=not args.no_fused_step, stage_candidates=not args.no_stage)
     shard = femnist_like(n, args.samples, seed=7, only=rank)[0]
     # a small pool of distinct pinned input sets the e2e loop cycles through
     pool = [femnist_like(n, args.samples, seed=100 + i, only=rank)[0] for i in range(3)]
@@ -230,7 +233,8 @@ def main():
         extra = {"ledger_blocks": eng.host_ledger.n_blocks(), "ledger_mismatches": errs[:2],
                  "chain_ok": eng.host_ledger.verify_chain(), "epoch": st["epoch"],
                  "global_loss": st["global_loss"], "symm": eng.heap.describe(),
-                 "launches_per_round": eng.launches_per_round}
+                 "launches_per_round": eng.launches_per_round, "fused_step": eng.fused_step,
+                 "staged_validation": eng.staged}
         if n > 1:
             digs = [None] * n
             dist.all_gather_object(digs, st["model_digest"])

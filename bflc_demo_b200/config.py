@@ -48,6 +48,7 @@ class FLConfig:
     stage_candidates: bool = True     # committee pulls each candidate's weights once (P2P) vs
                                       # the validation GEMMs TMA-loading peers' HBM directly
     cuda_graph: bool = True
+    fused_step: bool = True           # MLP: all local steps of a round in one persistent kernel
     ring_slots: int = 256
 
     def validate(self) -> "FLConfig":

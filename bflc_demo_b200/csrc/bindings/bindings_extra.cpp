@@ -122,6 +122,7 @@ void bind_extra(py::module_& m) {
     d["plan_opt_step_off"] = offsetof(bflc::RoundPlan, opt_step);
     d["plan_is_trainer_off"] = offsetof(bflc::RoundPlan, is_trainer);
     d["plan_is_comm_off"] = offsetof(bflc::RoundPlan, is_comm);
+    d["plan_step_barrier_off"] = offsetof(bflc::RoundPlan, step_barrier);
     d["state_epoch_off"] = offsetof(bflc::RoundState, epoch);
     d["state_role_off"] = offsetof(bflc::RoundState, role);
     d["state_global_loss_off"] = offsetof(bflc::RoundState, global_loss);
@@ -187,6 +188,35 @@ void bind_extra(py::module_& m) {
   });
 
   // ------------------------------------------------------------ optimizers
+  // whole local-training pass of the 2-layer MLP in one persistent kernel
+  m.def("mlp_round", [](at::Tensor x, at::Tensor labels, at::Tensor master, at::Tensor shadow,
+                        at::Tensor grad, std::vector<int64_t> offs, at::Tensor h, at::Tensor dlogits,
+                        at::Tensor dh, at::Tensor loss_sum, at::Tensor correct, int64_t barrier_ptr,
+                        int batch, int steps, int in_dim, int hidden, int n_classes, double lr,
+                        bool adam, const OptT& mm, const OptT& vv, int64_t step_base_ptr) {
+    TORCH_CHECK(offs.size() == 4, "offs = element offsets of w1, b1, w2, b2 in the flat buffer");
+    bflc::MlpRoundArgs r;
+    r.batch = batch; r.steps = steps; r.in_dim = in_dim; r.hidden = hidden; r.n_classes = n_classes;
+    r.ncp = (int)dlogits.stride(0);
+    r.n_params = master.numel();
+    r.x = x.data_ptr(); r.labels = labels.data_ptr<int32_t>();
+    float* mp = master.data_ptr<float>(); float* gp = grad.data_ptr<float>();
+    auto* sp = reinterpret_cast<uint16_t*>(shadow.data_ptr());
+    r.master = mp; r.shadow = sp; r.grad = gp;
+    r.w1_shadow = sp + offs[0]; r.w2_shadow = sp + offs[2];
+    r.b1 = mp + offs[1]; r.b2 = mp + offs[3];
+    r.gw1 = gp + offs[0]; r.gb1 = gp + offs[1]; r.gw2 = gp + offs[2]; r.gb2 = gp + offs[3];
+    r.h = h.data_ptr(); r.dlogits = dlogits.data_ptr(); r.dh = dh.data_ptr();
+    r.loss_sum = loss_sum.data_ptr<float>();
+    r.correct = reinterpret_cast<unsigned int*>(correct.data_ptr());
+    r.barrier = P<unsigned int>(barrier_ptr);
+    r.adam = adam;
+    r.adam_m = mm.has_value() ? mm->data_ptr<float>() : nullptr;
+    r.adam_v = vv.has_value() ? vv->data_ptr<float>() : nullptr;
+    r.lr = (float)lr;
+    r.step_base = P<const int>(step_base_ptr);
+    check(bflc::mlp_round_sm100(r, cur_stream()), "mlp_round_sm100");
+  });
   m.def("optim_step",
         [](bool adam, at::Tensor master, at::Tensor grad, const OptT& shadow, const OptT& mm,
            const OptT& vv, double lr, double wd, double b1, double b2, double eps, int step,

@@ -75,6 +75,32 @@ struct GemmProblem {
 cudaError_t gemm_sm100(const GemmProblem& p, cudaStream_t stream);
 // Build the B-operand tensor map the kernel would use (for b_maps_dev arrays).
 cudaError_t gemm_make_b_map(const GemmProblem& p, CUtensorMap* out_host);
+// Encode the TMA descriptor of one GEMM operand (rows_tile = 128 for A, the N-tile for B).
+cudaError_t gemm_make_operand_map(CUtensorMap* out, const GemmOperand& op, DType dt,
+                                  int rows_extent, int K, int batch, int rows_tile);
+
+// Whole local-training pass of the 2-layer MLP in ONE persistent kernel (mlp_round_sm100.cu).
+struct MlpRoundArgs {
+  int batch = 0, steps = 0, in_dim = 0, hidden = 0, n_classes = 0, ncp = 0;
+  long long n_params = 0;
+  const void* x = nullptr;            // bf16 [steps*batch][in_dim]
+  const int32_t* labels = nullptr;    // [steps*batch]
+  float* master = nullptr;            // flat fp32 parameters (w1 | b1 | w2 | b2, 8-aligned)
+  void* shadow = nullptr;             // flat bf16 copy
+  float* grad = nullptr;              // flat fp32 gradients (zeroed; left zeroed)
+  const void* w1_shadow = nullptr; const void* w2_shadow = nullptr;
+  const float* b1 = nullptr; const float* b2 = nullptr;
+  float* gw1 = nullptr; float* gb1 = nullptr; float* gw2 = nullptr; float* gb2 = nullptr;
+  void* h = nullptr; void* dlogits = nullptr; void* dh = nullptr;   // bf16 scratch
+  float* loss_sum = nullptr; unsigned int* correct = nullptr;
+  unsigned int* barrier = nullptr;    // zero before launch
+  const int* pred = nullptr;          // null -> thread-local predicate
+  bool adam = false; float* adam_m = nullptr; float* adam_v = nullptr;
+  float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
+  const int* step_base = nullptr;
+};
+cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream);
+
 // N-tile width the launcher would choose for a problem (z = batch * split_k)
 int gemm_pick_bn(int N, EpiKind kind, int M, int z);
 // number of kernels launched by this library since process start (bench bookkeeping)
@@ -202,6 +228,8 @@ struct RoundPlan {
   unsigned int upload_blocks_done;
   unsigned int consensus_blocks_done;
   unsigned long long digest_acc;
+  unsigned int step_barrier;         // phase barrier of the persistent training kernel (zeroed per round)
+  unsigned int pad2;
 };
 
 struct PeerTable {

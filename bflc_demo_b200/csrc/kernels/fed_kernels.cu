@@ -89,6 +89,7 @@ __global__ void k_plan(FedArgs f, PlanLayers layers) {
   plan->upload_blocks_done = 0;
   plan->consensus_blocks_done = 0;
   plan->digest_acc = 0ull;
+  plan->step_barrier = 0u;
   plan->opt_step = plan->opt_total;
   if (plan->is_trainer) plan->opt_total += layers.steps_per_round;
 }

@@ -620,6 +620,11 @@ static thread_local const int* g_pred = nullptr;
 void set_predicate(const int* pred) { g_pred = pred; }
 const int* current_predicate() { return g_pred; }
 
+cudaError_t gemm_make_operand_map(CUtensorMap* out, const GemmOperand& op, DType dt,
+                                  int rows_extent, int K, int batch, int rows_tile) {
+  return make_map(out, op, dt, rows_extent, K, batch, rows_tile);
+}
+
 int gemm_pick_bn(int N, EpiKind kind, int M, int z) {
   if (kind != EpiKind::GENERIC) return N <= 64 ? 64 : (N <= 128 ? 128 : 256);
   // Largest tile that still yields ~a wave of CTAs; tiny problems take the narrowest tile so

@@ -169,6 +169,7 @@ class FusedEngine:
         self.dyn_ptr = [plan_ptr + sz["plan_dyn_off"] + i * sz["GemmDynamic"] for i in range(2)]
         self.two_shot = cfg.two_shot if cfg.two_shot is not None else (P * 4 > (64 << 20) and world > 1)
         self.byz = 1 if rank in cfg.byzantine_ranks else 0
+        self.fused_step = bool(cfg.fused_step) and self.trainer.fused_ok(self.steps)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.stream = torch.cuda.Stream(device=self.dev)
         self.launches_per_round = 0
@@ -184,7 +185,13 @@ class FusedEngine:
         m.cast_u8_to_bf16(self.x_u8, self.x_bf, 1.0 / 255.0)
         # local training, predicated on the trainer role bit
         m.set_predicate(self.is_trainer_ptr)
-        self.trainer.train_epoch(self.x_bf, self.y, self.steps)
+        if self.fused_step:
+            # every local step of the round inside ONE persistent kernel (phase barriers instead
+            # of launches); the barrier word lives in the plan and is zeroed by k_plan
+            self.trainer.train_epoch_fused(self.x_bf, self.y, self.steps,
+                                           self.plan_ptr + self.sz["plan_step_barrier_off"])
+        else:
+            self.trainer.train_epoch(self.x_bf, self.y, self.steps)
         m.set_predicate(0)
         m.fed_upload(self.fed, self.S, self.steps * cfg.batch_size, self.byz, cfg.byzantine_scale)
         # committee validation: grouped GEMMs whose B operands are the trainers' uploads

@@ -164,3 +164,38 @@ def test_mlp_training_step_matches_torch():
     for k, v in spec.views(master).items():
         assert rel(v, new_ref[k]) < 3e-3, k
     assert bool((grad == 0).all())
+
+
+@pytest.mark.parametrize("B,steps,opt", [(256, 3, "sgd"), (512, 4, "adam"), (200, 2, "sgd")])
+def test_persistent_round_kernel_matches_six_kernel_path(B, steps, opt):
+    """mlp_round_sm100.cu (one launch, grid barriers) vs the per-GEMM launches (models/mlp.py)."""
+    from bflc_demo_b200.models.mlp import FlatMLP, mlp_spec
+    torch.manual_seed(11)
+    spec = mlp_spec(784, 256, 62)
+    init = torch.empty(spec.total)
+    spec.init_(init, seed=2)
+    X = torch.rand(B * steps, 784, device="cuda").bfloat16()
+    Y = torch.randint(0, 62, (B * steps,), device="cuda", dtype=torch.int32)
+    outs = []
+    for fused in (False, True):
+        master = init.cuda().clone()
+        shadow = master.bfloat16()
+        grad = torch.zeros_like(master)
+        tr = FlatMLP(spec, master, shadow, grad, B, lr=0.05 if opt == "sgd" else 1e-3, optimizer=opt)
+        if fused:
+            assert tr.fused_ok(steps)
+            bar = torch.zeros(1, device="cuda", dtype=torch.int32)
+            tr.train_epoch_fused(X, Y, steps, bar.data_ptr())
+        else:
+            tr.train_epoch(X, Y, steps)
+        torch.cuda.synchronize()
+        outs.append((master.clone(), shadow.clone(), tr.loss_sum.item(), int(tr.correct.item()),
+                     float(grad.abs().max())))
+    (m0, s0, l0, c0, g0), (m1, s1, l1, c1, g1) = outs
+    assert g0 == 0 and g1 == 0                       # both leave the gradient buffer zeroed
+    assert abs(l0 - l1) / abs(l0) < 2e-3
+    assert abs(c0 - c1) <= max(2, 0.01 * B * steps)
+    v0, v1 = spec.views(m0), spec.views(m1)
+    for k in ("w1", "b1", "w2", "b2"):
+        assert rel(v1[k], v0[k]) < 3e-3, k
+    assert rel(s1.float(), s0.float()) < 5e-3
