@@ -115,6 +115,20 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("bias_ptrs") = py::none(), py::arg("dbg_lbo_a") = 0, py::arg("dbg_sbo_a") = 0,
         py::arg("dbg_lbo_b") = 0, py::arg("dbg_sbo_b") = 0, py::arg("dyn_ptr") = 0,
         py::arg("force_bn") = 0);
+  m.def("gemm2", [](const at::Tensor& a, const at::Tensor& b, at::Tensor d, int64_t M, int64_t N,
+                    int64_t K, int64_t lda, int64_t ldb, double alpha, const OptT& bias, int64_t act) {
+    bflc::GemmProblem p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.a = {raw(a), lda, 0, false};
+    p.b = {raw(b), ldb, 0, false};
+    p.epi.d = d.data_ptr();
+    p.epi.d_dtype = d.scalar_type() == at::kFloat ? bflc::DType::F32 : bflc::DType::BF16;
+    p.epi.ldd = d.stride(0);
+    p.epi.alpha = (float)alpha;
+    p.epi.bias = opt_ptr<const float>(bias);
+    p.epi.act = static_cast<bflc::Act>(act);
+    check(bflc::gemm2_sm100(p, cur_stream()), "gemm2_sm100");
+  });
   m.def("gemm_b_map", &gemm_b_map);
   m.def("gemm_pick_bn", [](int64_t N, int64_t kind, int64_t M, int64_t z) {
     return bflc::gemm_pick_bn((int)N, static_cast<bflc::EpiKind>(kind), (int)M, (int)z);

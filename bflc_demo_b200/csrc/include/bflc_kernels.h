@@ -71,8 +71,23 @@ struct GemmProblem {
   int force_bn = 0;  // 0 = heuristic; 64/128/256 pins the N-tile (must match pre-built b maps)
 };
 
+// cuTensorMapEncodeTiled is a driver call and needs a context current on the calling thread;
+// worker threads (e.g. PyTorch's autograd thread) may never have bound the primary context
+// (observed: CUDA_ERROR_INVALID_CONTEXT).  Bind it once per thread -- never again, because
+// cudaFree is illegal while a stream capture is active.
+inline void bind_context_once() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    (void)cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 // returns cudaSuccess or the failing status; throws nothing
 cudaError_t gemm_sm100(const GemmProblem& p, cudaStream_t stream);
+// 2-CTA variant (cta_group::2, 256x256 tiles per CTA pair): bf16, K-major operands, generic
+// bias/activation epilogue only; returns cudaErrorNotSupported for anything else.
+cudaError_t gemm2_sm100(const GemmProblem& p, cudaStream_t stream);
 // Build the B-operand tensor map the kernel would use (for b_maps_dev arrays).
 cudaError_t gemm_make_b_map(const GemmProblem& p, CUtensorMap* out_host);
 // Encode the TMA descriptor of one GEMM operand (rows_tile = 128 for A, the N-tile for B).

@@ -641,20 +641,13 @@ int gemm_pick_bn(int N, EpiKind kind, int M, int z) {
 }
 
 cudaError_t gemm_make_b_map(const GemmProblem& p, CUtensorMap* out_host) {
-  (void)cudaFree(nullptr);  // make the primary context current on this thread
+  bind_context_once();
   const int BN = p.force_bn ? p.force_bn : gemm_pick_bn(p.N, p.epi.kind, p.M, p.batch);
   return make_map(out_host, p.b, p.ab_dtype, p.N, p.K, p.batch, BN);
 }
 
 cudaError_t gemm_sm100(const GemmProblem& p, cudaStream_t stream) {
-  // cuTensorMapEncodeTiled is a driver call and needs a context current on THIS thread; worker
-  // threads (e.g. PyTorch's autograd thread) may never have made a runtime call that binds the
-  // primary context (observed: CUDA_ERROR_INVALID_CONTEXT).  Bind it once per thread.
-  static thread_local bool ctx_bound = false;
-  if (!ctx_bound) {
-    (void)cudaFree(nullptr);
-    ctx_bound = true;
-  }
+  bind_context_once();
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.batch <= 0) return cudaErrorInvalidValue;
   const bool fp8 = p.ab_dtype == DType::FP8_E4M3;
   if (p.ab_dtype == DType::F32) return cudaErrorInvalidValue;

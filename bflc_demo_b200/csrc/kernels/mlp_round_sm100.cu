@@ -488,7 +488,7 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
 }  // namespace
 
 cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
-  (void)cudaFree(nullptr);  // the TMA descriptor encoder needs a current context on this thread
+  bind_context_once();
   if (r.hidden % 8 || r.in_dim % 8 || r.n_params % 4 || r.batch % 8 || r.ncp % 8 || r.n_classes > 64)
     return cudaErrorInvalidValue;
   const int mt_b = (r.batch + kBM - 1) / kBM, nt_h = (r.hidden + kBN - 1) / kBN;

@@ -90,3 +90,16 @@ def gemm_argmax_acc(a: torch.Tensor, b: torch.Tensor, labels: torch.Tensor, corr
     C().gemm(a, b, None, M, n_classes, K, batch, a.stride(-2), b.stride(-2), a_bs, b_bs, False,
              False, is_fp8, EPI_ARGMAX, 1, 0, 0, alpha, bias, 0, None, None, 0, None, 1, False,
              labels, labels_bs, 1.0, None, correct, b_maps, None, 0, 0, 0, 0, dyn_ptr)
+
+
+def gemm_2cta(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *,
+              out_dtype: torch.dtype = torch.bfloat16, alpha: float = 1.0,
+              bias: Optional[torch.Tensor] = None, act: int = ACT_NONE) -> torch.Tensor:
+    """Large-problem path: CTA pairs (``tcgen05.mma.cta_group::2``, UMMA M = 256) computing
+    256 x 256 tiles; ``a`` [M, K] and ``b`` [N, K] bf16, K-major (csrc/kernels/gemm2_sm100.cu)."""
+    M, K = a.shape
+    N = b.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=out_dtype)
+    C().gemm2(a, b, out, M, N, K, a.stride(0), b.stride(0), alpha, bias, act)
+    return out

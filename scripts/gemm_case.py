@@ -109,6 +109,24 @@ def main():
         a, b = mk(8192, 8192), mk(8192, 8192)
         o = torch.empty(8192, 8192, device=dev, dtype=torch.bfloat16)
         for _ in range(5): G.gemm(a, b, out=o)
+    elif case == "perf2":
+        res = {}
+        for (M, N, K) in [(8192, 8192, 8192), (4096, 4096, 4096), (16384, 1024, 784), (32768, 768, 3072)]:
+            a, b = mk(M, K), mk(N, K)
+            o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            def t(fn):
+                for _ in range(3): fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10): fn()
+                e1.record(); torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / 10
+            m1 = t(lambda: G.gemm(a, b, out=o)); m2 = t(lambda: G.gemm_2cta(a, b, out=o))
+            m3 = t(lambda: torch.matmul(a, b.t(), out=o))
+            f = 2 * M * N * K / 1e9
+            res[f"{M}x{N}x{K}"] = {"1cta_tflops": f / m1, "2cta_tflops": f / m2, "cublas_tflops": f / m3}
+        out["perf2"] = res
     elif case == "elem":
         n = 100003
         x = torch.randn(n, device=dev)

@@ -199,3 +199,15 @@ def test_persistent_round_kernel_matches_six_kernel_path(B, steps, opt):
     for k in ("w1", "b1", "w2", "b2"):
         assert rel(v1[k], v0[k]) < 3e-3, k
     assert rel(s1.float(), s0.float()) < 5e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 512), (512, 768, 1024), (300, 500, 200)])
+def test_gemm_2cta(G, M, N, K):
+    """cta_group::2 kernel (CTA pairs, UMMA M = 256) against fp32 PyTorch."""
+    torch.manual_seed(9)
+    a, b = mk(M, K), mk(N, K)
+    bias = torch.randn(N, device="cuda")
+    d = G.gemm_2cta(a, b, out_dtype=torch.float32)
+    assert rel(d, a.float() @ b.float().t()) < 1e-5
+    d2 = G.gemm_2cta(a, b, bias=bias, act=G.ACT_RELU)
+    assert rel(d2, torch.relu(a.float() @ b.float().t() + bias)) < 4e-3
