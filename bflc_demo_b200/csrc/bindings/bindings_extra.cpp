@@ -175,6 +175,7 @@ void bind_extra(py::module_& m) {
     check(bflc::fed_wait_trained(make_fed(fd), cur_stream()), "fed_wait_trained");
   });
   m.def("set_predicate", [](int64_t ptr) { bflc::set_predicate(P<const int>(ptr)); });
+  m.def("current_predicate_is_null", [] { return bflc::current_predicate() == nullptr; });
   m.def("set_pdl", [](bool on) { bflc::set_pdl(on); });
   m.def("pdl_fallbacks", [] { return bflc::pdl_fallbacks(); });
   m.def("set_debug_times", [](int64_t ptr) { bflc::set_debug_times(P<long long>(ptr)); });

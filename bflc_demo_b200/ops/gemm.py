@@ -8,6 +8,7 @@ Reference parity: K1 ``tf.matmul(x, W) + b`` (python-sdk/main.py:120,180,293).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -17,6 +18,7 @@ from .._native import C
 EPI_GENERIC, EPI_XENT, EPI_ARGMAX = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 _DT = {torch.float32: 0, torch.bfloat16: 1, torch.float8_e4m3fn: 2}
+_GEMM2 = os.environ.get("BFLC_GEMM2", "1") != "0"   # route big K-major GEMMs to the CTA-pair kernel
 
 
 def _mat_dims(t: torch.Tensor, mn: bool):
@@ -57,6 +59,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
             out = torch.empty(shape, device=a.device, dtype=out_dtype)
     ldd = out.stride(-2)
     d_bs = out.stride(0) if out.dim() == 3 else 0
+    # Large plain K-major problems go to the CTA-pair kernel (cta_group::2, 256x256 tiles):
+    # the 1-CTA 128x256 tile is bound by the L2->SM feed rate, the pair moves 2/3 of the bytes.
+    if (_GEMM2 and not is_fp8 and not a_mn and not b_mn and nb == 1 and a.dim() == 2 and split_k == 1
+            and not accumulate and aux_out is None and aux_in is None and colsum is None
+            and b_maps is None and dyn_ptr == 0 and out.dtype in (torch.float32, torch.bfloat16)
+            and ldd % 4 == 0 and M >= 512 and N >= 512 and M * N >= (1 << 22)
+            and C().current_predicate_is_null()):
+        C().gemm2(a, b, out, M, N, K, lda, ldb, alpha, bias, act)
+        return out
     C().gemm(a, b, out, M, N, K, nb, lda, ldb, a_bs, b_bs, a_mn, b_mn, is_fp8, EPI_GENERIC,
              _DT[out.dtype], ldd, d_bs, alpha, bias, act, aux_out, aux_in, act_bwd, colsum,
              split_k, accumulate, None, 0, 1.0, None, None, b_maps, None, *dbg, dyn_ptr)
