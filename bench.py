@@ -235,6 +235,17 @@ def main():
                  "global_loss": st["global_loss"], "symm": eng.heap.describe(),
                  "launches_per_round": eng.launches_per_round, "fused_step": eng.fused_step,
                  "staged_validation": eng.staged}
+        # device-stamped phase breakdown (%globaltimer inside the fed kernels), median of 9 extra
+        # rounds per rank, then the max over ranks of each phase
+        samples = []
+        for _ in range(9):
+            sync_all()
+            eng.run_round()
+            samples.append(eng.read_stamps())
+        drain()
+        keys = sorted(samples[0])
+        med = [sorted(s[k] for s in samples)[len(samples) // 2] for k in keys]
+        extra["phases_us_max_over_ranks"] = {k: round(v, 2) for k, v in zip(keys, reduce_max(med))}
         if n > 1:
             digs = [None] * n
             dist.all_gather_object(digs, st["model_digest"])

@@ -123,6 +123,7 @@ void bind_extra(py::module_& m) {
     d["plan_is_trainer_off"] = offsetof(bflc::RoundPlan, is_trainer);
     d["plan_is_comm_off"] = offsetof(bflc::RoundPlan, is_comm);
     d["plan_step_barrier_off"] = offsetof(bflc::RoundPlan, step_barrier);
+    d["plan_stamps_off"] = offsetof(bflc::RoundPlan, t_stamp);
     d["state_epoch_off"] = offsetof(bflc::RoundState, epoch);
     d["state_role_off"] = offsetof(bflc::RoundState, role);
     d["state_global_loss_off"] = offsetof(bflc::RoundState, global_loss);

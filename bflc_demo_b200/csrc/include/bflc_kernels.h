@@ -245,6 +245,19 @@ struct RoundPlan {
   unsigned long long digest_acc;
   unsigned int step_barrier;         // phase barrier of the persistent training kernel (zeroed per round)
   unsigned int pad2;
+  // %globaltimer (ns) phase stamps of the current round, see StampSlot
+  unsigned long long t_stamp[8];
+};
+
+enum StampSlot : int {
+  STAMP_PLAN = 0,          // k_plan start
+  STAMP_UPLOAD_BEGIN = 1,  // local training finished, k_upload running
+  STAMP_UPLOAD_END = 2,    // flags released on every peer
+  STAMP_PULL_BEGIN = 3,    // committee: k_pull running (waits on trainers' flags)
+  STAMP_PULL_END = 4,      // last pull block done -> validation GEMMs may start
+  STAMP_CONS_BEGIN = 5,    // validation finished, k_consensus running
+  STAMP_CONS_SCORED = 6,   // all committee score rows + uploads visible
+  STAMP_CONS_END = 7,      // new global model published, FLAG_DONE released
 };
 
 struct PeerTable {

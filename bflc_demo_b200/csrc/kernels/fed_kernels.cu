@@ -45,6 +45,15 @@ struct PlanLayers {
   int staged;  // 1: validation B operands are the local staging slots filled by k_pull
 };
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void stamp(RoundPlan* plan, int slot) {
+  atomicMax(&plan->t_stamp[slot], globaltimer_ns());
+}
+
 __global__ void k_plan(FedArgs f, PlanLayers layers) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
@@ -52,6 +61,8 @@ __global__ void k_plan(FedArgs f, PlanLayers layers) {
   char* me = f.peers.base[f.rank];
   const RoundState* st = at<RoundState>(me, f.lay.state_off);
   RoundPlan* plan = at<RoundPlan>(me, f.lay.plan_off);
+  for (int i = 0; i < 8; ++i) plan->t_stamp[i] = 0;
+  plan->t_stamp[STAMP_PLAN] = globaltimer_ns();
   uint32_t* flags = at<uint32_t>(me, f.lay.flags_off);
   const uint32_t epoch = st->epoch;
   const uint32_t par = epoch & 1u;
@@ -103,6 +114,7 @@ k_upload(FedArgs f, int n_samples, int n_loss_terms, int byz_mode, float byz_sca
   const RoundState* st = at<RoundState>(me, f.lay.state_off);
   RoundPlan* plan = at<RoundPlan>(me, f.lay.plan_off);
   if (!(st->role[f.rank] & ROLE_TRAINER)) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) stamp(plan, STAMP_UPLOAD_BEGIN);
   const uint32_t epoch = st->epoch;
   const uint32_t par = epoch & 1u;
   const float4* wm = at<const float4>(me, f.lay.work_master_off);
@@ -148,6 +160,8 @@ k_upload(FedArgs f, int n_samples, int n_loss_terms, int byz_mode, float byz_sca
     ptx::st_release_sys(at<uint32_t>(f.peers.base[r], f.lay.flags_off) + FLAG_TRAINED + f.rank,
                         epoch + 1);
   }
+  __syncthreads();
+  if (threadIdx.x == 0) stamp(plan, STAMP_UPLOAD_END);
 }
 
 // --------------------------------------------------------------- consensus
@@ -180,6 +194,7 @@ k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc)
   const uint32_t par = epoch & 1u;
   const int n = f.n_ranks;
   const bool i_am_comm = (st->role[f.rank] & ROLE_COMM) != 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) stamp(plan, STAMP_CONS_BEGIN);
 
   // (a) committee: push my score row into every replica's ledger page, then release.
   if (blockIdx.x == 0 && i_am_comm) {
@@ -203,6 +218,7 @@ k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc)
     if (st->role[r] & ROLE_TRAINER) ptx::wait_flag_ge(flags + FLAG_TRAINED + r, epoch + 1);
   }
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) stamp(plan, STAMP_CONS_SCORED);
 
   // (c) consensus math, redundantly per block (tiny), identical on every rank
   if (threadIdx.x == 0) {
@@ -406,6 +422,7 @@ k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc)
   if (threadIdx.x < n)
     ptx::st_release_sys(
         at<uint32_t>(f.peers.base[threadIdx.x], f.lay.flags_off) + FLAG_DONE + f.rank, epoch + 1);
+  if (threadIdx.x == 0) stamp(plan, STAMP_CONS_END);
 }
 
 __global__ void k_p2p_read(const float4* __restrict__ src, float4* __restrict__ dst, long long n) {
@@ -448,10 +465,11 @@ k_pull(FedArgs f, uint4* stage_shadow, float4* stage_master) {
   ptx::pdl_wait();
   char* me = f.peers.base[f.rank];
   const RoundState* st = at<RoundState>(me, f.lay.state_off);
-  const RoundPlan* plan = at<RoundPlan>(me, f.lay.plan_off);
+  RoundPlan* plan = at<RoundPlan>(me, f.lay.plan_off);
   if (!(st->role[f.rank] & ROLE_COMM)) return;
   const int z = blockIdx.y;
   if (z >= plan->n_cand) return;
+  if (blockIdx.x == 0 && z == 0 && threadIdx.x == 0) stamp(plan, STAMP_PULL_BEGIN);
   const int t = plan->cand_rank[z];
   const uint32_t epoch = st->epoch;
   const uint32_t par = epoch & 1u;
@@ -475,6 +493,8 @@ k_pull(FedArgs f, uint4* stage_shadow, float4* stage_master) {
     float4* dst = stage_master + static_cast<long long>(z) * nv;
     for (long long i = tid; i < nv; i += stride) dst[i] = ptx::ld_nc_f4(src + i);
   }
+  __syncthreads();
+  if (threadIdx.x == 0) stamp(plan, STAMP_PULL_END);
 }
 
 int fed_grid(long long n_params) {

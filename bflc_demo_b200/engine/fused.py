@@ -266,6 +266,22 @@ class FusedEngine:
         return dict(epoch=epoch, roles=roles, median=med, selected_mask=sel, global_loss=loss,
                     model_digest=digest)
 
+    def read_stamps(self) -> dict:
+        """%globaltimer phase stamps (ns) of the LAST finished round on this rank, turned into
+        durations (us).  ``exposed_comm_us`` = upload + candidate pull + consensus/FedAvg/publish,
+        i.e. everything in the round that is neither local training nor the validation GEMMs."""
+        torch.cuda.synchronize()
+        raw = bytes(self.plan_bytes.cpu().numpy())
+        t = struct.unpack_from("<8Q", raw, self.sz["plan_stamps_off"])
+
+        def d(a, b):
+            return (t[b] - t[a]) / 1e3 if t[a] and t[b] and t[b] >= t[a] else 0.0
+        out = dict(train_us=d(0, 1) if t[1] else 0.0, upload_us=d(1, 2), pull_us=d(3, 4),
+                   validate_us=d(4, 5) if t[4] else 0.0, consensus_wait_us=d(5, 6),
+                   aggregate_publish_us=d(6, 7), round_us=d(0, 7))
+        out["exposed_comm_us"] = out["upload_us"] + out["pull_us"] + d(5, 7)
+        return out
+
     def drain_blocks(self) -> List[str]:
         """Pull finished BlockRecords off the device ring into the host C++ ledger, which
         re-executes each election.  Returns the list of mismatches ([] = replicas agree)."""
