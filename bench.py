@@ -245,7 +245,11 @@ def main():
         drain()
         keys = sorted(samples[0])
         med = [sorted(s[k] for s in samples)[len(samples) // 2] for k in keys]
-        extra["phases_us_max_over_ranks"] = {k: round(v, 2) for k, v in zip(keys, reduce_max(med))}
+        ph = {k: round(v, 2) for k, v in zip(keys, reduce_max(med))}
+        # BASELINE's second metric: the part of a round that is neither local training nor the
+        # committee's validation GEMMs (upload + pull + score exchange + FedAvg + publish + skew)
+        ph["exposed_comm_us"] = round(max(ph["round_us"] - ph["train_us"] - ph["validate_us"], 0.0), 2)
+        extra["phases_us_max_over_ranks"] = ph
         if n > 1:
             digs = [None] * n
             dist.all_gather_object(digs, st["model_digest"])

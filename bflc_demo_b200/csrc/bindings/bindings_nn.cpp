@@ -105,6 +105,36 @@ void bind_nn(py::module_& m) {
                                dz.has_value() ? dz->data_ptr() : nullptr, optp<float>(colsum), rows,
                                C, mode, st()), "act_bwd_colsum");
   });
+  // ---- block-scaled fp8 (MXFP8) ----
+  m.def("mx8_sf_bytes", [](int64_t rows, int64_t K) { return bflc::mx8_sf_bytes((int)rows, (int)K); });
+  m.def("quantize_mx8", [](at::Tensor x, at::Tensor q, at::Tensor sf, int64_t R, int64_t K,
+                           double in_scale) {
+    bflc::DType dt = x.scalar_type() == at::kFloat      ? bflc::DType::F32
+                     : x.scalar_type() == at::kBFloat16 ? bflc::DType::BF16
+                                                        : bflc::DType::U8;
+    TORCH_CHECK(x.scalar_type() == at::kFloat || x.scalar_type() == at::kBFloat16 ||
+                    x.scalar_type() == at::kByte, "quantize_mx8: f32 / bf16 / u8 input");
+    TORCH_CHECK(x.stride(-1) == 1 && q.stride(-1) == 1, "quantize_mx8: contiguous rows");
+    TORCH_CHECK(sf.numel() >= bflc::mx8_sf_bytes((int)R, (int)K), "quantize_mx8: sf buffer too small");
+    check(bflc::quantize_mx8(x.data_ptr(), dt, x.stride(0), (int)R, (int)K, (float)in_scale,
+                             q.data_ptr(), q.stride(0), sf.data_ptr(), st()), "quantize_mx8");
+  });
+  m.def("gemm_mx8", [](at::Tensor a, at::Tensor sfa, at::Tensor b, at::Tensor sfb, at::Tensor d,
+                       int64_t M, int64_t N, int64_t K, double alpha, const OptT& bias, int64_t act) {
+    bflc::Mx8Problem p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.a = a.data_ptr(); p.lda = a.stride(0); p.sfa = static_cast<const uint8_t*>(sfa.data_ptr());
+    p.b = b.data_ptr(); p.ldb = b.stride(0); p.sfb = static_cast<const uint8_t*>(sfb.data_ptr());
+    TORCH_CHECK(sfa.numel() >= bflc::mx8_sf_bytes(p.M, p.K) && sfb.numel() >= bflc::mx8_sf_bytes(p.N, p.K),
+                "gemm_mx8: scale-factor buffers too small");
+    p.d = d.data_ptr();
+    p.d_dtype = d.scalar_type() == at::kFloat ? bflc::DType::F32 : bflc::DType::BF16;
+    p.ldd = d.stride(0);
+    p.alpha = (float)alpha;
+    p.bias = optp<const float>(bias);
+    p.act = static_cast<bflc::Act>(act);
+    check(bflc::gemm_mx8_sm100(p, st()), "gemm_mx8_sm100");
+  });
   m.def("transpose_0213", [](at::Tensor x, at::Tensor y, int d0, int d1, int d2, int d3) {
     check(bflc::transpose_0213_bf16(x.data_ptr(), y.data_ptr(), d0, d1, d2, d3, st()),
           "transpose_0213");

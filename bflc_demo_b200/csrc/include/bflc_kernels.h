@@ -15,7 +15,7 @@
 
 namespace bflc {
 
-enum class DType : int { F32 = 0, BF16 = 1, FP8_E4M3 = 2 };
+enum class DType : int { F32 = 0, BF16 = 1, FP8_E4M3 = 2, U8 = 3 };
 enum class Act : int { NONE = 0, RELU = 1, GELU = 2 };
 enum class EpiKind : int { GENERIC = 0, XENT = 1, ARGMAX_ACC = 2 };
 
@@ -88,6 +88,21 @@ cudaError_t gemm_sm100(const GemmProblem& p, cudaStream_t stream);
 // 2-CTA variant (cta_group::2, 256x256 tiles per CTA pair): bf16, K-major operands, generic
 // bias/activation epilogue only; returns cudaErrorNotSupported for anything else.
 cudaError_t gemm2_sm100(const GemmProblem& p, cudaStream_t stream);
+// Block-scaled fp8 (MXFP8: e4m3 + one UE8M0 scale per 32 K-elements), K-major A [M,K] and
+// B [N,K]; sfa/sfb are the chunk arrays written by quantize_mx8 (csrc/kernels/gemm_mx8_sm100.cu).
+struct Mx8Problem {
+  int M = 0, N = 0, K = 0;
+  const void* a = nullptr; long long lda = 0; const uint8_t* sfa = nullptr;
+  const void* b = nullptr; long long ldb = 0; const uint8_t* sfb = nullptr;
+  void* d = nullptr; DType d_dtype = DType::BF16; long long ldd = 0;
+  float alpha = 1.f; const float* bias = nullptr; Act act = Act::NONE;
+};
+cudaError_t gemm_mx8_sm100(const Mx8Problem& p, cudaStream_t stream);
+// bytes of the scale-factor chunk array for a [rows, K] operand
+long long mx8_sf_bytes(int rows, int K);
+// x [R, K] (f32 / bf16 / u8, row pitch ldx elements) * in_scale -> q e4m3 [R, ldq] + scale chunks
+cudaError_t quantize_mx8(const void* x, DType x_dtype, long long ldx, int R, int K, float in_scale,
+                         void* q, long long ldq, void* sf, cudaStream_t stream);
 // Build the B-operand tensor map the kernel would use (for b_maps_dev arrays).
 cudaError_t gemm_make_b_map(const GemmProblem& p, CUtensorMap* out_host);
 // Encode the TMA descriptor of one GEMM operand (rows_tile = 128 for A, the N-tile for B).

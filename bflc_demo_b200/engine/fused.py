@@ -279,7 +279,9 @@ class FusedEngine:
         out = dict(train_us=d(0, 1) if t[1] else 0.0, upload_us=d(1, 2), pull_us=d(3, 4),
                    validate_us=d(4, 5) if t[4] else 0.0, consensus_wait_us=d(5, 6),
                    aggregate_publish_us=d(6, 7), round_us=d(0, 7))
-        out["exposed_comm_us"] = out["upload_us"] + out["pull_us"] + d(5, 7)
+        # pull_us on a committee rank includes waiting for the trainers' flags (it starts with
+        # the round); the exposed part is what is left of the round after compute
+        out["exposed_comm_us"] = max(out["round_us"] - out["train_us"] - out["validate_us"], 0.0)
         return out
 
     def drain_blocks(self) -> List[str]:

@@ -122,11 +122,52 @@ def main():
                 for _ in range(10): fn()
                 e1.record(); torch.cuda.synchronize()
                 return e0.elapsed_time(e1) / 10
-            m1 = t(lambda: G.gemm(a, b, out=o)); m2 = t(lambda: G.gemm_2cta(a, b, out=o))
+            G._GEMM2 = False                       # force the 1-CTA kernel for the comparison
+            m1 = t(lambda: G.gemm(a, b, out=o))
+            G._GEMM2 = True
+            m2 = t(lambda: G.gemm_2cta(a, b, out=o))
             m3 = t(lambda: torch.matmul(a, b.t(), out=o))
             f = 2 * M * N * K / 1e9
             res[f"{M}x{N}x{K}"] = {"1cta_tflops": f / m1, "2cta_tflops": f / m2, "cublas_tflops": f / m3}
         out["perf2"] = res
+    elif case == "perf3":      # block-scaled fp8 vs per-tensor fp8 vs bf16 CTA-pair vs cuBLAS bf16
+        from bflc_demo_b200.ops.mx8 import gemm_mx8, quantize_mx8
+        res = {}
+        for (M, N, K) in [(8192, 8192, 8192), (4096, 4096, 4096), (16384, 1024, 1024), (4096, 256, 784)]:
+            a, b = mk(M, K), mk(N, K)
+            qa, qb = quantize_mx8(a), quantize_mx8(b)
+            fa, fb = a.to(torch.float8_e4m3fn), b.to(torch.float8_e4m3fn)
+            o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            def t(fn):
+                for _ in range(3): fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10): fn()
+                e1.record(); torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / 10
+            f = 2 * M * N * K / 1e9
+            res[f"{M}x{N}x{K}"] = {
+                "mx8_tflops": f / t(lambda: gemm_mx8(qa, qb, out=o)),
+                "fp8_pertensor_tflops": f / t(lambda: G.gemm(fa, fb, out=o)),
+                "bf16_tflops": f / t(lambda: G.gemm(a, b, out=o)),
+                "cublas_bf16_tflops": f / t(lambda: torch.matmul(a, b.t(), out=o)),
+                "quantize_a_us": 1e3 * t(lambda: quantize_mx8(a, out=qa)),
+                "mx8_err_vs_bf16": rel_err(gemm_mx8(qa, qb, out_dtype=torch.float32), a.float() @ b.float().t())}
+        out["perf3"] = res
+    elif case.startswith("ncu_"):   # a few launches of one kernel for an ncu --set full capture
+        from bflc_demo_b200.ops.mx8 import gemm_mx8, quantize_mx8
+        a, b = mk(8192, 8192), mk(8192, 8192)
+        o = torch.empty(8192, 8192, device=dev, dtype=torch.bfloat16)
+        if case == "ncu_2cta":
+            for _ in range(3): G.gemm_2cta(a, b, out=o)
+        elif case == "ncu_1cta":
+            import bflc_demo_b200.ops.gemm as GG
+            GG._GEMM2 = False
+            for _ in range(3): G.gemm(a, b, out=o)
+        elif case == "ncu_mx8":
+            qa, qb = quantize_mx8(a), quantize_mx8(b)
+            for _ in range(3): gemm_mx8(qa, qb, out=o)
     elif case == "elem":
         n = 100003
         x = torch.randn(n, device=dev)
