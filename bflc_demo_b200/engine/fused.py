@@ -277,7 +277,9 @@ class FusedEngine:
         def d(a, b):
             return (t[b] - t[a]) / 1e3 if t[a] and t[b] and t[b] >= t[a] else 0.0
         out = dict(train_us=d(0, 1) if t[1] else 0.0, upload_us=d(1, 2), pull_us=d(3, 4),
-                   validate_us=d(4, 5) if t[4] else 0.0, consensus_wait_us=d(5, 6),
+                   # direct (unstaged) validation has no pull stamps: it starts after the upload
+                   validate_us=d(4, 5) if t[4] else (d(2, 5) if t[2] else 0.0),
+                   consensus_wait_us=d(5, 6),
                    aggregate_publish_us=d(6, 7), round_us=d(0, 7))
         # pull_us on a committee rank includes waiting for the trainers' flags (it starts with
         # the round); the exposed part is what is left of the round after compute

@@ -38,6 +38,9 @@ class GenericFedEngine:
         torch.cuda.set_device(device)
         self.dev = torch.device("cuda", device)
         self.mod = C()
+        # cfg.dtype "fp8": forward GEMMs of Linear / Conv2d run block-scaled fp8 (ops/mx8.py)
+        from ..ops import nn as _nn
+        _nn.set_precision("mx8" if cfg.dtype == "fp8" else "bf16")
         self.sz = sz = self.mod.struct_sizes()
         self.spec = net.spec
         P = self.n_params = net.spec.total

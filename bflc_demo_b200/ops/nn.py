@@ -22,6 +22,48 @@ from . import gemm as G
 
 BF = torch.bfloat16
 
+# Forward-GEMM precision of Linear / Conv2d: "bf16" (kind::f16) or "mx8" (block-scaled fp8,
+# kind::mxf8f6f4.block_scale: activations and weights are quantised to e4m3 with one UE8M0
+# scale per 32 K-elements right before the GEMM).  Backward GEMMs stay bf16 on the saved bf16
+# operands (forward-fp8 / backward-bf16 recipe); master weights, gradients and optimizer fp32.
+_PRECISION = "bf16"
+_MX_BUF: dict = {}
+
+
+def set_precision(p: str) -> str:
+    """-> the previous setting."""
+    global _PRECISION
+    if p not in ("bf16", "mx8"):
+        raise ValueError("precision must be 'bf16' or 'mx8'")
+    prev, _PRECISION = _PRECISION, p
+    return prev
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def _mx_quant(tag: str, t: torch.Tensor):
+    from .mx8 import MX8, quantize_mx8
+    R, K = t.shape
+    key = (tag, R, K, t.device.index)
+    buf = _MX_BUF.get(key)
+    if buf is None:
+        ld = (K + 15) // 16 * 16
+        buf = MX8(torch.zeros(R, ld, device=t.device, dtype=torch.float8_e4m3fn),
+                  torch.empty(C().mx8_sf_bytes(R, K), device=t.device, dtype=torch.uint8), R, K)
+        _MX_BUF[key] = buf
+    return quantize_mx8(t, out=buf)
+
+
+def _fwd_gemm(x, w, y, bias, act, pre):
+    """y = act(x @ w^T + bias) in the configured forward precision."""
+    if _PRECISION == "mx8" and act != G.ACT_GELU and y.stride(0) % 4 == 0:
+        from .mx8 import gemm_mx8
+        gemm_mx8(_mx_quant("x", x), _mx_quant("w", w), out=y, bias=bias, act=act)
+    else:
+        G.gemm(x, w, out=y, bias=bias, act=act, aux_out=pre)
+
 
 def _split_k(out_rows: int, out_cols: int, k: int) -> int:
     """Split the reduction when a weight-gradient GEMM has few output tiles but a long K."""
@@ -49,7 +91,7 @@ class LinearFn(Function):
         M, N = x.shape[0], w.shape[0]
         y = torch.empty(M, N, device=x.device, dtype=BF)
         pre = torch.empty_like(y) if act == G.ACT_GELU else None
-        G.gemm(x, w, out=y, bias=b, act=act, aux_out=pre)
+        _fwd_gemm(x, w, y, b, act, pre)
         ctx.save_for_backward(x, w, y if act == G.ACT_RELU else pre)
         ctx.gw, ctx.gb, ctx.act = gw, gb, act
         return y
@@ -123,7 +165,7 @@ class Conv2dFn(Function):
         C().im2col(x, col, N, Cin, H, W, kh, kw, stride, pad, OH, OW)
         y = torch.empty(rows, Cout, device=x.device, dtype=BF)
         pre = torch.empty_like(y) if act == G.ACT_GELU else None
-        G.gemm(col, w, out=y, bias=b, act=act, aux_out=pre)
+        _fwd_gemm(col, w, y, b, act, pre)
         ctx.save_for_backward(col, w, y if act == G.ACT_RELU else pre)
         ctx.gw, ctx.gb, ctx.act = gw, gb, act
         ctx.geom = (N, Cin, H, W, kh, kw, stride, pad, OH, OW)

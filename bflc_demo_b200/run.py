@@ -39,6 +39,9 @@ def main(argv=None):
     ap.add_argument("--checkpoint", default="")
     ap.add_argument("--resume", default="")
     ap.add_argument("--no-stage", action="store_true", help="validate straight out of peers' HBM")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"],
+                    help="fp8: block-scaled (MXFP8) forward GEMMs; routes the MLP through the generic engine")
+    ap.add_argument("--generic", action="store_true", help="run the MLP through GenericFedEngine")
     a = ap.parse_args(argv)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -53,7 +56,7 @@ def main(argv=None):
     S, B, LR = a.samples or defaults[0], a.batch or defaults[1], a.lr or defaults[2]
     cfg = FLConfig.for_world(world, model=a.model, batch_size=B, samples_per_client=S,
                              learning_rate=LR, optimizer=a.optimizer, byzantine_ranks=a.byzantine,
-                             stage_candidates=not a.no_stage, ring_slots=1024)
+                             stage_candidates=not a.no_stage, ring_slots=1024, dtype=a.dtype)
     if a.model == "mlp":
         shard = femnist_like(world, S, seed=7, only=rank)[0]
         test = femnist_like(1, 2048, seed=7, only=0)[0]
@@ -64,7 +67,7 @@ def main(argv=None):
         shard = tokens_like(world, S, seed=7)[rank]
         test = tokens_like(1, 128, seed=8)[0]
 
-    if a.model == "mlp":
+    if a.model == "mlp" and a.dtype == "bf16" and not a.generic:
         from .engine.fused import FusedEngine
         eng = FusedEngine(cfg, shard, rank=rank, world=world, device=lr_)
         eng.capture()

@@ -221,3 +221,31 @@ def test_bert_small_trains():
     assert losses[-1] < losses[0]
     full = BertBase(2)
     assert 1.05e8 < full.spec.total < 1.15e8  # BERT-base parameter count
+
+
+def test_mx8_forward_precision_linear_and_models(F):
+    """Block-scaled fp8 forward (tcgen05 kind::mxf8f6f4.block_scale) behind ops.nn: the layer
+    output tracks the bf16 layer, backward still produces bf16-path gradients, and the MLP /
+    LeNet-5 configs BASELINE.json names as fp8 train."""
+    from bflc_demo_b200.models.nets import LeNet5, MLPNet
+    from bflc_demo_b200.ops import gemm as G
+    torch.manual_seed(9)
+    x = _leaf(256, 784)
+    w = (torch.randn(256, 784, device="cuda") * 0.05).to(BF)
+    b = torch.randn(256, device="cuda") * 0.1
+    gw, gb = torch.zeros(256, 784, device="cuda"), torch.zeros(256, device="cuda")
+    y_bf = F.linear(x, w, b, None, None, G.ACT_RELU).detach()
+    prev = F.set_precision("mx8")
+    try:
+        assert prev == "bf16" and F.get_precision() == "mx8"
+        y = F.linear(x, w, b, gw, gb, G.ACT_RELU)
+        assert rel(y, y_bf) < 0.05
+        y.backward(torch.randn_like(y))
+        assert float(gw.abs().sum()) > 0 and x.grad is not None
+        for net, xr, ncls in ((MLPNet(784, 256, 62), torch.randint(0, 255, (256, 784), device="cuda", dtype=torch.uint8), 62),
+                              (LeNet5(10), torch.randint(0, 255, (64, 3, 32, 32), device="cuda", dtype=torch.uint8), 10)):
+            yl = torch.randint(0, ncls, (xr.shape[0],), device="cuda", dtype=torch.int32)
+            losses, master, shadow = _train_steps(net, net.preprocess(xr), yl, steps=8, lr=0.05)
+            assert losses[-1] < losses[0]
+    finally:
+        F.set_precision("bf16")
