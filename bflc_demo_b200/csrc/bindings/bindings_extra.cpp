@@ -219,6 +219,21 @@ void bind_extra(py::module_& m) {
     r.step_base = P<const int>(step_base_ptr);
     check(bflc::mlp_round_sm100(r, cur_stream()), "mlp_round_sm100");
   });
+  // committee validation of every candidate in one launch (fwd1 -> relu -> fwd2 -> argmax)
+  m.def("mlp_val", [](at::Tensor x, at::Tensor labels, at::Tensor correct, at::Tensor maps,
+                      int64_t dyn1_ptr, int64_t dyn2_ptr, int n_val, int in_dim, int hidden,
+                      int n_classes, int max_cand) {
+    bflc::MlpValArgs r;
+    r.n_val = n_val; r.in_dim = in_dim; r.hidden = hidden; r.n_classes = n_classes;
+    r.max_cand = max_cand;
+    r.x = x.data_ptr(); r.ldx = x.stride(0);
+    r.maps = reinterpret_cast<const CUtensorMap*>(maps.data_ptr());
+    r.dyn1 = P<const bflc::GemmDynamic>(dyn1_ptr);
+    r.dyn2 = P<const bflc::GemmDynamic>(dyn2_ptr);
+    r.labels = labels.data_ptr<int32_t>();
+    r.correct = reinterpret_cast<unsigned int*>(correct.data_ptr());
+    check(bflc::mlp_val_sm100(r, cur_stream()), "mlp_val_sm100");
+  });
   m.def("optim_step",
         [](bool adam, at::Tensor master, at::Tensor grad, const OptT& shadow, const OptT& mm,
            const OptT& vv, double lr, double wd, double b1, double b2, double eps, int step,

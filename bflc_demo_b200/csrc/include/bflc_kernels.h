@@ -131,6 +131,21 @@ struct MlpRoundArgs {
 };
 cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream);
 
+// Committee validation of up to max_cand candidates in one launch (hidden == 256, classes <= 64):
+// per (128 rows, candidate) CTA  relu(x W1_z^T + b1_z) W2_z^T + b2_z -> argmax == label -> correct[z].
+// `maps` is the device tensor-map table the round plan indexes (layer-1 maps encoded with a
+// 256-row box, layer-2 maps with a 64-row box); dyn1/dyn2 are the plan's per-layer GemmDynamic.
+struct GemmDynamic;
+struct MlpValArgs {
+  int n_val = 0, in_dim = 0, hidden = 0, n_classes = 0, max_cand = 0;
+  const void* x = nullptr; long long ldx = 0;     // bf16 [n_val][in_dim]
+  const CUtensorMap* maps = nullptr;
+  const GemmDynamic* dyn1 = nullptr; const GemmDynamic* dyn2 = nullptr;
+  const int32_t* labels = nullptr; unsigned int* correct = nullptr;
+  const int* pred = nullptr;
+};
+cudaError_t mlp_val_sm100(const MlpValArgs& r, cudaStream_t stream);
+
 // N-tile width the launcher would choose for a problem (z = batch * split_k)
 int gemm_pick_bn(int N, EpiKind kind, int M, int z);
 // number of kernels launched by this library since process start (bench bookkeeping)

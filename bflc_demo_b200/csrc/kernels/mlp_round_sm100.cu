@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "bflc_kernels.h"
@@ -33,21 +34,39 @@ namespace {
 constexpr int kBM = 128, kBN = 64, kStages = 8;
 constexpr int kABytes = kBM * 128, kBBytes = kBN * 128, kStageBytes = kABytes + kBBytes;
 constexpr int kTileBytes = kStages * kStageBytes;
-constexpr int kBarBytes = 256;
+constexpr int kBarBytes = 512;
 constexpr int kStgLd = 36;
 constexpr int kStgBytes = 4 * 32 * kStgLd * 4;
-constexpr int kSmemTotal = kTileBytes + kBarBytes + kStgBytes + kBN * 4 + 1024;
+constexpr int kBiasFloats = 320;   // chain: b1[256] | b2[64]; tile jobs use the first kBN
+constexpr int kSmemTotal = kTileBytes + kBarBytes + kStgBytes + kBiasFloats * 4 + 1024;
 constexpr int kThreads = 192;
 constexpr int kGrid = 32;
 
-enum EpiMode : int { E_BIAS_RELU_BF16 = 0, E_XENT = 1, E_F32 = 2, E_MASK_COLSUM_BF16 = 3 };
+// ---- fused chain (hidden == 256): the same 192 KB of ring memory, re-cut as
+//   3 stages x (x tile 16 KB + W1 tile 32 KB) for fwd1, then after fwd1 has retired
+//   [0, 64 KB) h as fwd2's A operand | [96, 128 KB) W2 MN-major (dh's B) | [128, 144 KB) dlogits
+//   (dh's A), and a dedicated [144, 176 KB) W2 K-major (fwd2's B) loaded up front.
+constexpr int kCStages = 3;
+constexpr int kCA = kBM * 128, kCB = 256 * 128, kCStage = kCA + kCB;
+constexpr int kOffH = 0;
+constexpr int kOffW2MN = 2 * kCStage;
+constexpr int kOffDL = kOffW2MN + 32768;
+constexpr int kOffW2K = kCStages * kCStage;
+static_assert(kOffDL + 16384 <= kOffW2K && kOffW2K + 32768 <= kTileBytes, "chain smem layout");
+constexpr int kChainH = 256;
+constexpr int kTmemCols = 512;     // chain: h / dh accumulator [0,256) + logits [256,320)
 
-struct Maps {  // 10 TMA descriptors, all bf16, SWIZZLE_128B
+enum EpiMode : int { E_BIAS_RELU_BF16 = 0, E_XENT = 1, E_F32 = 2, E_MASK_COLSUM_BF16 = 3,
+                     E_OPT = 4 };  // E_OPT: the tile IS the gradient -> optimizer applied in the epilogue
+
+struct Maps {  // 11 TMA descriptors, all bf16, SWIZZLE_128B
   CUtensorMap x_k, w1_k, h_k, w2_k, dl_mn, h_mn, dl_k, w2_mn, dh_mn, x_mn;
+  CUtensorMap w1_k256;   // W1 with a 256-row box (chain: the whole hidden width in one tile)
 };
 
 struct Args {
   int B, steps, in_dim, hidden, n_classes, ncp;  // ncp = dlogits row stride (padded classes)
+  int chain;                     // 1: fwd1 -> xent -> dh fused per 128-row tile (chain_* below)
   long long n_params;
   const int* pred;               // whole kernel is a no-op when *pred == 0 (non-trainer rank)
   unsigned int* barrier;         // device-wide phase barrier counter (zeroed before launch)
@@ -77,11 +96,21 @@ struct Job {  // one 128 x 64 output tile
   float* colsum;
   const int32_t* labels;        // E_XENT (already offset to this step's rows)
   float grad_scale;
+  float bc1, bc2;               // E_OPT + Adam: bias corrections of this step
 };
 
 struct Pipe {  // persistent pipeline state of one role
   uint32_t it;    // K-blocks processed so far (ring slot / parity)
   uint32_t tile;  // tiles processed so far (accumulator barrier parity)
+};
+struct ChainBars {
+  uint64_t* full; uint64_t* empty;   // [kCStages] fwd1 ring
+  uint64_t* w2k; uint64_t* w2mn;     // W2 operand tiles landed
+  uint64_t* acc_h; uint64_t* h_ready; uint64_t* acc_l; uint64_t* dl_ready; uint64_t* acc_dh;
+};
+struct CPipe {
+  uint32_t it;   // fwd1 K-blocks processed (ring slot / parity)
+  uint32_t n;    // chains processed (parity of the once-per-chain barriers)
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -160,6 +189,55 @@ __device__ __forceinline__ void mma_tile(const Job& j, uint8_t* smem, uint64_t* 
   ++pp.tile;
 }
 
+// SGD / Adam on n (<= 4) consecutive parameters starting at flat index pi, gradient in g[]:
+// fp32 master, bf16 shadow (and the Adam moments) are updated in place.  Coherent loads: other
+// CTAs of this kernel wrote these buffers in earlier phases.
+__device__ __forceinline__ void opt_apply(const Args& a, long long pi, int n, const float* g,
+                                          float bc1, float bc2) {
+  float w[4], m[4], v[4];
+  const bool vec = n == 4 && (pi & 3) == 0;
+  if (vec) {
+    const float4 w4 = __ldcg(reinterpret_cast<const float4*>(a.master + pi));
+    w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+    if (a.adam) {
+      const float4 m4 = __ldcg(reinterpret_cast<const float4*>(a.adam_m + pi));
+      const float4 v4 = __ldcg(reinterpret_cast<const float4*>(a.adam_v + pi));
+      m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
+      v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
+    }
+  } else {
+    for (int k = 0; k < n; ++k) {
+      w[k] = __ldcg(a.master + pi + k);
+      if (a.adam) { m[k] = __ldcg(a.adam_m + pi + k); v[k] = __ldcg(a.adam_v + pi + k); }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k >= n) break;
+    if (a.adam) {
+      m[k] = a.beta1 * m[k] + (1.f - a.beta1) * g[k];
+      v[k] = a.beta2 * v[k] + (1.f - a.beta2) * g[k] * g[k];
+      w[k] -= a.lr * (m[k] / bc1) / (sqrtf(v[k] / bc2) + a.eps);
+    } else {
+      w[k] -= a.lr * g[k];
+    }
+  }
+  if (vec) {
+    *reinterpret_cast<float4*>(a.master + pi) = make_float4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint2*>(a.shadow + pi) = make_uint2(pack2(w[0], w[1]), pack2(w[2], w[3]));
+    if (a.adam) {
+      *reinterpret_cast<float4*>(a.adam_m + pi) = make_float4(m[0], m[1], m[2], m[3]);
+      *reinterpret_cast<float4*>(a.adam_v + pi) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  } else {
+    for (int k = 0; k < n; ++k) {
+      a.master[pi + k] = w[k];
+      a.shadow[pi + k] = __float2bfloat16(w[k]);
+      if (a.adam) { a.adam_m[pi + k] = m[k]; a.adam_v[pi + k] = v[k]; }
+    }
+  }
+}
+
 // epilogue warps 2..5; `warp` is the hardware warp index
 __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int warp, int lane,
                                               uint64_t* accum_bar, uint32_t tmem_base,
@@ -225,7 +303,11 @@ __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int w
         if (rw >= j.M || col >= j.N) continue;
         const float4 x = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cg);
         const long long off = static_cast<long long>(rw) * j.ldd + col;
-        if (j.mode == E_F32) {
+        if (j.mode == E_OPT) {
+          const float g[4] = {x.x, x.y, x.z, x.w};
+          const int nn = j.N - col < 4 ? j.N - col : 4;
+          opt_apply(a, (reinterpret_cast<float*>(j.d) - a.master) + off, nn, g, j.bc1, j.bc2);
+        } else if (j.mode == E_F32) {
           float* d = reinterpret_cast<float*>(j.d) + off;
           if (col + 3 < j.N) *reinterpret_cast<float4*>(d) = x;
           else {
@@ -312,6 +394,268 @@ __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int w
   ptx::tc_fence_before_sync();
 }
 
+// ---------------------------------------------------------------- fused chain of one 128-row tile
+//   fwd1  acc[128 x 256] = x W1^T            (TMA ring, 13 K-blocks)            TMEM cols [0,256)
+//   E1    h = relu(acc + b1) -> bf16 -> smem (128B-swizzled K-major = fwd2's A operand) + global
+//   fwd2  logits[128 x 64] = h W2^T          (A, B from smem)                    TMEM cols [256,320)
+//   E2    softmax-xent per row (one thread owns a row) -> dlogits -> smem (dh's A operand) + global
+//   dh    acc[128 x 256] = dlogits W2        (B = W2 MN-major)                   TMEM cols [0,256)
+//   E3    dh = acc * relu'(h) -> bf16 global, db1
+// h never makes the global -> TMA round trip and the three GEMMs cost one grid barrier, not three.
+__device__ __forceinline__ void st_sw128(uint8_t* tile, int r, int chunk, uint4 v) {
+  *reinterpret_cast<uint4*>(tile + r * 128 + ((chunk ^ (r & 7)) << 4)) = v;
+}
+
+__device__ __forceinline__ void chain_produce(const Maps& maps, const Args& a, uint8_t* smem,
+                                              const ChainBars& cb, CPipe& cp, int row0) {
+  const uint32_t par = cp.n & 1;
+  if (ptx::elect_one()) {
+    ptx::mbar_expect_tx(cb.w2k, 32768);
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb)
+      ptx::tma_load_3d(smem + kOffW2K + kb * 8192, &maps.w2_k, cb.w2k, kb * 64, 0, 0);
+  }
+  __syncwarp();
+  const int kb_d = (a.in_dim + 63) / 64;
+  for (int i = 0; i < kb_d; ++i, ++cp.it) {
+    const int s = cp.it % kCStages;
+    const uint32_t ph = (cp.it / kCStages) & 1;
+    ptx::mbar_wait(&cb.empty[s], ph ^ 1);
+    if (ptx::elect_one()) {
+      uint8_t* sa = smem + s * kCStage;
+      ptx::mbar_expect_tx(&cb.full[s], kCStage);
+      ptx::tma_load_3d(sa, &maps.x_k, &cb.full[s], i * 64, row0, 0);
+      ptx::tma_load_3d(sa + kCA, &maps.w1_k256, &cb.full[s], i * 64, 0, 0);
+    }
+    __syncwarp();
+  }
+  ptx::mbar_wait(cb.acc_h, par);   // every fwd1 MMA has retired: the stage memory is free
+  if (ptx::elect_one()) {
+    ptx::mbar_expect_tx(cb.w2mn, 32768);
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn)
+      ptx::tma_load_3d(smem + kOffW2MN + jn * 8192, &maps.w2_mn, cb.w2mn, jn * 64, 0, 0);
+  }
+  __syncwarp();
+  ++cp.n;
+}
+
+__device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, const ChainBars& cb,
+                                          uint32_t tmem_base, CPipe& cp) {
+  const uint32_t par = cp.n & 1;
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  const uint32_t base_lo = ptx::smem_u32(smem) >> 4;
+  const int kb_d = (a.in_dim + 63) / 64;
+  // fwd1: 128 x 256 x in_dim
+  const uint32_t id1 = ptx::make_idesc(1u, 0u, 0u, kBM, 256);
+  for (int i = 0; i < kb_d; ++i, ++cp.it) {
+    const int s = cp.it % kCStages;
+    const uint32_t ph = (cp.it / kCStages) & 1;
+    ptx::mbar_wait(&cb.full[s], ph);
+    ptx::tc_fence_after_sync();
+    if (ptx::elect_one()) {
+      const uint32_t lo_a = (base_lo + static_cast<uint32_t>(s) * (kCStage >> 4)) | (1u << 16);
+      const uint32_t lo_b = lo_a + (kCA >> 4);
+#pragma unroll
+      for (uint32_t k = 0; k < 4; ++k)
+        ptx::umma_f16(tmem_base, (static_cast<uint64_t>(hi) << 32) | (lo_a + k * 2u),
+                      (static_cast<uint64_t>(hi) << 32) | (lo_b + k * 2u), id1, (i > 0 || k > 0) ? 1u : 0u);
+      ptx::umma_commit(&cb.empty[s]);
+    }
+    __syncwarp();
+  }
+  if (ptx::elect_one()) ptx::umma_commit(cb.acc_h);
+  __syncwarp();
+  // fwd2: 128 x 64 x 256, A = h (smem, written by the epilogue warps), B = W2 K-major
+  ptx::mbar_wait(cb.w2k, par);
+  ptx::mbar_wait(cb.h_ready, par);
+  ptx::tc_fence_after_sync();
+  if (ptx::elect_one()) {
+    const uint32_t id2 = ptx::make_idesc(1u, 0u, 0u, kBM, 64);
+    const uint32_t lo_a0 = (base_lo + (kOffH >> 4)) | (1u << 16);
+    const uint32_t lo_b0 = (base_lo + (kOffW2K >> 4)) | (1u << 16);
+#pragma unroll
+    for (uint32_t kb = 0; kb < 4; ++kb)
+#pragma unroll
+      for (uint32_t k = 0; k < 4; ++k)
+        ptx::umma_f16(tmem_base + 256, (static_cast<uint64_t>(hi) << 32) | (lo_a0 + kb * (16384u >> 4) + k * 2u),
+                      (static_cast<uint64_t>(hi) << 32) | (lo_b0 + kb * (8192u >> 4) + k * 2u), id2,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+    ptx::umma_commit(cb.acc_l);
+  }
+  __syncwarp();
+  // dh: 128 x 256 x 64, A = dlogits (smem), B = W2 MN-major (4 chunks of 64 hidden columns)
+  ptx::mbar_wait(cb.w2mn, par);
+  ptx::mbar_wait(cb.dl_ready, par);
+  ptx::tc_fence_after_sync();
+  if (ptx::elect_one()) {
+    const uint32_t id3 = ptx::make_idesc(1u, 0u, 1u, kBM, 256);
+    const uint32_t lo_a0 = (base_lo + (kOffDL >> 4)) | (1u << 16);
+    const uint32_t lo_b0 = (base_lo + (kOffW2MN >> 4)) | ((8192u >> 4) << 16);
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k)
+      ptx::umma_f16(tmem_base, (static_cast<uint64_t>(hi) << 32) | (lo_a0 + k * 2u),
+                    (static_cast<uint64_t>(hi) << 32) | (lo_b0 + k * (2048u >> 4)), id3, k > 0 ? 1u : 0u);
+    ptx::umma_commit(cb.acc_dh);
+  }
+  __syncwarp();
+  ++cp.n;
+}
+
+__device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, const ChainBars& cb,
+                                               uint32_t tmem_base, int warp, int lane, float* stage_base,
+                                               float* sb, CPipe& cp, int m0, int r0) {
+  const uint32_t par = cp.n & 1;
+  const int q = warp & 3;
+  const int rl = q * 32 + lane;        // row inside the tile == TMEM lane
+  const int row = m0 + rl;             // row inside the mini-batch
+  const bool row_ok = row < a.B;
+  const int C = a.n_classes;
+  float* stg = stage_base + (warp - 2) * (32 * kStgLd);
+  {
+    const int et = threadIdx.x - 64;   // coherent loads: the optimizer of this kernel rewrites the biases
+    for (int i = et; i < kChainH; i += 128) sb[i] = __ldcg(a.b1 + i);
+    if (et < 64) sb[kChainH + et] = et < C ? __ldcg(a.b2 + et) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+  // ---- E1: h
+  ptx::mbar_wait(cb.acc_h, par);
+  ptx::tc_fence_after_sync();
+  uint32_t mask[8];
+  {
+    uint8_t* hs = smem + kOffH;
+    __nv_bfloat16* hg = a.h + static_cast<long long>(row) * a.hidden;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+      ptx::tmem_ld_wait();
+      uint32_t pk[16];
+      uint32_t m = 0;
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+        const float v0 = fmaxf(__uint_as_float(r[k]) + sb[c * 32 + k], 0.f);
+        const float v1 = fmaxf(__uint_as_float(r[k + 1]) + sb[c * 32 + k + 1], 0.f);
+        m |= (v0 > 0.f ? 1u : 0u) << k;
+        m |= (v1 > 0.f ? 1u : 0u) << (k + 1);
+        pk[k >> 1] = pack2(v0, v1);
+      }
+      mask[c] = m;
+      uint8_t* tile = hs + (c >> 1) * 16384;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const uint4 v = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+        st_sw128(tile, rl, (c & 1) * 4 + jj, v);
+        if (row_ok) reinterpret_cast<uint4*>(hg + c * 32)[jj] = v;
+      }
+    }
+  }
+  ptx::fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor core
+  ptx::tc_fence_before_sync();
+  ptx::mbar_arrive(cb.h_ready);
+
+  // ---- E2: softmax cross-entropy of the row
+  ptx::mbar_wait(cb.acc_l, par);
+  ptx::tc_fence_after_sync();
+  {
+    const int32_t label = row_ok ? a.labels[r0 + row] : -1;
+    float vmax = -INFINITY, zlab = 0.f;
+    int amax = -1;
+    float z[64];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(taddr + 256 + c * 32, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int n = c * 32 + k;
+        const float x = __uint_as_float(r[k]) + sb[kChainH + n];
+        z[n] = x;
+        if (n < C) {
+          if (x > vmax) { vmax = x; amax = n; }
+          if (n == label) zlab = x;
+        }
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int n = 0; n < 64; ++n)
+      if (n < C) sum += __expf(z[n] - vmax);
+    const float inv = 1.f / sum;
+    float loss = row_ok ? (__logf(sum) + vmax - zlab) : 0.f;
+    const bool hit = row_ok && (amax == label);
+    const float gs = 1.f / static_cast<float>(a.B);
+    uint8_t* dls = smem + kOffDL;
+    __nv_bfloat16* dlg = a.dlogits + static_cast<long long>(row) * a.ncp;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int n = c * 32 + k;
+        v[k] = (n < C && row_ok) ? (__expf(z[n] - vmax) * inv - (n == label ? 1.f : 0.f)) * gs : 0.f;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const uint4 u = make_uint4(pack2(v[8 * jj], v[8 * jj + 1]), pack2(v[8 * jj + 2], v[8 * jj + 3]),
+                                   pack2(v[8 * jj + 4], v[8 * jj + 5]), pack2(v[8 * jj + 6], v[8 * jj + 7]));
+        st_sw128(dls, rl, c * 4 + jj, u);
+        if (row_ok && c * 32 + jj * 8 < a.ncp) reinterpret_cast<uint4*>(dlg + c * 32)[jj] = u;
+      }
+      stage_put(stg, lane, v);
+      __syncwarp();
+      float tot = 0.f;
+      for (int rr = 0; rr < 32; ++rr) tot += stg[rr * kStgLd + lane];
+      if (c * 32 + lane < C) atomicAdd(a.gb2 + c * 32 + lane, tot);
+      __syncwarp();
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, off);
+    const unsigned cnt = __popc(__ballot_sync(0xffffffffu, hit));
+    if (lane == 0) {
+      atomicAdd(a.loss_sum, loss);
+      if (cnt) atomicAdd(a.correct, cnt);
+    }
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before_sync();
+  ptx::mbar_arrive(cb.dl_ready);
+
+  // ---- E3: dh = (dlogits W2) * relu'(h), db1
+  ptx::mbar_wait(cb.acc_dh, par);
+  ptx::tc_fence_after_sync();
+  {
+    __nv_bfloat16* dg = a.dh + static_cast<long long>(row) * a.hidden;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+      ptx::tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = ((mask[c] >> k) & 1u) ? __uint_as_float(r[k]) : 0.f;
+      if (row_ok) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          reinterpret_cast<uint4*>(dg + c * 32)[jj] =
+              make_uint4(pack2(v[8 * jj], v[8 * jj + 1]), pack2(v[8 * jj + 2], v[8 * jj + 3]),
+                         pack2(v[8 * jj + 4], v[8 * jj + 5]), pack2(v[8 * jj + 6], v[8 * jj + 7]));
+      }
+      stage_put(stg, lane, v);
+      __syncwarp();
+      float tot = 0.f;
+      for (int rr = 0; rr < 32; ++rr) tot += stg[rr * kStgLd + lane];
+      atomicAdd(a.gb1 + c * 32 + lane, tot);
+      __syncwarp();
+    }
+  }
+  ptx::tc_fence_before_sync();
+  ++cp.n;
+}
+
 // Device-wide barrier between phases.  All kGrid CTAs are co-resident (one per SM), the counter
 // only grows.  Writers: bar.sync orders every thread's writes before thread 0's gpu-scope
 // fence (cumulative release); readers: acquire, then a proxy fence so the next phase's TMA
@@ -346,7 +690,9 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kTileBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* accum_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* cbar = accum_bar + 1;      // chain barriers: full[3] empty[3] + 7 single-use
+  ChainBars cb{cbar, cbar + kCStages, cbar + 6, cbar + 7, cbar + 8, cbar + 9, cbar + 10, cbar + 11, cbar + 12};
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cbar + 13);
   float* stage_base = reinterpret_cast<float*>(smem + kTileBytes + kBarBytes);
   float* sbias = stage_base + 4 * 32 * kStgLd;
 
@@ -358,20 +704,28 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
       ptx::mbar_init(&empty_bar[s], 1);
     }
     ptx::mbar_init(accum_bar, 1);
+    for (int s = 0; s < kCStages; ++s) {
+      ptx::mbar_init(&cb.full[s], 1);
+      ptx::mbar_init(&cb.empty[s], 1);
+    }
+    ptx::mbar_init(cb.w2k, 1); ptx::mbar_init(cb.w2mn, 1);
+    ptx::mbar_init(cb.acc_h, 1); ptx::mbar_init(cb.acc_l, 1); ptx::mbar_init(cb.acc_dh, 1);
+    ptx::mbar_init(cb.h_ready, 128); ptx::mbar_init(cb.dl_ready, 128);
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, kBN);
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, kTmemCols);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   ptx::pdl_wait();
   if (a.pred != nullptr && *a.pred == 0) {
-    if (warp == 1) ptx::tmem_dealloc(tmem_base, kBN);
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
     return;
   }
 
   Pipe pp{0u, 0u};
+  CPipe cp{0u, 0u};
   unsigned int bar_epoch = 0;
   const int t = blockIdx.x;
   const int B = a.B, H = a.hidden, C = a.n_classes, D = a.in_dim;
@@ -389,6 +743,52 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
 
   for (int step = 0; step < a.steps; ++step) {
     const int r0 = step * B;
+    float bc1 = 1.f, bc2 = 1.f;
+    if (a.adam) {
+      const int tt = (a.step_base ? *a.step_base : 0) + step + 1;
+      bc1 = 1.f - powf(a.beta1, static_cast<float>(tt));
+      bc2 = 1.f - powf(a.beta2, static_cast<float>(tt));
+    }
+    const bool eo = a.chain == 2;   // optimizer fused into the weight-gradient epilogues
+    if (a.chain) {
+      // ---- A: fwd1 -> xent -> dh chained per 128-row tile (no global round trip, no barrier)
+      if (t < mt_b) {
+        const int m0 = t * kBM;
+        if (warp == 0) chain_produce(maps, a, smem, cb, cp, r0 + m0);
+        else if (warp == 1) chain_mma(a, smem, cb, tmem_base, cp);
+        else chain_epilogue(a, smem, cb, tmem_base, warp, lane, stage_base, sbias, cp, m0, r0);
+      }
+      grid_barrier(a.barrier, bar_epoch);
+      // ---- B: dW1 = dh^T x (tiles [0, mt_h*nt_d))  ||  dW2 = dlogits^T h (next nt_h tiles)
+      if (t < mt_h * nt_d) {
+        Job j{};
+        j.ta = &maps.dh_mn; j.tb = &maps.x_mn; j.a_mn = 1; j.b_mn = 1;
+        j.m0 = (t / nt_d) * kBM; j.n0 = (t % nt_d) * kBN; j.M = H; j.N = D;
+        j.a_c0 = j.m0; j.a_c1 = 0; j.b_c0 = j.n0; j.b_c1 = r0; j.n_kb = kb_b;
+        j.mode = eo ? E_OPT : E_F32; j.d = eo ? a.master + (a.gw1 - a.grad) : a.gw1; j.ldd = D;
+        j.bc1 = bc1; j.bc2 = bc2;
+        run(j);
+      } else if (t < mt_h * nt_d + nt_h) {
+        const int u = t - mt_h * nt_d;
+        Job j{};
+        j.ta = &maps.dl_mn; j.tb = &maps.h_mn; j.a_mn = 1; j.b_mn = 1;
+        j.m0 = 0; j.n0 = u * kBN; j.M = C; j.N = H;
+        j.a_c0 = 0; j.a_c1 = 0; j.b_c0 = j.n0; j.b_c1 = 0; j.n_kb = kb_b;
+        j.mode = eo ? E_OPT : E_F32; j.d = eo ? a.master + (a.gw2 - a.grad) : a.gw2; j.ldd = H;
+        j.bc1 = bc1; j.bc2 = bc2;
+        run(j);
+      } else if (eo && t == mt_h * nt_d + nt_h) {
+        // biases: their gradients were accumulated by the chain's column sums; consume + re-zero
+        for (int i = threadIdx.x; i < H + C; i += blockDim.x) {
+          float* gp = i < H ? a.gb1 + i : a.gb2 + (i - H);
+          const float g = __ldcg(gp);
+          *gp = 0.f;
+          opt_apply(a, gp - a.grad, 1, &g, bc1, bc2);
+        }
+      }
+      grid_barrier(a.barrier, bar_epoch);
+      if (eo) continue;   // the optimizer ran in the epilogues
+    } else {
     // ---- P1: h = relu(x W1^T + b1)
     if (t < mt_b * nt_h) {
       Job j{};
@@ -438,16 +838,11 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
       run(j);
     }
     grid_barrier(a.barrier, bar_epoch);
+    }  // !chain
     // ---- P5: optimizer over the flat buffer (all threads of all CTAs)
     {
       const long long nv = a.n_params / 4;
       const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-      float bc1 = 1.f, bc2 = 1.f;
-      if (a.adam) {
-        const int tt = (a.step_base ? *a.step_base : 0) + step + 1;
-        bc1 = 1.f - powf(a.beta1, static_cast<float>(tt));
-        bc2 = 1.f - powf(a.beta2, static_cast<float>(tt));
-      }
       for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
            i += stride) {
         const float4 w4 = __ldcg(reinterpret_cast<const float4*>(a.master) + i);
@@ -481,7 +876,187 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_base, kBN);
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------- committee validation chain
+// One CTA per (128 validation rows, candidate z): fwd1 -> relu -> fwd2 -> argmax == label, with
+// candidate z's weights addressed through device-resident tensor maps (local staging slots or a
+// peer GPU's upload buffer) selected by the round plan -- "QueryAllUpdates" + scoring
+// (reference C:299-311, M:226-247) without materialising logits or hidden activations.
+constexpr int kValSmem = kOffW2K + 32768 + kBarBytes + kBiasFloats * 4 + 1024;
+
+struct ValArgs {
+  int n_val, in_dim, n_classes;
+  const CUtensorMap* maps;               // table indexed by dyn{1,2}->map_index[z]
+  const GemmDynamic* dyn1; const GemmDynamic* dyn2;
+  const int32_t* labels; unsigned int* correct;
+  const int* pred;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_val_kernel(const __grid_constant__ CUtensorMap tmX, const ValArgs v) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kOffW2K + 32768);
+  uint64_t* empty = full + kCStages;
+  uint64_t* w2k = empty + kCStages;
+  uint64_t* acc_h = w2k + 1;
+  uint64_t* h_ready = acc_h + 1;
+  uint64_t* acc_l = h_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_l + 1);
+  float* sb = reinterpret_cast<float*>(smem + kOffW2K + 32768 + kBarBytes);
+
+  ptx::pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = blockIdx.y, m0 = blockIdx.x * kBM;
+  if (warp == 0 && lane == 0) {
+    ptx::tma_prefetch_desc(&tmX);
+    for (int s = 0; s < kCStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(w2k, 1); ptx::mbar_init(acc_h, 1); ptx::mbar_init(acc_l, 1);
+    ptx::mbar_init(h_ready, 128);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, kTmemCols);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();
+  const bool inactive = (v.pred != nullptr && *v.pred == 0) || z >= v.dyn1->active_batches;
+  if (inactive) {
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+    return;
+  }
+  const int kb_d = (v.in_dim + 63) / 64;
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  const uint32_t base_lo = ptx::smem_u32(smem) >> 4;
+
+  if (warp == 0) {
+    if (v.dyn1->wait_flag[z] != nullptr) {   // candidate z's trainer has published its upload
+      if (lane == 0) ptx::wait_flag_ge(v.dyn1->wait_flag[z], v.dyn1->wait_value);
+      __syncwarp();
+    }
+    const CUtensorMap* m1 = v.maps + v.dyn1->map_index[z];
+    const CUtensorMap* m2 = v.maps + v.dyn2->map_index[z];
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(w2k, 32768);
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) ptx::tma_load_3d(smem + kOffW2K + kb * 8192, m2, w2k, kb * 64, 0, 0);
+    }
+    __syncwarp();
+    for (int i = 0; i < kb_d; ++i) {
+      const int s = i % kCStages;
+      const uint32_t ph = (i / kCStages) & 1;
+      ptx::mbar_wait(&empty[s], ph ^ 1);
+      if (ptx::elect_one()) {
+        uint8_t* sa = smem + s * kCStage;
+        ptx::mbar_expect_tx(&full[s], kCStage);
+        ptx::tma_load_3d(sa, &tmX, &full[s], i * 64, m0, 0);
+        ptx::tma_load_3d(sa + kCA, m1, &full[s], i * 64, 0, 0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t id1 = ptx::make_idesc(1u, 0u, 0u, kBM, 256);
+    for (int i = 0; i < kb_d; ++i) {
+      const int s = i % kCStages;
+      const uint32_t ph = (i / kCStages) & 1;
+      ptx::mbar_wait(&full[s], ph);
+      ptx::tc_fence_after_sync();
+      if (ptx::elect_one()) {
+        const uint32_t lo_a = (base_lo + static_cast<uint32_t>(s) * (kCStage >> 4)) | (1u << 16);
+        const uint32_t lo_b = lo_a + (kCA >> 4);
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k)
+          ptx::umma_f16(tmem_base, (static_cast<uint64_t>(hi) << 32) | (lo_a + k * 2u),
+                        (static_cast<uint64_t>(hi) << 32) | (lo_b + k * 2u), id1, (i > 0 || k > 0) ? 1u : 0u);
+        ptx::umma_commit(&empty[s]);
+      }
+      __syncwarp();
+    }
+    if (ptx::elect_one()) ptx::umma_commit(acc_h);
+    __syncwarp();
+    ptx::mbar_wait(w2k, 0);
+    ptx::mbar_wait(h_ready, 0);
+    ptx::tc_fence_after_sync();
+    if (ptx::elect_one()) {
+      const uint32_t id2 = ptx::make_idesc(1u, 0u, 0u, kBM, 64);
+      const uint32_t lo_a0 = (base_lo + (kOffH >> 4)) | (1u << 16);
+      const uint32_t lo_b0 = (base_lo + (kOffW2K >> 4)) | (1u << 16);
+#pragma unroll
+      for (uint32_t kb = 0; kb < 4; ++kb)
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k)
+          ptx::umma_f16(tmem_base + 256, (static_cast<uint64_t>(hi) << 32) | (lo_a0 + kb * (16384u >> 4) + k * 2u),
+                        (static_cast<uint64_t>(hi) << 32) | (lo_b0 + kb * (8192u >> 4) + k * 2u), id2,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+      ptx::umma_commit(acc_l);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3, rl = q * 32 + lane, row = m0 + rl;
+    const bool row_ok = row < v.n_val;
+    const int C = v.n_classes;
+    {
+      const int et = threadIdx.x - 64;
+      const float* b1 = v.dyn1->bias[z];
+      const float* b2 = v.dyn2->bias[z];
+      for (int i = et; i < kChainH; i += 128) sb[i] = b1 != nullptr ? b1[i] : 0.f;
+      if (et < 64) sb[kChainH + et] = (b2 != nullptr && et < C) ? b2[et] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    ptx::mbar_wait(acc_h, 0);
+    ptx::tc_fence_after_sync();
+#pragma unroll 2
+    for (int c = 0; c < 8; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+      ptx::tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int k = 0; k < 32; k += 2)
+        pk[k >> 1] = pack2(fmaxf(__uint_as_float(r[k]) + sb[c * 32 + k], 0.f),
+                           fmaxf(__uint_as_float(r[k + 1]) + sb[c * 32 + k + 1], 0.f));
+      uint8_t* tile = smem + kOffH + (c >> 1) * 16384;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        st_sw128(tile, rl, (c & 1) * 4 + jj, make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]));
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before_sync();
+    ptx::mbar_arrive(h_ready);
+    ptx::mbar_wait(acc_l, 0);
+    ptx::tc_fence_after_sync();
+    const int32_t label = row_ok ? v.labels[row] : -1;
+    float vmax = -INFINITY;
+    int amax = -1;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(taddr + 256 + c * 32, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int n = c * 32 + k;
+        const float x = __uint_as_float(r[k]) + sb[kChainH + n];
+        if (n < C && x > vmax) { vmax = x; amax = n; }
+      }
+    }
+    const unsigned cnt = __popc(__ballot_sync(0xffffffffu, row_ok && amax == label));
+    if (lane == 0 && cnt) atomicAdd(v.correct + z, cnt);
+    ptx::tc_fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -493,7 +1068,10 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
     return cudaErrorInvalidValue;
   const int mt_b = (r.batch + kBM - 1) / kBM, nt_h = (r.hidden + kBN - 1) / kBN;
   const int nt_d = (r.in_dim + kBN - 1) / kBN, mt_h = (r.hidden + kBM - 1) / kBM;
-  const int need = std::max(std::max(mt_b * nt_h + nt_h, mt_h * nt_d), mt_b);
+  static const bool chain_env = [] { const char* e = std::getenv("BFLC_MLP_CHAIN"); return !(e && e[0] == '0'); }();
+  const bool chain = chain_env && r.hidden == kChainH && r.ncp == 64 && r.n_classes <= 64;
+  const int need = chain ? std::max(mt_h * nt_d + nt_h + 1, mt_b)
+                         : std::max(std::max(mt_b * nt_h + nt_h, mt_h * nt_d), mt_b);
   if (need > kGrid * 4) return cudaErrorInvalidValue;
   const int grid = need > kGrid ? need : kGrid;
   if (grid > 148) return cudaErrorInvalidValue;
@@ -517,10 +1095,13 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
   if ((e = mk(&m.w2_mn, r.w2_shadow, r.hidden, true, r.hidden, r.n_classes, kBN)) != cudaSuccess) return e;
   if ((e = mk(&m.dh_mn, r.dh, r.hidden, true, r.hidden, r.batch, kBM)) != cudaSuccess) return e;
   if ((e = mk(&m.x_mn, r.x, r.in_dim, true, r.in_dim, (int)rows_x, kBN)) != cudaSuccess) return e;
+  if ((e = mk(&m.w1_k256, r.w1_shadow, r.in_dim, false, r.hidden, r.in_dim, chain ? 256 : kBN)) != cudaSuccess) return e;
 
   Args a{};
   a.B = r.batch; a.steps = r.steps; a.in_dim = r.in_dim; a.hidden = r.hidden;
   a.n_classes = r.n_classes; a.ncp = r.ncp; a.n_params = r.n_params;
+  static const bool epiopt_env = [] { const char* e = std::getenv("BFLC_MLP_EPIOPT"); return !(e && e[0] == '0'); }();
+  a.chain = chain ? (epiopt_env ? 2 : 1) : 0;
   a.pred = r.pred ? r.pred : current_predicate();
   a.barrier = r.barrier;
   a.master = r.master; a.b1 = r.b1; a.b2 = r.b2;
@@ -541,6 +1122,30 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
   }
   note_launch();
   return launch_pdl(mlp_round_kernel, dim3(grid), dim3(kThreads), kSmemTotal, stream, m, a);
+}
+
+cudaError_t mlp_val_sm100(const MlpValArgs& r, cudaStream_t stream) {
+  bind_context_once();
+  if (r.hidden != kChainH || r.n_classes > 64 || r.in_dim % 8 || r.n_val <= 0 || r.max_cand <= 0)
+    return cudaErrorInvalidValue;
+  CUtensorMap tx;
+  GemmOperand op{r.x, r.ldx, 0, false};
+  cudaError_t e = gemm_make_operand_map(&tx, op, DType::BF16, r.n_val, r.in_dim, 1, kBM);
+  if (e != cudaSuccess) return e;
+  ValArgs v{};
+  v.n_val = r.n_val; v.in_dim = r.in_dim; v.n_classes = r.n_classes;
+  v.maps = r.maps; v.dyn1 = r.dyn1; v.dyn2 = r.dyn2;
+  v.labels = r.labels; v.correct = r.correct;
+  v.pred = r.pred ? r.pred : current_predicate();
+  static bool configured = false;
+  if (!configured) {
+    e = cudaFuncSetAttribute(mlp_val_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kValSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  note_launch();
+  return launch_pdl(mlp_val_kernel, dim3((r.n_val + kBM - 1) / kBM, r.max_cand), dim3(kThreads), kValSmem,
+                    stream, tx, v);
 }
 
 }  // namespace bflc

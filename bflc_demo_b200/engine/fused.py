@@ -19,6 +19,8 @@ i.e. python-sdk/main.py:103-169, 196-228 and CommitteePrecompiled.cpp:215-456.
 """
 from __future__ import annotations
 
+import os
+
 import struct
 from typing import Dict, List, Optional
 
@@ -138,6 +140,13 @@ class FusedEngine:
         # N-tile widths are pinned so the pre-encoded peer tensor maps match the launches
         self.val_bn = [self.mod.gemm_pick_bn(e1.shape[0], G.EPI_GENERIC, self.n_val, world),
                        self.mod.gemm_pick_bn(e2.shape[0], G.EPI_ARGMAX, self.n_val, world)]
+        # hidden == 256: the whole validation forward of every candidate is ONE launch
+        # (mlp_val_sm100: fwd1 -> relu -> fwd2 -> argmax per (128 rows, candidate) CTA, hidden
+        # activations stay in TMEM / smem); its layer-1 maps use a 256-row box.
+        self.val_chain = (cfg.hidden == 256 and e2.shape[0] <= 64
+                          and os.environ.get("BFLC_VAL_CHAIN", "1") != "0")
+        if self.val_chain:
+            self.val_bn = [256, 64]
         # Two ways to feed the candidates' weights to the validation GEMMs:
         #  staged (default): fed_pull_candidates streams each trainer's bf16 weights out of its
         #    HBM once (as soon as that trainer's flag is up); the GEMM B maps cover the local
@@ -199,6 +208,19 @@ class FusedEngine:
             m.fed_pull_candidates(self.fed, self.cand_shadow, None)
         xv, yv = self.x_bf[: self.n_val], self.y[: self.n_val]
         H = cfg.hidden
+        if self.val_chain:
+            m.set_predicate(self.is_comm_ptr)
+            m.mlp_val(xv, yv, self.val_correct, self.b_maps, self.dyn_ptr[0], self.dyn_ptr[1],
+                      self.n_val, self.in_dim, H, self.spec.by_name["w2"].shape[0], self.world)
+            m.set_predicate(0)
+        else:
+            self._validate_two_gemms(xv, yv, H)
+        m.fed_consensus_aggregate(self.fed, self.n_val, cfg.weight_by_score, self.two_shot,
+                                  cfg.use_multicast and self.heap.has_multicast)
+        self.launches_per_round = int(m.launch_count() - n0)
+
+    def _validate_two_gemms(self, xv, yv, H):
+        m = self.mod
         m.gemm(xv, self.work_shadow, self.h_val, self.n_val, H, self.in_dim, self.world,
                self.in_dim, self.in_dim, 0, 0, False, False, False, G.EPI_GENERIC, 1, H,
                self.n_val * H, 1.0, None, G.ACT_RELU, None, None, 0, None, 1, False, None, 0, 1.0,
@@ -207,9 +229,6 @@ class FusedEngine:
                self.world, H, H, self.n_val * H, 0, False, False, False, G.EPI_ARGMAX, 1, 0, 0, 1.0,
                None, 0, None, None, 0, None, 1, False, yv, 0, 1.0, None, self.val_correct,
                self.b_maps, None, 0, 0, 0, 0, self.dyn_ptr[1], self.val_bn[1])
-        m.fed_consensus_aggregate(self.fed, self.n_val, cfg.weight_by_score, self.two_shot,
-                                  cfg.use_multicast and self.heap.has_multicast)
-        self.launches_per_round = int(m.launch_count() - n0)
 
     def capture(self):
         """Warm up eagerly (lazy kernel attribute setup), then capture one round."""
