@@ -195,7 +195,8 @@ void bind_extra(py::module_& m) {
                         at::Tensor grad, std::vector<int64_t> offs, at::Tensor h, at::Tensor dlogits,
                         at::Tensor dh, at::Tensor loss_sum, at::Tensor correct, int64_t barrier_ptr,
                         int batch, int steps, int in_dim, int hidden, int n_classes, double lr,
-                        bool adam, const OptT& mm, const OptT& vv, int64_t step_base_ptr) {
+                        bool adam, const OptT& mm, const OptT& vv, int64_t step_base_ptr,
+                        const OptT& dbg) {
     TORCH_CHECK(offs.size() == 4, "offs = element offsets of w1, b1, w2, b2 in the flat buffer");
     bflc::MlpRoundArgs r;
     r.batch = batch; r.steps = steps; r.in_dim = in_dim; r.hidden = hidden; r.n_classes = n_classes;
@@ -217,6 +218,10 @@ void bind_extra(py::module_& m) {
     r.adam_v = vv.has_value() ? vv->data_ptr<float>() : nullptr;
     r.lr = (float)lr;
     r.step_base = P<const int>(step_base_ptr);
+    if (dbg.has_value()) {
+      TORCH_CHECK(dbg->numel() >= (int64_t)steps * 16 && dbg->element_size() == 8, "dbg: int64 [steps, 16]");
+      r.dbg = reinterpret_cast<unsigned long long*>(dbg->data_ptr());
+    }
     check(bflc::mlp_round_sm100(r, cur_stream()), "mlp_round_sm100");
   });
   // committee validation of every candidate in one launch (fwd1 -> relu -> fwd2 -> argmax)

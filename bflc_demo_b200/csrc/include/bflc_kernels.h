@@ -128,6 +128,7 @@ struct MlpRoundArgs {
   bool adam = false; float* adam_m = nullptr; float* adam_v = nullptr;
   float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
   const int* step_base = nullptr;
+  unsigned long long* dbg = nullptr;  // optional [steps][16] %globaltimer stamps (CTA 0)
 };
 cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream);
 

@@ -500,7 +500,7 @@ k_pull(FedArgs f, uint4* stage_shadow, float4* stage_master) {
 int fed_grid(long long n_params) {
   // one 16-byte element per thread while the grid fits in ~4 resident blocks per SM: the copies
   // are latency-bound (small models), so every load should be in flight at once
-  long long blocks = (n_params / 4 + kFedThreads - 1) / kFedThreads;
+  long long blocks = (n_params / 4 + kFedThreads * 2 - 1) / (kFedThreads * 2);
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
   return static_cast<int>(blocks);

@@ -66,7 +66,9 @@ struct Maps {  // 11 TMA descriptors, all bf16, SWIZZLE_128B
 
 struct Args {
   int B, steps, in_dim, hidden, n_classes, ncp;  // ncp = dlogits row stride (padded classes)
-  int chain;                     // 1: fwd1 -> xent -> dh fused per 128-row tile (chain_* below)
+  int chain;                     // 0: P1|P2|P3   1: fwd1->xent->dh chained   3: P1 | fwd2->xent->dh chained
+  int epiopt;                    // optimizer applied in the weight-gradient epilogues (no P5)
+  unsigned long long* dbg;       // optional %globaltimer stamps [steps][16] written by CTA 0
   long long n_params;
   const int* pred;               // whole kernel is a no-op when *pred == 0 (non-trainer rank)
   unsigned int* barrier;         // device-wide phase barrier counter (zeroed before launch)
@@ -255,10 +257,54 @@ __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int w
       sbias[i] = (j.bias != nullptr && j.n0 + i < j.N) ? __ldcg(j.bias + j.n0 + i) : 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");
   }
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  if (j.mode == E_OPT && !a.adam) {
+    // SGD in the epilogue: this thread's share of the parameter tile is fetched while the MMAs
+    // are still running, so the update costs no exposed load latency
+    const long long pbase = reinterpret_cast<float*>(j.d) - a.master;
+    float4 wpre[kBN / 32][8];
+#pragma unroll
+    for (int c = 0; c < kBN / 32; ++c)
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rw = row_base + it * 4 + cr, col = j.n0 + c * 32 + cg;
+        wpre[c][it] = (rw < j.M && col + 3 < j.N)
+                          ? __ldcg(reinterpret_cast<const float4*>(a.master + pbase + static_cast<long long>(rw) * j.ldd + col))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    ptx::mbar_wait(accum_bar, pp.tile & 1);
+    ptx::tc_fence_after_sync();
+    ++pp.tile;
+#pragma unroll
+    for (int c = 0; c < kBN / 32; ++c) {
+      const int nc = j.n0 + c * 32;
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+      ptx::tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+      stage_put(stg, lane, v);
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + cr, rw = row_base + rr, col = nc + cg;
+        if (rw >= j.M || col + 3 >= j.N) continue;
+        const float4 g = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cg);
+        float4 w = wpre[c][it];
+        w.x -= a.lr * g.x; w.y -= a.lr * g.y; w.z -= a.lr * g.z; w.w -= a.lr * g.w;
+        const long long pi = pbase + static_cast<long long>(rw) * j.ldd + col;
+        *reinterpret_cast<float4*>(a.master + pi) = w;
+        *reinterpret_cast<uint2*>(a.shadow + pi) = make_uint2(pack2(w.x, w.y), pack2(w.z, w.w));
+      }
+      __syncwarp();
+    }
+    ptx::tc_fence_before_sync();
+    return;
+  }
   ptx::mbar_wait(accum_bar, pp.tile & 1);
   ptx::tc_fence_after_sync();
   ++pp.tile;
-  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
   if (j.mode != E_XENT) {
 #pragma unroll 1
@@ -407,8 +453,27 @@ __device__ __forceinline__ void st_sw128(uint8_t* tile, int r, int chunk, uint4 
 }
 
 __device__ __forceinline__ void chain_produce(const Maps& maps, const Args& a, uint8_t* smem,
-                                              const ChainBars& cb, CPipe& cp, int row0) {
+                                              const ChainBars& cb, CPipe& cp, int r0, int m0, bool f1) {
   const uint32_t par = cp.n & 1;
+  const int row0 = r0 + m0;
+  if (!f1) {
+    // h was produced by P1: TMA drops its 128 x 256 tile straight into the swizzled A-operand
+    // slots; both W2 forms can be fetched at once (no fwd1 stages to alias)
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(cb.w2k, 32768);
+      ptx::mbar_expect_tx(&cb.full[0], 65536);
+      ptx::mbar_expect_tx(cb.w2mn, 32768);
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        ptx::tma_load_3d(smem + kOffW2K + kb * 8192, &maps.w2_k, cb.w2k, kb * 64, 0, 0);
+        ptx::tma_load_3d(smem + kOffH + kb * 16384, &maps.h_k, &cb.full[0], kb * 64, m0, 0);
+        ptx::tma_load_3d(smem + kOffW2MN + kb * 8192, &maps.w2_mn, cb.w2mn, kb * 64, 0, 0);
+      }
+    }
+    __syncwarp();
+    ++cp.n;
+    return;
+  }
   if (ptx::elect_one()) {
     ptx::mbar_expect_tx(cb.w2k, 32768);
 #pragma unroll
@@ -441,14 +506,14 @@ __device__ __forceinline__ void chain_produce(const Maps& maps, const Args& a, u
 }
 
 __device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, const ChainBars& cb,
-                                          uint32_t tmem_base, CPipe& cp) {
+                                          uint32_t tmem_base, CPipe& cp, bool f1) {
   const uint32_t par = cp.n & 1;
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   const uint32_t base_lo = ptx::smem_u32(smem) >> 4;
   const int kb_d = (a.in_dim + 63) / 64;
   // fwd1: 128 x 256 x in_dim
   const uint32_t id1 = ptx::make_idesc(1u, 0u, 0u, kBM, 256);
-  for (int i = 0; i < kb_d; ++i, ++cp.it) {
+  for (int i = 0; f1 && i < kb_d; ++i, ++cp.it) {
     const int s = cp.it % kCStages;
     const uint32_t ph = (cp.it / kCStages) & 1;
     ptx::mbar_wait(&cb.full[s], ph);
@@ -464,11 +529,13 @@ __device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, const Ch
     }
     __syncwarp();
   }
-  if (ptx::elect_one()) ptx::umma_commit(cb.acc_h);
-  __syncwarp();
-  // fwd2: 128 x 64 x 256, A = h (smem, written by the epilogue warps), B = W2 K-major
+  if (f1) {
+    if (ptx::elect_one()) ptx::umma_commit(cb.acc_h);
+    __syncwarp();
+  }
+  // fwd2: 128 x 64 x 256, A = h (smem: written by the epilogue warps, or by TMA), B = W2 K-major
   ptx::mbar_wait(cb.w2k, par);
-  ptx::mbar_wait(cb.h_ready, par);
+  ptx::mbar_wait(f1 ? cb.h_ready : &cb.full[0], par);
   ptx::tc_fence_after_sync();
   if (ptx::elect_one()) {
     const uint32_t id2 = ptx::make_idesc(1u, 0u, 0u, kBM, 64);
@@ -504,8 +571,16 @@ __device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, const Ch
 
 __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, const ChainBars& cb,
                                                uint32_t tmem_base, int warp, int lane, float* stage_base,
-                                               float* sb, CPipe& cp, int m0, int r0) {
+                                               float* sb, CPipe& cp, int m0, int r0, bool f1,
+                                               unsigned long long* dbg) {
   const uint32_t par = cp.n & 1;
+  auto stampc = [&](int slot) {
+    if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) {
+      unsigned long long tns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+      dbg[slot] = tns;
+    }
+  };
   const int q = warp & 3;
   const int rl = q * 32 + lane;        // row inside the tile == TMEM lane
   const int row = m0 + rl;             // row inside the mini-batch
@@ -521,9 +596,33 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
   // ---- E1: h
+  uint32_t mask[8];
+  if (!f1) {
+    // h tile came in by TMA: only the relu mask is needed (read back through the swizzle)
+    ptx::mbar_wait(&cb.full[0], par);
+    const uint8_t* hs = smem + kOffH;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t m = 0;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int chunk = (c & 1) * 4 + jj;
+        const uint4 u = *reinterpret_cast<const uint4*>(hs + (c >> 1) * 16384 + rl * 128 + ((chunk ^ (rl & 7)) << 4));
+        const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          // bf16 > 0  <=>  sign clear and not zero
+          m |= (((wds[e] & 0xFFFFu) != 0u && (wds[e] & 0x8000u) == 0u) ? 1u : 0u) << (jj * 8 + e * 2);
+          m |= (((wds[e] >> 16) != 0u && (wds[e] & 0x80000000u) == 0u) ? 1u : 0u) << (jj * 8 + e * 2 + 1);
+        }
+      }
+      mask[c] = m;
+    }
+    stampc(6);
+  } else {
   ptx::mbar_wait(cb.acc_h, par);
   ptx::tc_fence_after_sync();
-  uint32_t mask[8];
+  stampc(6);
   {
     uint8_t* hs = smem + kOffH;
     __nv_bfloat16* hg = a.h + static_cast<long long>(row) * a.hidden;
@@ -555,10 +654,13 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
   ptx::fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor core
   ptx::tc_fence_before_sync();
   ptx::mbar_arrive(cb.h_ready);
+  }
+  stampc(7);
 
   // ---- E2: softmax cross-entropy of the row
   ptx::mbar_wait(cb.acc_l, par);
   ptx::tc_fence_after_sync();
+  stampc(8);
   {
     const int32_t label = row_ok ? a.labels[r0 + row] : -1;
     float vmax = -INFINITY, zlab = 0.f;
@@ -623,10 +725,12 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before_sync();
   ptx::mbar_arrive(cb.dl_ready);
+  stampc(9);
 
   // ---- E3: dh = (dlogits W2) * relu'(h), db1
   ptx::mbar_wait(cb.acc_dh, par);
   ptx::tc_fence_after_sync();
+  stampc(10);
   {
     __nv_bfloat16* dg = a.dh + static_cast<long long>(row) * a.hidden;
 #pragma unroll
@@ -653,6 +757,7 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
     }
   }
   ptx::tc_fence_before_sync();
+  stampc(11);
   ++cp.n;
 }
 
@@ -741,6 +846,18 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
     else epilogue_tile(j, a, warp, lane, accum_bar, tmem_base, stage_base, sbias, pp);
   };
 
+  // Phase plan of one step (a.chain, a.epiopt pick the variant; all are numerically equivalent):
+  //   chain 1:  [fwd1 -> xent -> dh chained per M-tile]                       | B
+  //   chain 3:  P1 fwd1 (16 tiles) | [fwd2 -> xent -> dh chained per M-tile]  | B
+  //   chain 0:  P1 | P2 xent | P3 dh                                          | B
+  //   B = dW1 || dW2 (+ SGD/Adam in the epilogue and a bias CTA when epiopt, else a flat P5)
+  auto stamp = [&](int step, int slot) {
+    if (a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) {
+      unsigned long long tns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+      a.dbg[step * 16 + slot] = tns;
+    }
+  };
   for (int step = 0; step < a.steps; ++step) {
     const int r0 = step * B;
     float bc1 = 1.f, bc2 = 1.f;
@@ -749,128 +866,101 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
       bc1 = 1.f - powf(a.beta1, static_cast<float>(tt));
       bc2 = 1.f - powf(a.beta2, static_cast<float>(tt));
     }
-    const bool eo = a.chain == 2;   // optimizer fused into the weight-gradient epilogues
-    if (a.chain) {
-      // ---- A: fwd1 -> xent -> dh chained per 128-row tile (no global round trip, no barrier)
+    const bool eo = a.epiopt != 0;
+    stamp(step, 0);
+    if (a.chain != 1) {
+      // ---- P1: h = relu(x W1^T + b1)
+      if (t < mt_b * nt_h) {
+        Job j{};
+        j.ta = &maps.x_k; j.tb = &maps.w1_k; j.a_mn = 0; j.b_mn = 0;
+        j.m0 = (t / nt_h) * kBM; j.n0 = (t % nt_h) * kBN; j.M = B; j.N = H;
+        j.a_c0 = 0; j.a_c1 = r0 + j.m0; j.b_c0 = 0; j.b_c1 = j.n0; j.n_kb = kb_d;
+        j.mode = E_BIAS_RELU_BF16; j.d = a.h; j.ldd = H; j.bias = a.b1;
+        run(j);
+      }
+      grid_barrier(a.barrier, bar_epoch);
+      stamp(step, 1);
+    }
+    if (a.chain != 0) {
+      // ---- chained tail (or whole) of the forward/backward pass per 128-row tile
       if (t < mt_b) {
         const int m0 = t * kBM;
-        if (warp == 0) chain_produce(maps, a, smem, cb, cp, r0 + m0);
-        else if (warp == 1) chain_mma(a, smem, cb, tmem_base, cp);
-        else chain_epilogue(a, smem, cb, tmem_base, warp, lane, stage_base, sbias, cp, m0, r0);
+        const bool f1 = a.chain == 1;
+        if (warp == 0) chain_produce(maps, a, smem, cb, cp, r0, m0, f1);
+        else if (warp == 1) chain_mma(a, smem, cb, tmem_base, cp, f1);
+        else chain_epilogue(a, smem, cb, tmem_base, warp, lane, stage_base, sbias, cp, m0, r0, f1,
+                            a.dbg != nullptr ? a.dbg + step * 16 : nullptr);
       }
       grid_barrier(a.barrier, bar_epoch);
-      // ---- B: dW1 = dh^T x (tiles [0, mt_h*nt_d))  ||  dW2 = dlogits^T h (next nt_h tiles)
-      if (t < mt_h * nt_d) {
-        Job j{};
-        j.ta = &maps.dh_mn; j.tb = &maps.x_mn; j.a_mn = 1; j.b_mn = 1;
-        j.m0 = (t / nt_d) * kBM; j.n0 = (t % nt_d) * kBN; j.M = H; j.N = D;
-        j.a_c0 = j.m0; j.a_c1 = 0; j.b_c0 = j.n0; j.b_c1 = r0; j.n_kb = kb_b;
-        j.mode = eo ? E_OPT : E_F32; j.d = eo ? a.master + (a.gw1 - a.grad) : a.gw1; j.ldd = D;
-        j.bc1 = bc1; j.bc2 = bc2;
-        run(j);
-      } else if (t < mt_h * nt_d + nt_h) {
-        const int u = t - mt_h * nt_d;
-        Job j{};
-        j.ta = &maps.dl_mn; j.tb = &maps.h_mn; j.a_mn = 1; j.b_mn = 1;
-        j.m0 = 0; j.n0 = u * kBN; j.M = C; j.N = H;
-        j.a_c0 = 0; j.a_c1 = 0; j.b_c0 = j.n0; j.b_c1 = 0; j.n_kb = kb_b;
-        j.mode = eo ? E_OPT : E_F32; j.d = eo ? a.master + (a.gw2 - a.grad) : a.gw2; j.ldd = H;
-        j.bc1 = bc1; j.bc2 = bc2;
-        run(j);
-      } else if (eo && t == mt_h * nt_d + nt_h) {
-        // biases: their gradients were accumulated by the chain's column sums; consume + re-zero
-        for (int i = threadIdx.x; i < H + C; i += blockDim.x) {
-          float* gp = i < H ? a.gb1 + i : a.gb2 + (i - H);
-          const float g = __ldcg(gp);
-          *gp = 0.f;
-          opt_apply(a, gp - a.grad, 1, &g, bc1, bc2);
-        }
-      }
-      grid_barrier(a.barrier, bar_epoch);
-      if (eo) continue;   // the optimizer ran in the epilogues
+      stamp(step, 2);
     } else {
-    // ---- P1: h = relu(x W1^T + b1)
-    if (t < mt_b * nt_h) {
-      Job j{};
-      j.ta = &maps.x_k; j.tb = &maps.w1_k; j.a_mn = 0; j.b_mn = 0;
-      j.m0 = (t / nt_h) * kBM; j.n0 = (t % nt_h) * kBN; j.M = B; j.N = H;
-      j.a_c0 = 0; j.a_c1 = r0 + j.m0; j.b_c0 = 0; j.b_c1 = j.n0; j.n_kb = kb_d;
-      j.mode = E_BIAS_RELU_BF16; j.d = a.h; j.ldd = H; j.bias = a.b1;
-      run(j);
+      // ---- P2: logits -> dlogits / loss / db2
+      if (t < mt_b) {
+        Job j{};
+        j.ta = &maps.h_k; j.tb = &maps.w2_k; j.a_mn = 0; j.b_mn = 0;
+        j.m0 = t * kBM; j.n0 = 0; j.M = B; j.N = C;
+        j.a_c0 = 0; j.a_c1 = j.m0; j.b_c0 = 0; j.b_c1 = 0; j.n_kb = kb_h;
+        j.mode = E_XENT; j.d = a.dlogits; j.ldd = a.ncp; j.bias = a.b2; j.colsum = a.gb2;
+        j.labels = a.labels + r0; j.grad_scale = 1.f / static_cast<float>(B);
+        run(j);
+      }
+      grid_barrier(a.barrier, bar_epoch);
+      // ---- P3: dh = (dlogits W2) * relu'(h), db1
+      if (t < mt_b * nt_h) {
+        Job j{};
+        j.ta = &maps.dl_k; j.tb = &maps.w2_mn; j.a_mn = 0; j.b_mn = 1;
+        j.m0 = (t / nt_h) * kBM; j.n0 = (t % nt_h) * kBN; j.M = B; j.N = H;
+        j.a_c0 = 0; j.a_c1 = j.m0; j.b_c0 = j.n0; j.b_c1 = 0; j.n_kb = kb_c;
+        j.mode = E_MASK_COLSUM_BF16; j.d = a.dh; j.ldd = H; j.aux = a.h; j.colsum = a.gb1;
+        run(j);
+      }
+      grid_barrier(a.barrier, bar_epoch);
+      stamp(step, 2);
     }
-    grid_barrier(a.barrier, bar_epoch);
-    // ---- P2: logits -> dlogits / loss / db2
-    if (t < mt_b) {
-      Job j{};
-      j.ta = &maps.h_k; j.tb = &maps.w2_k; j.a_mn = 0; j.b_mn = 0;
-      j.m0 = t * kBM; j.n0 = 0; j.M = B; j.N = C;
-      j.a_c0 = 0; j.a_c1 = j.m0; j.b_c0 = 0; j.b_c1 = 0; j.n_kb = kb_h;
-      j.mode = E_XENT; j.d = a.dlogits; j.ldd = a.ncp; j.bias = a.b2; j.colsum = a.gb2;
-      j.labels = a.labels + r0; j.grad_scale = 1.f / static_cast<float>(B);
-      run(j);
-    }
-    grid_barrier(a.barrier, bar_epoch);
-    // ---- P3: dW2 (tiles [0, nt_h))  ||  dh (tiles [nt_h, nt_h + mt_b*nt_h))
-    if (t < nt_h) {
-      Job j{};
-      j.ta = &maps.dl_mn; j.tb = &maps.h_mn; j.a_mn = 1; j.b_mn = 1;
-      j.m0 = 0; j.n0 = t * kBN; j.M = C; j.N = H;
-      j.a_c0 = 0; j.a_c1 = 0; j.b_c0 = j.n0; j.b_c1 = 0; j.n_kb = kb_b;
-      j.mode = E_F32; j.d = a.gw2; j.ldd = H;
-      run(j);
-    } else if (t < nt_h + mt_b * nt_h) {
-      const int u = t - nt_h;
-      Job j{};
-      j.ta = &maps.dl_k; j.tb = &maps.w2_mn; j.a_mn = 0; j.b_mn = 1;
-      j.m0 = (u / nt_h) * kBM; j.n0 = (u % nt_h) * kBN; j.M = B; j.N = H;
-      j.a_c0 = 0; j.a_c1 = j.m0; j.b_c0 = j.n0; j.b_c1 = 0; j.n_kb = kb_c;
-      j.mode = E_MASK_COLSUM_BF16; j.d = a.dh; j.ldd = H; j.aux = a.h; j.colsum = a.gb1;
-      run(j);
-    }
-    grid_barrier(a.barrier, bar_epoch);
-    // ---- P4: dW1 = dh^T x
+    // ---- B: dW1 = dh^T x (tiles [0, mt_h*nt_d))  ||  dW2 = dlogits^T h (next nt_h tiles)  || biases
     if (t < mt_h * nt_d) {
       Job j{};
       j.ta = &maps.dh_mn; j.tb = &maps.x_mn; j.a_mn = 1; j.b_mn = 1;
       j.m0 = (t / nt_d) * kBM; j.n0 = (t % nt_d) * kBN; j.M = H; j.N = D;
       j.a_c0 = j.m0; j.a_c1 = 0; j.b_c0 = j.n0; j.b_c1 = r0; j.n_kb = kb_b;
-      j.mode = E_F32; j.d = a.gw1; j.ldd = D;
+      j.mode = eo ? E_OPT : E_F32; j.d = eo ? a.master + (a.gw1 - a.grad) : a.gw1; j.ldd = D;
+      j.bc1 = bc1; j.bc2 = bc2;
       run(j);
+    } else if (t < mt_h * nt_d + nt_h) {
+      const int u = t - mt_h * nt_d;
+      Job j{};
+      j.ta = &maps.dl_mn; j.tb = &maps.h_mn; j.a_mn = 1; j.b_mn = 1;
+      j.m0 = 0; j.n0 = u * kBN; j.M = C; j.N = H;
+      j.a_c0 = 0; j.a_c1 = 0; j.b_c0 = j.n0; j.b_c1 = 0; j.n_kb = kb_b;
+      j.mode = eo ? E_OPT : E_F32; j.d = eo ? a.master + (a.gw2 - a.grad) : a.gw2; j.ldd = H;
+      j.bc1 = bc1; j.bc2 = bc2;
+      run(j);
+    } else if (eo && t == mt_h * nt_d + nt_h) {
+      // biases: their gradients were accumulated by column sums earlier in the step; consume + re-zero
+      for (int i = threadIdx.x; i < H + C; i += blockDim.x) {
+        float* gp = i < H ? a.gb1 + i : a.gb2 + (i - H);
+        const float g = __ldcg(gp);
+        *gp = 0.f;
+        opt_apply(a, gp - a.grad, 1, &g, bc1, bc2);
+      }
     }
+    stamp(step, 3);
     grid_barrier(a.barrier, bar_epoch);
-    }  // !chain
+    stamp(step, 4);
+    if (eo) continue;   // the optimizer ran in the epilogues
     // ---- P5: optimizer over the flat buffer (all threads of all CTAs)
     {
       const long long nv = a.n_params / 4;
       const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-      for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
-           i += stride) {
-        const float4 w4 = __ldcg(reinterpret_cast<const float4*>(a.master) + i);
+      for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv; i += stride) {
         const float4 g4 = __ldcg(reinterpret_cast<const float4*>(a.grad) + i);
-        float w[4] = {w4.x, w4.y, w4.z, w4.w};
         const float g[4] = {g4.x, g4.y, g4.z, g4.w};
-        if (a.adam) {
-          const float4 m4 = __ldcg(reinterpret_cast<const float4*>(a.adam_m) + i);
-          const float4 v4 = __ldcg(reinterpret_cast<const float4*>(a.adam_v) + i);
-          float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            m[k] = a.beta1 * m[k] + (1.f - a.beta1) * g[k];
-            v[k] = a.beta2 * v[k] + (1.f - a.beta2) * g[k] * g[k];
-            w[k] -= a.lr * (m[k] / bc1) / (sqrtf(v[k] / bc2) + a.eps);
-          }
-          reinterpret_cast<float4*>(a.adam_m)[i] = make_float4(m[0], m[1], m[2], m[3]);
-          reinterpret_cast<float4*>(a.adam_v)[i] = make_float4(v[0], v[1], v[2], v[3]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) w[k] -= a.lr * g[k];
-        }
-        reinterpret_cast<float4*>(a.master)[i] = make_float4(w[0], w[1], w[2], w[3]);
-        reinterpret_cast<uint2*>(a.shadow)[i] = make_uint2(pack2(w[0], w[1]), pack2(w[2], w[3]));
+        opt_apply(a, 4 * i, 4, g, bc1, bc2);
         reinterpret_cast<float4*>(a.grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     grid_barrier(a.barrier, bar_epoch);
+    stamp(step, 5);
   }
 
   __syncthreads();
@@ -1068,10 +1158,12 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
     return cudaErrorInvalidValue;
   const int mt_b = (r.batch + kBM - 1) / kBM, nt_h = (r.hidden + kBN - 1) / kBN;
   const int nt_d = (r.in_dim + kBN - 1) / kBN, mt_h = (r.hidden + kBM - 1) / kBM;
-  static const bool chain_env = [] { const char* e = std::getenv("BFLC_MLP_CHAIN"); return !(e && e[0] == '0'); }();
-  const bool chain = chain_env && r.hidden == kChainH && r.ncp == 64 && r.n_classes <= 64;
-  const int need = chain ? std::max(mt_h * nt_d + nt_h + 1, mt_b)
-                         : std::max(std::max(mt_b * nt_h + nt_h, mt_h * nt_d), mt_b);
+  // BFLC_MLP_CHAIN = 0 | 1 | 3 (phase plan, see the kernel), BFLC_MLP_EPIOPT = 0 | 1
+  static const int chain_env = [] { const char* e = std::getenv("BFLC_MLP_CHAIN"); return e ? std::atoi(e) : 3; }();
+  static const bool epiopt_env = [] { const char* e = std::getenv("BFLC_MLP_EPIOPT"); return !(e && e[0] == '0'); }();
+  const bool chain_ok = r.hidden == kChainH && r.ncp == 64 && r.n_classes <= 64;
+  const int chain = chain_ok ? (chain_env == 1 ? 1 : (chain_env == 0 ? 0 : 3)) : 0;
+  const int need = std::max(mt_b * nt_h, mt_h * nt_d + nt_h + 1);
   if (need > kGrid * 4) return cudaErrorInvalidValue;
   const int grid = need > kGrid ? need : kGrid;
   if (grid > 148) return cudaErrorInvalidValue;
@@ -1095,13 +1187,12 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
   if ((e = mk(&m.w2_mn, r.w2_shadow, r.hidden, true, r.hidden, r.n_classes, kBN)) != cudaSuccess) return e;
   if ((e = mk(&m.dh_mn, r.dh, r.hidden, true, r.hidden, r.batch, kBM)) != cudaSuccess) return e;
   if ((e = mk(&m.x_mn, r.x, r.in_dim, true, r.in_dim, (int)rows_x, kBN)) != cudaSuccess) return e;
-  if ((e = mk(&m.w1_k256, r.w1_shadow, r.in_dim, false, r.hidden, r.in_dim, chain ? 256 : kBN)) != cudaSuccess) return e;
+  if ((e = mk(&m.w1_k256, r.w1_shadow, r.in_dim, false, r.hidden, r.in_dim, chain == 1 ? 256 : kBN)) != cudaSuccess) return e;
 
   Args a{};
   a.B = r.batch; a.steps = r.steps; a.in_dim = r.in_dim; a.hidden = r.hidden;
   a.n_classes = r.n_classes; a.ncp = r.ncp; a.n_params = r.n_params;
-  static const bool epiopt_env = [] { const char* e = std::getenv("BFLC_MLP_EPIOPT"); return !(e && e[0] == '0'); }();
-  a.chain = chain ? (epiopt_env ? 2 : 1) : 0;
+  a.chain = chain; a.epiopt = epiopt_env ? 1 : 0; a.dbg = r.dbg;
   a.pred = r.pred ? r.pred : current_predicate();
   a.barrier = r.barrier;
   a.master = r.master; a.b1 = r.b1; a.b2 = r.b2;

@@ -114,19 +114,20 @@ class FlatMLP:
         """Shape limits of the persistent one-launch trainer (csrc/kernels/mlp_round_sm100.cu)."""
         B, H, D = self.batch, self.hidden, self.in_dim
         mt_b, nt_h, nt_d, mt_h = -(-B // 128), -(-H // 64), -(-D // 64), -(-H // 128)
-        need = max(mt_b * nt_h + nt_h, mt_h * nt_d, mt_b)
+        need = max(mt_b * nt_h, mt_h * nt_d + nt_h + 1)
         return (need <= 128 and B % 8 == 0 and H % 8 == 0 and D % 8 == 0 and self.n_classes <= 64)
 
     def train_epoch_fused(self, X: torch.Tensor, Y: torch.Tensor, steps: int,
-                          barrier_ptr: int) -> None:
+                          barrier_ptr: int, dbg: Optional[torch.Tensor] = None) -> None:
         """All ``steps`` mini-batch steps in ONE persistent kernel launch; ``barrier_ptr`` is a
-        device uint32 that is zero on entry (the phase barrier)."""
+        device uint32 that is zero on entry (the phase barrier).  ``dbg``: optional int64
+        [steps, 16] buffer that receives %globaltimer phase stamps of CTA 0."""
         e = self.spec.by_name
         offs = [e["w1"].offset, e["b1"].offset, e["w2"].offset, e["b2"].offset]
         C().mlp_round(X, Y, self.master, self.shadow, self.grad, offs, self.h, self.dlogits,
                       self.dh, self.loss_sum, self.correct, barrier_ptr, self.batch, steps,
                       self.in_dim, self.hidden, self.n_classes, self.lr,
-                      self.optimizer == "adam", self.m, self.v, self.step_dev_ptr)
+                      self.optimizer == "adam", self.m, self.v, self.step_dev_ptr, dbg)
 
     # ------------------------------------------------------------ evaluation
     def accuracy_counts(self, X: torch.Tensor, Y: torch.Tensor, shadow: Optional[torch.Tensor] = None,
