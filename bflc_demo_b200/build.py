@@ -95,6 +95,8 @@ def build_all(verbose: bool = True) -> dict:
 
     # --- ledger runtime (pure C++)
     for src in sorted((CSRC / "ledger").glob("*.cpp")):
+        if src.stem.endswith("_selftest"):      # stand-alone sanitizer driver (has its own main)
+            continue
         obj = OBJ / ("ledger_" + src.stem + ".o")
         flags = CXX_FLAGS + inc_flags + [f"-I{py_inc}", f"-I{pyb_inc}"]
         objs_ledger.append(obj)

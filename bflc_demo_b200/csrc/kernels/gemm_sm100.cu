@@ -83,6 +83,14 @@ struct SmemLayout {
 
 constexpr int kStgLd = 36;  // floats per staged row: 16-byte aligned, conflict-free both ways
 
+// sum of column `lane` over the first rmax rows of a staged 32 x 32 sub-tile; the 32 loads are
+// independent (a rolled `tot += stg[...]` loop serialises ~25-cycle smem latencies)
+__device__ __forceinline__ float col_sum32(const float* stg, int lane, int rmax) {
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) t[rr & 3] += rr < rmax ? stg[rr * kStgLd + lane] : 0.f;
+  return (t[0] + t[1]) + (t[2] + t[3]);
+}
 __device__ __forceinline__ void stage_put(float* stg, int lane, const float (&v)[32]) {
   float4* rowp = reinterpret_cast<float4*>(stg + lane * kStgLd);
 #pragma unroll
@@ -415,9 +423,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tile_store<2, false>(stg, p.d, tile_off, p.ldd, row_base, nc, p.M, p.N, cr, cg, p.vec_ok);
         if (p.colsum != nullptr) {
           // column sums straight from the staged tile: lane j adds up column j over valid rows
-          float tot = 0.f;
-          const int rmax = min(32, p.M - row_base);
-          for (int rr = 0; rr < rmax; ++rr) tot += stg[rr * kStgLd + lane];
+          const float tot = col_sum32(stg, lane, min(32, p.M - row_base));
           if (nc + lane < p.N) atomicAdd(p.colsum + nc + lane, tot);
         }
         __syncwarp();
@@ -495,8 +501,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tile_store<1, false>(stg, p.d, tile_off, p.ldd, row_base, nc, p.M,
                                  static_cast<int>(p.ldd), cr, cg, p.vec_ok);
           if (p.colsum != nullptr) {
-            float tot = 0.f;
-            for (int rr = 0; rr < 32; ++rr) tot += stg[rr * kStgLd + lane];
+            const float tot = col_sum32(stg, lane, 32);
             if (nc + lane < p.N) atomicAdd(p.colsum + nc + lane, tot);
           }
           __syncwarp();
