@@ -460,16 +460,18 @@ __device__ __forceinline__ void st_sw128(uint8_t* tile, int r, int chunk, uint4 
 }
 
 __device__ __forceinline__ void chain_produce(const Maps& maps, const Args& a, uint8_t* smem,
-                                              const ChainBars& cb, CPipe& cp, int r0, int m0, bool f1) {
+                                              const ChainBars& cb, CPipe& cp, int r0, int m0, bool f1,
+                                              int slice) {
   const uint32_t par = cp.n & 1;
   const int row0 = r0 + m0;
   if (!f1) {
     // h was produced by P1: TMA drops its 128 x 256 tile straight into the swizzled A-operand
-    // slots; both W2 forms can be fetched at once (no fwd1 stages to alias)
+    // slots; both W2 forms can be fetched at once (no fwd1 stages to alias).  This CTA computes
+    // only hidden columns [64*slice, 64*slice+64) of dh: one 8 KB chunk of W2^T.
     if (ptx::elect_one()) {
       ptx::mbar_expect_tx(cb.w2k, 32768);
       ptx::mbar_expect_tx(&cb.full[0], 65536);
-      ptx::mbar_expect_tx(cb.w2mn, 32768);
+      ptx::mbar_expect_tx(cb.w2mn, 8192);
       // in the order the chain consumes them: h and W2 (fwd2) first, W2^T (dh) last
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb)
@@ -477,9 +479,7 @@ __device__ __forceinline__ void chain_produce(const Maps& maps, const Args& a, u
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb)
         ptx::tma_load_3d(smem + kOffW2K + kb * 8192, &maps.w2_k, cb.w2k, kb * 64, 0, 0);
-#pragma unroll
-      for (int kb = 0; kb < 4; ++kb)
-        ptx::tma_load_3d(smem + kOffW2MN + kb * 8192, &maps.w2_mn, cb.w2mn, kb * 64, 0, 0);
+      ptx::tma_load_3d(smem + kOffW2MN, &maps.w2_mn, cb.w2mn, slice * 64, 0, 0);
     }
     __syncwarp();
     ++cp.n;
@@ -567,7 +567,7 @@ __device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, const Ch
   ptx::mbar_wait(cb.dl_ready, par);
   ptx::tc_fence_after_sync();
   if (ptx::elect_one()) {
-    const uint32_t id3 = ptx::make_idesc(1u, 0u, 1u, kBM, 256);
+    const uint32_t id3 = ptx::make_idesc(1u, 0u, 1u, kBM, f1 ? 256 : 64);   // !f1: one 64-column slice
     const uint32_t lo_a0 = (base_lo + (kOffDL >> 4)) | (1u << 16);
     const uint32_t lo_b0 = (base_lo + (kOffW2MN >> 4)) | ((8192u >> 4) << 16);
 #pragma unroll
@@ -582,7 +582,7 @@ __device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, const Ch
 
 __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, const ChainBars& cb,
                                                uint32_t tmem_base, int warp, int lane, float* stage_base,
-                                               float* sb, CPipe& cp, int m0, int r0, bool f1,
+                                               float* sb, CPipe& cp, int m0, int r0, bool f1, int slice,
                                                unsigned long long* dbg) {
   const uint32_t par = cp.n & 1;
   auto stampc = [&](int slot) {
@@ -609,12 +609,14 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
 
   // ---- E1: h
   uint32_t mask[8];
+  uint32_t mk[2] = {0u, 0u};     // !f1: relu mask of this CTA's 64 hidden columns
   if (!f1) {
     // h tile came in by TMA: only the relu mask is needed (read back through the swizzle)
     ptx::mbar_wait(&cb.full[0], par);
     const uint8_t* hs = smem + kOffH;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = 2 * slice + cc;
       uint32_t m = 0;
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
@@ -628,7 +630,7 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
           m |= (((wds[e] >> 16) != 0u && (wds[e] & 0x80000000u) == 0u) ? 1u : 0u) << (jj * 8 + e * 2 + 1);
         }
       }
-      mask[c] = m;
+      mk[cc] = m;
     }
     stampc(6);
   } else {
@@ -703,8 +705,9 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
     float loss = row_ok ? (__logf(sum) + vmax - zlab) : 0.f;
     const bool hit = row_ok && (amax == label);
     const float gs = 1.f / static_cast<float>(a.B);
+    // the 4 slice-CTAs of an M-tile all need dlogits in smem, but the bookkeeping is done once:
+    const bool do_colsum = f1 || slice == 1, do_global = f1 || slice == 2, do_loss = f1 || slice == 3;
     uint8_t* dls = smem + kOffDL;
-    __nv_bfloat16* dlg = a.dlogits + static_cast<long long>(row) * a.ncp;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       float v[32];
@@ -718,25 +721,39 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
         const uint4 u = make_uint4(pack2(v[8 * jj], v[8 * jj + 1]), pack2(v[8 * jj + 2], v[8 * jj + 3]),
                                    pack2(v[8 * jj + 4], v[8 * jj + 5]), pack2(v[8 * jj + 6], v[8 * jj + 7]));
         st_sw128(dls, rl, c * 4 + jj, u);
-        if (row_ok && c * 32 + jj * 8 < a.ncp) reinterpret_cast<uint4*>(dlg + c * 32)[jj] = u;
       }
-      stage_put(stg, lane, v);
-      __syncwarp();
-      const float tot = col_sum32(stg, lane, 32);
-      if (c * 32 + lane < C) atomicAdd(a.gb2 + c * 32 + lane, tot);
-      __syncwarp();
+      if (do_colsum) {
+        stage_put(stg, lane, v);
+        __syncwarp();
+        const float tot = col_sum32(stg, lane, 32);
+        if (c * 32 + lane < C) atomicAdd(a.gb2 + c * 32 + lane, tot);
+        __syncwarp();
+      }
+    }
+    // hand the tile to the dh MMA first, then finish the bookkeeping underneath it
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before_sync();
+    ptx::mbar_arrive(cb.dl_ready);
+    // dlogits -> global for dW2, read back out of the swizzled tile so that one store
+    // instruction covers 4 whole rows (a row-per-thread store touches 32 lines per instruction)
+    __syncwarp();
+    if (do_global) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rt = q * 32 + it * 4 + (lane >> 3), ch = lane & 7;
+        const uint4 u = *reinterpret_cast<const uint4*>(dls + rt * 128 + ((ch ^ (rt & 7)) << 4));
+        if (m0 + rt < a.B && ch * 8 < a.ncp)
+          *reinterpret_cast<uint4*>(a.dlogits + static_cast<long long>(m0 + rt) * a.ncp + ch * 8) = u;
+      }
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, off);
     const unsigned cnt = __popc(__ballot_sync(0xffffffffu, hit));
-    if (lane == 0) {
+    if (lane == 0 && do_loss) {
       atomicAdd(a.loss_sum, loss);
       if (cnt) atomicAdd(a.correct, cnt);
     }
   }
-  ptx::fence_proxy_async_smem();
-  ptx::tc_fence_before_sync();
-  ptx::mbar_arrive(cb.dl_ready);
   stampc(9);
 
   // ---- E3: dh = (dlogits W2) * relu'(h), db1
@@ -744,7 +761,39 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
   ptx::tc_fence_after_sync();
   stampc(10);
   {
-    __nv_bfloat16* dg = a.dh + static_cast<long long>(row) * a.hidden;
+    // The h tile in [0, 64 KB) is dead (fwd2 retired before acc_l, the mask is in registers): it
+    // becomes a 128 x 512-byte bf16 staging tile so that dh leaves the SM one whole row (4 full
+    // lines) per store instruction instead of 32 scattered 16-byte pieces.
+    uint8_t* ds = smem + kOffH;
+    if (!f1) {
+      // 64-column slice: 128-byte staging rows, 4 whole rows per store instruction
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(taddr + cc * 32, r);
+        ptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = ((mk[cc] >> k) & 1u) ? __uint_as_float(r[k]) : 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          st_sw128(ds, rl, cc * 4 + jj,
+                   make_uint4(pack2(v[8 * jj], v[8 * jj + 1]), pack2(v[8 * jj + 2], v[8 * jj + 3]),
+                              pack2(v[8 * jj + 4], v[8 * jj + 5]), pack2(v[8 * jj + 6], v[8 * jj + 7])));
+        stage_put(stg, lane, v);
+        __syncwarp();
+        const float tot = col_sum32(stg, lane, 32);
+        atomicAdd(a.gb1 + (2 * slice + cc) * 32 + lane, tot);
+        __syncwarp();
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rt = q * 32 + it * 4 + (lane >> 3), ch = lane & 7;
+        const uint4 u = *reinterpret_cast<const uint4*>(ds + rt * 128 + ((ch ^ (rt & 7)) << 4));
+        if (m0 + rt < a.B)
+          *reinterpret_cast<uint4*>(a.dh + static_cast<long long>(m0 + rt) * a.hidden + slice * 64 + ch * 8) = u;
+      }
+    } else {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       uint32_t r[32];
@@ -753,18 +802,24 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
       float v[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) v[k] = ((mask[c] >> k) & 1u) ? __uint_as_float(r[k]) : 0.f;
-      if (row_ok) {
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-          reinterpret_cast<uint4*>(dg + c * 32)[jj] =
-              make_uint4(pack2(v[8 * jj], v[8 * jj + 1]), pack2(v[8 * jj + 2], v[8 * jj + 3]),
-                         pack2(v[8 * jj + 4], v[8 * jj + 5]), pack2(v[8 * jj + 6], v[8 * jj + 7]));
-      }
+      for (int jj = 0; jj < 4; ++jj)
+        *reinterpret_cast<uint4*>(ds + rl * 512 + (((c * 4 + jj) ^ (rl & 7)) << 4)) =
+            make_uint4(pack2(v[8 * jj], v[8 * jj + 1]), pack2(v[8 * jj + 2], v[8 * jj + 3]),
+                       pack2(v[8 * jj + 4], v[8 * jj + 5]), pack2(v[8 * jj + 6], v[8 * jj + 7]));
       stage_put(stg, lane, v);
       __syncwarp();
       const float tot = col_sum32(stg, lane, 32);
       atomicAdd(a.gb1 + c * 32 + lane, tot);
       __syncwarp();
+    }
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr) {
+      const int rt = q * 32 + rr;
+      if (m0 + rt >= a.B) break;
+      const uint4 u = *reinterpret_cast<const uint4*>(ds + rt * 512 + ((lane ^ (rt & 7)) << 4));
+      *reinterpret_cast<uint4*>(a.dh + static_cast<long long>(m0 + rt) * a.hidden + lane * 8) = u;
+    }
     }
   }
   ptx::tc_fence_before_sync();
@@ -894,12 +949,15 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
     }
     if (a.chain != 0) {
       // ---- chained tail (or whole) of the forward/backward pass per 128-row tile
-      if (t < mt_b) {
-        const int m0 = t * kBM;
-        const bool f1 = a.chain == 1;
-        if (warp == 0) chain_produce(maps, a, smem, cb, cp, r0, m0, f1);
+      // chain 1: one CTA per M-tile; chain 3: four CTAs per M-tile, each redoes fwd2 + xent (cheap)
+      // and owns a 64-column slice of dh, so the long dh epilogue runs 4-wide
+      const bool f1 = a.chain == 1;
+      const int xs = f1 ? 1 : 4;
+      if (t < mt_b * xs) {
+        const int m0 = (t / xs) * kBM, slice = t % xs;
+        if (warp == 0) chain_produce(maps, a, smem, cb, cp, r0, m0, f1, slice);
         else if (warp == 1) chain_mma(a, smem, cb, tmem_base, cp, f1);
-        else chain_epilogue(a, smem, cb, tmem_base, warp, lane, stage_base, sbias, cp, m0, r0, f1,
+        else chain_epilogue(a, smem, cb, tmem_base, warp, lane, stage_base, sbias, cp, m0, r0, f1, slice,
                             a.dbg != nullptr ? a.dbg + step * 16 : nullptr);
       }
       grid_barrier(a.barrier, bar_epoch);
@@ -1174,7 +1232,7 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
   static const bool epiopt_env = [] { const char* e = std::getenv("BFLC_MLP_EPIOPT"); return !(e && e[0] == '0'); }();
   const bool chain_ok = r.hidden == kChainH && r.ncp == 64 && r.n_classes <= 64;
   const int chain = chain_ok ? (chain_env == 1 ? 1 : (chain_env == 0 ? 0 : 3)) : 0;
-  const int need = std::max(mt_b * nt_h, mt_h * nt_d + nt_h + 1);
+  const int need = std::max(std::max(mt_b * nt_h, mt_h * nt_d + nt_h + 1), chain == 3 ? mt_b * 4 : 0);
   if (need > kGrid * 4) return cudaErrorInvalidValue;
   const int grid = need > kGrid ? need : kGrid;
   if (grid > 148) return cudaErrorInvalidValue;
