@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--no-fused-step", action="store_true", help="fused arm: one launch per GEMM instead of the persistent training kernel")
     ap.add_argument("--no-stage", action="store_true", help="fused arm: validation GEMMs TMA-load peers' HBM directly")
     ap.add_argument("--broadcast", action="store_true", help="nccl arm: literal average+broadcast")
+    ap.add_argument("--two-shot", default="auto", choices=["auto", "on", "off"],
+                    help="fused arm: FedAvg as reduce-own-slice + multicast publish (auto: by model size)")
     return ap.parse_args()
 
 
@@ -135,7 +137,8 @@ def main():
                              batch_size=args.batch, samples_per_client=args.samples,
                              optimizer=args.optimizer, learning_rate=0.05, dtype="bf16",
                              cuda_graph=not args.no_graph, ring_slots=1024,
-                             fused_step=not args.no_fused_step, stage_candidates=not args.no_stage)
+                             fused_step=not args.no_fused_step, stage_candidates=not args.no_stage,
+                             two_shot={"auto": None, "on": True, "off": False}[args.two_shot])
     shard = femnist_like(n, args.samples, seed=7, only=rank)[0]
     # a small pool of distinct pinned input sets the e2e loop cycles through
     pool = [femnist_like(n, args.samples, seed=100 + i, only=rank)[0] for i in range(3)]
@@ -234,6 +237,7 @@ def main():
                  "chain_ok": eng.host_ledger.verify_chain(), "epoch": st["epoch"],
                  "global_loss": st["global_loss"], "symm": eng.heap.describe(),
                  "launches_per_round": eng.launches_per_round, "fused_step": eng.fused_step,
+                 "two_shot": bool(eng.two_shot),
                  "staged_validation": eng.staged}
         # device-stamped phase breakdown (%globaltimer inside the fed kernels), median of 9 extra
         # rounds per rank, then the max over ranks of each phase
