@@ -196,7 +196,7 @@ void bind_extra(py::module_& m) {
                         at::Tensor dh, at::Tensor loss_sum, at::Tensor correct, int64_t barrier_ptr,
                         int batch, int steps, int in_dim, int hidden, int n_classes, double lr,
                         bool adam, const OptT& mm, const OptT& vv, int64_t step_base_ptr,
-                        const OptT& dbg) {
+                        const OptT& dbg, int plan, int epiopt) {
     TORCH_CHECK(offs.size() == 4, "offs = element offsets of w1, b1, w2, b2 in the flat buffer");
     bflc::MlpRoundArgs r;
     r.batch = batch; r.steps = steps; r.in_dim = in_dim; r.hidden = hidden; r.n_classes = n_classes;
@@ -218,6 +218,7 @@ void bind_extra(py::module_& m) {
     r.adam_v = vv.has_value() ? vv->data_ptr<float>() : nullptr;
     r.lr = (float)lr;
     r.step_base = P<const int>(step_base_ptr);
+    r.plan = plan; r.epiopt = epiopt;
     if (dbg.has_value()) {
       TORCH_CHECK(dbg->numel() >= (int64_t)steps * 16 && dbg->element_size() == 8, "dbg: int64 [steps, 16]");
       r.dbg = reinterpret_cast<unsigned long long*>(dbg->data_ptr());

@@ -129,6 +129,8 @@ struct MlpRoundArgs {
   float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
   const int* step_base = nullptr;
   unsigned long long* dbg = nullptr;  // optional [steps][16] %globaltimer stamps (CTA 0)
+  int plan = -1;     // phase plan override: 0 | 1 | 3 | 4 (see mlp_round_sm100.cu); -1 = env / default
+  int epiopt = -1;   // optimizer in the weight-gradient epilogues: 0 | 1; -1 = env / default
 };
 cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream);
 

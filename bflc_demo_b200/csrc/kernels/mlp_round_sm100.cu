@@ -54,7 +54,16 @@ constexpr int kOffDL = kOffW2MN + 32768;
 constexpr int kOffW2K = kCStages * kCStage;
 static_assert(kOffDL + 16384 <= kOffW2K && kOffW2K + 32768 <= kTileBytes, "chain smem layout");
 constexpr int kChainH = 256;
+constexpr int kDefaultPlan = 3;    // phase plan when neither the caller nor BFLC_MLP_CHAIN picks one
 constexpr int kTmemCols = 512;     // chain: h / dh accumulator [0,256) + logits [256,320)
+// ---- cluster plan (chain == 4): ring cut to 4 stages [0, 96 KB); the upper half is dedicated:
+//   [96, 160 KB) h tile assembled over DSMEM by the 4 fwd1 CTAs of an M-tile | [160, 192 KB) W2
+//   K-major, prefetched at step start.  W2^T slice and dlogits alias the (then dead) ring.
+constexpr int kOffH4 = 96 * 1024, kOffW2K4 = 160 * 1024, kOffW2MN4 = 0, kOffDL4 = 16 * 1024;
+constexpr int kOffHQ4 = 32 * 1024;   // this CTA's own 128 x 64 quarter of h, staged for the bulk copies
+static_assert(kOffW2K4 + 32768 <= kTileBytes, "cluster plan smem layout");
+
+struct ChainLay { int h, w2k, w2mn, dl; };   // byte offsets of the chain operands in this plan
 
 enum EpiMode : int { E_BIAS_RELU_BF16 = 0, E_XENT = 1, E_F32 = 2, E_MASK_COLSUM_BF16 = 3,
                      E_OPT = 4 };  // E_OPT: the tile IS the gradient -> optimizer applied in the epilogue
@@ -99,6 +108,8 @@ struct Job {  // one 128 x 64 output tile
   const int32_t* labels;        // E_XENT (already offset to this step's rows)
   float grad_scale;
   float bc1, bc2;               // E_OPT + Adam: bias corrections of this step
+  int dsm, dsm_kb;              // E_BIAS_RELU_BF16 in the cluster plan: broadcast into h-tile K-block dsm_kb
+  uint64_t* dsm_bar;            // (local address of) the mbarrier each destination CTA waits on
 };
 
 struct Pipe {  // persistent pipeline state of one role
@@ -143,12 +154,43 @@ __device__ __forceinline__ float col_sum32(const float* stg, int lane, int rmax)
   return (t[0] + t[1]) + (t[2] + t[3]);
 }
 
+// 16-byte chunk `chunk` of row r of a 128-byte-swizzled K-major operand tile (defined below)
+__device__ __forceinline__ void st_sw128(uint8_t* tile, int r, int chunk, uint4 v);
+
+// ---- thread-block cluster helpers (cluster plan, chain == 4)
+__device__ __forceinline__ void dsm_st_v4(uint32_t local_smem_addr, uint32_t cta_rank, uint4 v) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem_addr), "r"(cta_rank));
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+// 16-byte-multiple copy local smem -> smem of CTA `cta_rank` of the cluster, completing `bytes` of
+// the transaction count of THAT CTA's mbarrier (both given as this CTA's addresses of the same
+// objects; mapa translates them)
+__device__ __forceinline__ void dsm_bulk_copy(uint32_t dst_local, uint32_t src_local, uint32_t bytes,
+                                              uint32_t bar_local, uint32_t cta_rank) {
+  uint32_t rdst, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(dst_local), "r"(cta_rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar_local), "r"(cta_rank));
+  asm volatile(
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(rdst), "r"(src_local), "r"(bytes), "r"(rbar)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- producer / MMA / epilogue
+// `ns` = ring depth in use (8, or 4 in the cluster plan where the upper half of the ring memory
+// holds the DSMEM-assembled h tile and the prefetched W2)
 __device__ __forceinline__ void produce_tile(const Job& j, uint8_t* smem, uint64_t* full_bar,
-                                             uint64_t* empty_bar, Pipe& pp) {
+                                             uint64_t* empty_bar, Pipe& pp, uint32_t ns) {
   for (int i = 0; i < j.n_kb; ++i, ++pp.it) {
-    const int s = pp.it % kStages;
-    const uint32_t ph = (pp.it / kStages) & 1;
+    const int s = pp.it % ns;
+    const uint32_t ph = (pp.it / ns) & 1;
     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
     uint8_t* sa = smem + s * kStageBytes;
     uint8_t* sb = sa + kABytes;
@@ -171,7 +213,7 @@ __device__ __forceinline__ void produce_tile(const Job& j, uint8_t* smem, uint64
 
 __device__ __forceinline__ void mma_tile(const Job& j, uint8_t* smem, uint64_t* full_bar,
                                          uint64_t* empty_bar, uint64_t* accum_bar,
-                                         uint32_t tmem_base, Pipe& pp) {
+                                         uint32_t tmem_base, Pipe& pp, uint32_t ns) {
   const uint32_t idesc = ptx::make_idesc(1u, j.a_mn ? 1u : 0u, j.b_mn ? 1u : 0u, kBM, kBN);
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024, v1, SWIZZLE_128B
   const uint32_t base_lo = ptx::smem_u32(smem) >> 4;
@@ -180,8 +222,8 @@ __device__ __forceinline__ void mma_tile(const Job& j, uint8_t* smem, uint64_t* 
   const uint32_t lo_b0 = (base_lo + (kABytes >> 4)) | (lbo_b << 16);
   const uint32_t ks_a = (j.a_mn ? 2048u : 32u) >> 4, ks_b = (j.b_mn ? 2048u : 32u) >> 4;
   for (int i = 0; i < j.n_kb; ++i, ++pp.it) {
-    const int s = pp.it % kStages;
-    const uint32_t ph = (pp.it / kStages) & 1;
+    const int s = pp.it % ns;
+    const uint32_t ph = (pp.it / ns) & 1;
     ptx::mbar_wait(&full_bar[s], ph);
     ptx::tc_fence_after_sync();
     const uint32_t so = static_cast<uint32_t>(s) * (kStageBytes >> 4);
@@ -253,7 +295,7 @@ __device__ __forceinline__ void opt_apply(const Args& a, long long pi, int n, co
 // epilogue warps 2..5; `warp` is the hardware warp index
 __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int warp, int lane,
                                               uint64_t* accum_bar, uint32_t tmem_base,
-                                              float* stage_base, float* sbias, Pipe& pp) {
+                                              float* stage_base, float* sbias, Pipe& pp, uint8_t* smem) {
   const int q = warp & 3;
   float* stg = stage_base + (warp - 2) * (32 * kStgLd);
   const int row_base = j.m0 + q * 32;
@@ -330,6 +372,16 @@ __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int w
       if (j.mode == E_BIAS_RELU_BF16) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
+        if (j.dsm) {
+          // cluster plan: stage this CTA's 128 x 64 quarter of h as one swizzled 16 KB A-operand
+          // K-block in local smem (the ring is dead: the accumulator barrier has fired)
+          const int rl = q * 32 + lane;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            st_sw128(smem + kOffHQ4, rl, c * 4 + jj,
+                     make_uint4(pack2(v[8 * jj], v[8 * jj + 1]), pack2(v[8 * jj + 2], v[8 * jj + 3]),
+                                pack2(v[8 * jj + 4], v[8 * jj + 5]), pack2(v[8 * jj + 6], v[8 * jj + 7])));
+        }
       } else if (j.mode == E_MASK_COLSUM_BF16) {
         // coalesced (L2-coherent) load of the mask tile through the staging buffer
 #pragma unroll
@@ -380,6 +432,21 @@ __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int w
         if (nc + lane < j.N) atomicAdd(j.colsum + nc + lane, tot);
       }
       __syncwarp();
+    }
+    if (j.dsm) {
+      // ... and push it into K-block `dsm_kb` of the fwd2 A-operand tile of all four CTAs of the
+      // cluster with the bulk-copy engine (smem -> distributed smem); every copy completes
+      // 16 KB of the transaction the destination's mbarrier was armed with at step start, so
+      // the chain phase needs neither a grid barrier nor a TMA reload of h.
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const uint32_t src = ptx::smem_u32(smem + kOffHQ4);
+        const uint32_t dst = ptx::smem_u32(smem + kOffH4 + j.dsm_kb * 16384);
+        const uint32_t bar = ptx::smem_u32(j.dsm_bar);
+#pragma unroll
+        for (uint32_t rk = 0; rk < 4; ++rk) dsm_bulk_copy(dst, src, 16384u, bar, rk);
+      }
     }
   } else {
     // softmax cross-entropy over the N (<= 64) logits of each row
@@ -460,10 +527,22 @@ __device__ __forceinline__ void st_sw128(uint8_t* tile, int r, int chunk, uint4 
 }
 
 __device__ __forceinline__ void chain_produce(const Maps& maps, const Args& a, uint8_t* smem,
-                                              const ChainBars& cb, CPipe& cp, int r0, int m0, bool f1,
-                                              int slice) {
+                                              const ChainBars& cb, CPipe& cp, int r0, int m0, int mode,
+                                              int slice, const ChainLay& L) {
   const uint32_t par = cp.n & 1;
   const int row0 = r0 + m0;
+  const bool f1 = mode == 1;
+  if (mode == 4) {
+    // cluster plan: h arrives over DSMEM, W2 was prefetched at step start; only this CTA's
+    // 8 KB slice of W2^T is left to fetch (into ring memory that is dead by now)
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(cb.w2mn, 8192);
+      ptx::tma_load_3d(smem + L.w2mn, &maps.w2_mn, cb.w2mn, slice * 64, 0, 0);
+    }
+    __syncwarp();
+    ++cp.n;
+    return;
+  }
   if (!f1) {
     // h was produced by P1: TMA drops its 128 x 256 tile straight into the swizzled A-operand
     // slots; both W2 forms can be fetched at once (no fwd1 stages to alias).  This CTA computes
@@ -475,11 +554,11 @@ __device__ __forceinline__ void chain_produce(const Maps& maps, const Args& a, u
       // in the order the chain consumes them: h and W2 (fwd2) first, W2^T (dh) last
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb)
-        ptx::tma_load_3d(smem + kOffH + kb * 16384, &maps.h_k, &cb.full[0], kb * 64, m0, 0);
+        ptx::tma_load_3d(smem + L.h + kb * 16384, &maps.h_k, &cb.full[0], kb * 64, m0, 0);
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb)
-        ptx::tma_load_3d(smem + kOffW2K + kb * 8192, &maps.w2_k, cb.w2k, kb * 64, 0, 0);
-      ptx::tma_load_3d(smem + kOffW2MN, &maps.w2_mn, cb.w2mn, slice * 64, 0, 0);
+        ptx::tma_load_3d(smem + L.w2k + kb * 8192, &maps.w2_k, cb.w2k, kb * 64, 0, 0);
+      ptx::tma_load_3d(smem + L.w2mn, &maps.w2_mn, cb.w2mn, slice * 64, 0, 0);
     }
     __syncwarp();
     ++cp.n;
@@ -517,7 +596,8 @@ __device__ __forceinline__ void chain_produce(const Maps& maps, const Args& a, u
 }
 
 __device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, const ChainBars& cb,
-                                          uint32_t tmem_base, CPipe& cp, bool f1) {
+                                          uint32_t tmem_base, CPipe& cp, int mode, const ChainLay& L) {
+  const bool f1 = mode == 1;
   const uint32_t par = cp.n & 1;
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   const uint32_t base_lo = ptx::smem_u32(smem) >> 4;
@@ -546,12 +626,14 @@ __device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, const Ch
   }
   // fwd2: 128 x 64 x 256, A = h (smem: written by the epilogue warps, or by TMA), B = W2 K-major
   ptx::mbar_wait(cb.w2k, par);
+  // h tile: written by this CTA's epilogue warps (1), by TMA (3), or by the cluster over DSMEM
+  // before the cluster barrier every thread of this CTA has already passed (4)
   ptx::mbar_wait(f1 ? cb.h_ready : &cb.full[0], par);
   ptx::tc_fence_after_sync();
   if (ptx::elect_one()) {
     const uint32_t id2 = ptx::make_idesc(1u, 0u, 0u, kBM, 64);
-    const uint32_t lo_a0 = (base_lo + (kOffH >> 4)) | (1u << 16);
-    const uint32_t lo_b0 = (base_lo + (kOffW2K >> 4)) | (1u << 16);
+    const uint32_t lo_a0 = (base_lo + (static_cast<uint32_t>(L.h) >> 4)) | (1u << 16);
+    const uint32_t lo_b0 = (base_lo + (static_cast<uint32_t>(L.w2k) >> 4)) | (1u << 16);
 #pragma unroll
     for (uint32_t kb = 0; kb < 4; ++kb)
 #pragma unroll
@@ -568,8 +650,8 @@ __device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, const Ch
   ptx::tc_fence_after_sync();
   if (ptx::elect_one()) {
     const uint32_t id3 = ptx::make_idesc(1u, 0u, 1u, kBM, f1 ? 256 : 64);   // !f1: one 64-column slice
-    const uint32_t lo_a0 = (base_lo + (kOffDL >> 4)) | (1u << 16);
-    const uint32_t lo_b0 = (base_lo + (kOffW2MN >> 4)) | ((8192u >> 4) << 16);
+    const uint32_t lo_a0 = (base_lo + (static_cast<uint32_t>(L.dl) >> 4)) | (1u << 16);
+    const uint32_t lo_b0 = (base_lo + (static_cast<uint32_t>(L.w2mn) >> 4)) | ((8192u >> 4) << 16);
 #pragma unroll
     for (uint32_t k = 0; k < 4; ++k)
       ptx::umma_f16(tmem_base, (static_cast<uint64_t>(hi) << 32) | (lo_a0 + k * 2u),
@@ -582,8 +664,9 @@ __device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, const Ch
 
 __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, const ChainBars& cb,
                                                uint32_t tmem_base, int warp, int lane, float* stage_base,
-                                               float* sb, CPipe& cp, int m0, int r0, bool f1, int slice,
-                                               unsigned long long* dbg) {
+                                               float* sb, CPipe& cp, int m0, int r0, int mode, int slice,
+                                               const ChainLay& L, unsigned long long* dbg) {
+  const bool f1 = mode == 1;
   const uint32_t par = cp.n & 1;
   auto stampc = [&](int slot) {
     if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) {
@@ -612,8 +695,8 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
   uint32_t mk[2] = {0u, 0u};     // !f1: relu mask of this CTA's 64 hidden columns
   if (!f1) {
     // h tile came in by TMA: only the relu mask is needed (read back through the swizzle)
-    ptx::mbar_wait(&cb.full[0], par);
-    const uint8_t* hs = smem + kOffH;
+    ptx::mbar_wait(&cb.full[0], par);   // plan 3: the TMA of the h tile; plan 4: the cluster's pushes
+    const uint8_t* hs = smem + L.h;
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
       const int c = 2 * slice + cc;
@@ -707,7 +790,7 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
     const float gs = 1.f / static_cast<float>(a.B);
     // the 4 slice-CTAs of an M-tile all need dlogits in smem, but the bookkeeping is done once:
     const bool do_colsum = f1 || slice == 1, do_global = f1 || slice == 2, do_loss = f1 || slice == 3;
-    uint8_t* dls = smem + kOffDL;
+    uint8_t* dls = smem + L.dl;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       float v[32];
@@ -764,7 +847,7 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
     // The h tile in [0, 64 KB) is dead (fwd2 retired before acc_l, the mask is in registers): it
     // becomes a 128 x 512-byte bf16 staging tile so that dh leaves the SM one whole row (4 full
     // lines) per store instruction instead of 32 scattered 16-byte pieces.
-    uint8_t* ds = smem + kOffH;
+    uint8_t* ds = smem + L.h;
     if (!f1) {
       // 64-column slice: 128-byte staging rows, 4 whole rows per store instruction
 #pragma unroll
@@ -906,10 +989,11 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
   const int mt_h = (H + kBM - 1) / kBM;                 // M-tiles over hidden (dW1)
   const int kb_d = (D + 63) / 64, kb_h = (H + 63) / 64, kb_b = (B + 63) / 64, kb_c = (C + 63) / 64;
 
+  const uint32_t ns = a.chain == 4 ? 4u : static_cast<uint32_t>(kStages);
   auto run = [&](const Job& j) {
-    if (warp == 0) produce_tile(j, smem, full_bar, empty_bar, pp);
-    else if (warp == 1) mma_tile(j, smem, full_bar, empty_bar, accum_bar, tmem_base, pp);
-    else epilogue_tile(j, a, warp, lane, accum_bar, tmem_base, stage_base, sbias, pp);
+    if (warp == 0) produce_tile(j, smem, full_bar, empty_bar, pp, ns);
+    else if (warp == 1) mma_tile(j, smem, full_bar, empty_bar, accum_bar, tmem_base, pp, ns);
+    else epilogue_tile(j, a, warp, lane, accum_bar, tmem_base, stage_base, sbias, pp, smem);
   };
 
   // Phase plan of one step (a.chain, a.epiopt pick the variant; all are numerically equivalent):
@@ -934,6 +1018,20 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
     }
     const bool eo = a.epiopt != 0;
     stamp(step, 0);
+    const ChainLay L = a.chain == 4 ? ChainLay{kOffH4, kOffW2K4, kOffW2MN4, kOffDL4}
+                                    : ChainLay{kOffH, kOffW2K, kOffW2MN, kOffDL};
+    const bool in_chain_cta = a.chain >= 3 && t < mt_b * 4;
+    if (a.chain == 4 && in_chain_cta && warp == 0) {
+      // cluster plan: W2 (fwd2's B operand) is stable since the last barrier -- fetch it under P1
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(&cb.full[0], 65536);   // 4 x 16 KB of h, pushed by the cluster's fwd1 CTAs
+        ptx::mbar_expect_tx(cb.w2k, 32768);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+          ptx::tma_load_3d(smem + L.w2k + kb * 8192, &maps.w2_k, cb.w2k, kb * 64, 0, 0);
+      }
+      __syncwarp();
+    }
     if (a.chain != 1) {
       // ---- P1: h = relu(x W1^T + b1)
       if (t < mt_b * nt_h) {
@@ -942,23 +1040,31 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
         j.m0 = (t / nt_h) * kBM; j.n0 = (t % nt_h) * kBN; j.M = B; j.N = H;
         j.a_c0 = 0; j.a_c1 = r0 + j.m0; j.b_c0 = 0; j.b_c1 = j.n0; j.n_kb = kb_d;
         j.mode = E_BIAS_RELU_BF16; j.d = a.h; j.ldd = H; j.bias = a.b1;
+        j.dsm = a.chain == 4 ? 1 : 0; j.dsm_kb = t % nt_h; j.dsm_bar = &cb.full[0];
         run(j);
       }
-      grid_barrier(a.barrier, bar_epoch);
+      if (a.chain == 4) {
+        // The four fwd1 CTAs of an M-tile are one thread-block cluster and are exactly the four
+        // chain CTAs of that M-tile: no device-wide barrier -- each chain CTA just waits on its
+        // own mbarrier for the four 16 KB pushes.  The CTA-wide barrier only makes sure this
+        // CTA's fwd1 MMAs have retired before the chain reuses ring memory.
+        if (in_chain_cta) __syncthreads();
+      } else {
+        grid_barrier(a.barrier, bar_epoch);
+      }
       stamp(step, 1);
     }
     if (a.chain != 0) {
       // ---- chained tail (or whole) of the forward/backward pass per 128-row tile
-      // chain 1: one CTA per M-tile; chain 3: four CTAs per M-tile, each redoes fwd2 + xent (cheap)
-      // and owns a 64-column slice of dh, so the long dh epilogue runs 4-wide
-      const bool f1 = a.chain == 1;
-      const int xs = f1 ? 1 : 4;
+      // chain 1: one CTA per M-tile; chain 3/4: four CTAs per M-tile, each redoes fwd2 + xent
+      // (cheap) and owns a 64-column slice of dh, so the long dh epilogue runs 4-wide
+      const int xs = a.chain == 1 ? 1 : 4;
       if (t < mt_b * xs) {
         const int m0 = (t / xs) * kBM, slice = t % xs;
-        if (warp == 0) chain_produce(maps, a, smem, cb, cp, r0, m0, f1, slice);
-        else if (warp == 1) chain_mma(a, smem, cb, tmem_base, cp, f1);
-        else chain_epilogue(a, smem, cb, tmem_base, warp, lane, stage_base, sbias, cp, m0, r0, f1, slice,
-                            a.dbg != nullptr ? a.dbg + step * 16 : nullptr);
+        if (warp == 0) chain_produce(maps, a, smem, cb, cp, r0, m0, a.chain, slice, L);
+        else if (warp == 1) chain_mma(a, smem, cb, tmem_base, cp, a.chain, L);
+        else chain_epilogue(a, smem, cb, tmem_base, warp, lane, stage_base, sbias, cp, m0, r0, a.chain,
+                            slice, L, a.dbg != nullptr ? a.dbg + step * 16 : nullptr);
       }
       grid_barrier(a.barrier, bar_epoch);
       stamp(step, 2);
@@ -1227,11 +1333,17 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
     return cudaErrorInvalidValue;
   const int mt_b = (r.batch + kBM - 1) / kBM, nt_h = (r.hidden + kBN - 1) / kBN;
   const int nt_d = (r.in_dim + kBN - 1) / kBN, mt_h = (r.hidden + kBM - 1) / kBM;
-  // BFLC_MLP_CHAIN = 0 | 1 | 3 (phase plan, see the kernel), BFLC_MLP_EPIOPT = 0 | 1
-  static const int chain_env = [] { const char* e = std::getenv("BFLC_MLP_CHAIN"); return e ? std::atoi(e) : 3; }();
-  static const bool epiopt_env = [] { const char* e = std::getenv("BFLC_MLP_EPIOPT"); return !(e && e[0] == '0'); }();
+  // phase plan: r.plan / r.epiopt when >= 0, else BFLC_MLP_CHAIN = 0 | 1 | 3 | 4 and
+  // BFLC_MLP_EPIOPT = 0 | 1 (see the kernel), else the defaults
+  static const int chain_env0 = [] { const char* e = std::getenv("BFLC_MLP_CHAIN"); return e ? std::atoi(e) : kDefaultPlan; }();
+  static const bool epiopt_env0 = [] { const char* e = std::getenv("BFLC_MLP_EPIOPT"); return !(e && e[0] == '0'); }();
+  const int chain_env = r.plan >= 0 ? r.plan : chain_env0;
+  const bool epiopt_env = r.epiopt >= 0 ? r.epiopt != 0 : epiopt_env0;
   const bool chain_ok = r.hidden == kChainH && r.ncp == 64 && r.n_classes <= 64;
-  const int chain = chain_ok ? (chain_env == 1 ? 1 : (chain_env == 0 ? 0 : 3)) : 0;
+  // the cluster plan needs nt_h == 4 (one cluster of 4 CTAs per M-tile) and <= 8 M-tiles
+  const bool cluster_ok = chain_ok && nt_h == 4 && mt_b * 4 <= kGrid;
+  const int chain = !chain_ok ? 0
+                    : chain_env == 0 ? 0 : chain_env == 1 ? 1 : (chain_env == 4 && cluster_ok) ? 4 : 3;
   const int need = std::max(std::max(mt_b * nt_h, mt_h * nt_d + nt_h + 1), chain == 3 ? mt_b * 4 : 0);
   if (need > kGrid * 4) return cudaErrorInvalidValue;
   const int grid = need > kGrid ? need : kGrid;
@@ -1281,6 +1393,22 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
     configured = true;
   }
   note_launch();
+  if (chain == 4) {
+    // clusters of 4 consecutive CTAs (cluster c = M-tile c for c < mt_b), plus the PDL attribute
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((grid + 3) / 4 * 4);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, mlp_round_kernel, m, a);
+  }
   return launch_pdl(mlp_round_kernel, dim3(grid), dim3(kThreads), kSmemTotal, stream, m, a);
 }
 
