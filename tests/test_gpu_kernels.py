@@ -166,13 +166,13 @@ def test_mlp_training_step_matches_torch():
     assert bool((grad == 0).all())
 
 
-@pytest.mark.parametrize("plan,epiopt", [(-1, -1), (0, 0), (0, 1), (1, 1), (3, 0), (3, 1), (4, 1)])
+@pytest.mark.parametrize("plan,epiopt", [(-1, -1), (0, 0), (0, 1), (1, 1), (3, 0), (3, 1)])
 @pytest.mark.parametrize("B,steps,opt", [(256, 3, "sgd"), (512, 4, "adam"), (200, 2, "sgd")])
 def test_persistent_round_kernel_matches_six_kernel_path(B, steps, opt, plan, epiopt):
     """mlp_round_sm100.cu (one launch, grid barriers) vs the per-GEMM launches (models/mlp.py),
     for every phase plan: separate phases (0), whole chain per M-tile (1), fwd1 + 4-way sliced
-    xent/dh chain (3), the same with the h tile assembled over DSMEM inside a 4-CTA cluster (4);
-    optimizer as a flat phase (epiopt 0) or inside the weight-gradient epilogues (1)."""
+    xent/dh chain (3; the DSMEM/cluster variant 4 is experimental and maps to 3 unless
+    BFLC_MLP_EXPERIMENTAL=1); optimizer as a flat phase (epiopt 0) or inside the weight-gradient epilogues (1)."""
     from bflc_demo_b200.models.mlp import FlatMLP, mlp_spec
     torch.manual_seed(11)
     spec = mlp_spec(784, 256, 62)
