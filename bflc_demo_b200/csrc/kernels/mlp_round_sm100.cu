@@ -778,6 +778,7 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
         }
       }
     }
+    stampc(12);
     float sum = 0.f;
 #pragma unroll
     for (int n = 0; n < 64; ++n) {   // z <- exp(z - max): each exponential is evaluated once
@@ -814,9 +815,11 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
       }
     }
     // hand the tile to the dh MMA first, then finish the bookkeeping underneath it
+    stampc(13);
     ptx::fence_proxy_async_smem();
     ptx::tc_fence_before_sync();
     ptx::mbar_arrive(cb.dl_ready);
+    stampc(14);
     // dlogits -> global for dW2, read back out of the swizzled tile so that one store
     // instruction covers 4 whole rows (a row-per-thread store touches 32 lines per instruction)
     __syncwarp();

@@ -2,13 +2,16 @@
 CUDA graph each round; who trains and who validates is decided by data in the HBM ledger
 page (role bits), not by launch topology.
 
-  round graph (all ranks):
-    fed_plan_round                     QueryState       (local read of the ledger page)
-    cast u8 -> bf16                    this round's inputs
-    [trainer]  steps x 6 kernels       local training   (models/mlp.py)
+  round graph (all ranks; 7-8 launches):
+    fed_plan_round  ||  cast u8->bf16  QueryState (local read of the ledger page); this round's
+                                       inputs on a parallel graph branch
+    [trainer]  mlp_round               the whole local epoch in ONE persistent kernel
+                                       (csrc/kernels/mlp_round_sm100.cu; per-GEMM launches with
+                                       ``fused_step=False``: models/mlp.py)
     fed_upload                         UploadLocalUpdate (publish + release flags on peers)
-    [committee] 2 grouped GEMMs        QueryAllUpdates + validation: TMA pulls every
-                                       trainer's weights out of its HBM over NVLink
+    [committee] fed_pull_candidates    QueryAllUpdates: each candidate's weights cross NVLink once
+                mlp_val                validation of every candidate in one launch (or two grouped
+                                       GEMMs whose TMA pulls the trainers' HBM directly)
     fed_consensus_aggregate            UploadScores + Aggregate + QueryGlobalModel
 
 No NCCL call and no host synchronisation inside a round.  The host C++ ledger drains the

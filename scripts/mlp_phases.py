@@ -24,9 +24,10 @@ def main():
         tot.append(e0.elapsed_time(e1) * 1e3)
     d = dbg.cpu().double()
     names = {0: "step_begin", 1: "after_P1_barrier", 6: "chain:h/acc_h ready", 7: "chain:E1 done",
-             8: "chain:logits ready", 9: "chain:E2 done", 10: "chain:dh acc ready", 11: "chain:E3 done",
+             8: "chain:logits ready", 12: "chain:E2 max pass done", 13: "chain:E2 tile written",
+             14: "chain:E2 arrived", 9: "chain:E2 done", 10: "chain:dh acc ready", 11: "chain:E3 done",
              2: "after_chain/P3_barrier", 3: "B tile done", 4: "after_B_barrier", 5: "after_P5_barrier"}
-    order = [0, 1, 6, 7, 8, 9, 10, 11, 2, 3, 4, 5]
+    order = [0, 1, 6, 7, 8, 12, 13, 14, 9, 10, 11, 2, 3, 4, 5]
     rows = {}
     for s in range(1, steps):          # skip the cold first step
         t0 = d[s, 0].item()
