@@ -759,32 +759,43 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
   ptx::tc_fence_after_sync();
   stampc(8);
   {
-    float vmax = -INFINITY, zlab = 0.f;
-    int amax = -1;
+    // Latency matters more than instruction count here (one warp per SM sub-partition): both
+    // TMEM loads are in flight together, and max / argmax / sum use four independent chains.
     float z[64];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(taddr + 256 + c * 32, r);
+    {
+      uint32_t ra[32], rb[32];
+      ptx::tmem_ld_32x32b_x32(taddr + 256, ra);
+      ptx::tmem_ld_32x32b_x32(taddr + 288, rb);
       ptx::tmem_ld_wait();
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
-        const int n = c * 32 + k;
-        const float x = __uint_as_float(r[k]) + sb[kChainH + n];
-        z[n] = x;
-        if (n < C) {
-          if (x > vmax) { vmax = x; amax = n; }
-          if (n == label) zlab = x;
-        }
+        z[k] = __uint_as_float(ra[k]) + sb[kChainH + k];
+        z[32 + k] = __uint_as_float(rb[k]) + sb[kChainH + 32 + k];
       }
     }
+    float pm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int pi[4] = {-1, -1, -1, -1};
+    float zlab = 0.f;
+#pragma unroll
+    for (int n = 0; n < 64; ++n) {
+      if (n < C) {
+        if (z[n] > pm[n & 3]) { pm[n & 3] = z[n]; pi[n & 3] = n; }
+        if (n == label) zlab = z[n];
+      }
+    }
+    float vmax = pm[0];
+    int amax = pi[0];
+#pragma unroll
+    for (int jq = 1; jq < 4; ++jq)   // first maximum wins, as in the serial scan
+      if (pm[jq] > vmax || (pm[jq] == vmax && pi[jq] >= 0 && pi[jq] < amax)) { vmax = pm[jq]; amax = pi[jq]; }
     stampc(12);
-    float sum = 0.f;
+    float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int n = 0; n < 64; ++n) {   // z <- exp(z - max): each exponential is evaluated once
       z[n] = n < C ? __expf(z[n] - vmax) : 0.f;
-      sum += z[n];
+      ps[n & 3] += z[n];
     }
+    const float sum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
     const float inv = 1.f / sum;
     float loss = row_ok ? (__logf(sum) + vmax - zlab) : 0.f;
     const bool hit = row_ok && (amax == label);
