@@ -124,6 +124,7 @@ void bind_extra(py::module_& m) {
     d["plan_is_comm_off"] = offsetof(bflc::RoundPlan, is_comm);
     d["plan_step_barrier_off"] = offsetof(bflc::RoundPlan, step_barrier);
     d["plan_stamps_off"] = offsetof(bflc::RoundPlan, t_stamp);
+    d["plan_round_seq_off"] = offsetof(bflc::RoundPlan, round_seq);
     d["state_epoch_off"] = offsetof(bflc::RoundState, epoch);
     d["state_role_off"] = offsetof(bflc::RoundState, role);
     d["state_global_loss_off"] = offsetof(bflc::RoundState, global_loss);
@@ -196,7 +197,8 @@ void bind_extra(py::module_& m) {
                         at::Tensor dh, at::Tensor loss_sum, at::Tensor correct, int64_t barrier_ptr,
                         int batch, int steps, int in_dim, int hidden, int n_classes, double lr,
                         bool adam, const OptT& mm, const OptT& vv, int64_t step_base_ptr,
-                        const OptT& dbg, int plan, int epiopt) {
+                        const OptT& dbg, int plan, int epiopt, int64_t x_ready_ptr,
+                        int64_t round_seq_ptr) {
     TORCH_CHECK(offs.size() == 4, "offs = element offsets of w1, b1, w2, b2 in the flat buffer");
     bflc::MlpRoundArgs r;
     r.batch = batch; r.steps = steps; r.in_dim = in_dim; r.hidden = hidden; r.n_classes = n_classes;
@@ -219,6 +221,7 @@ void bind_extra(py::module_& m) {
     r.lr = (float)lr;
     r.step_base = P<const int>(step_base_ptr);
     r.plan = plan; r.epiopt = epiopt;
+    r.x_ready = P<const unsigned int>(x_ready_ptr); r.round_seq = P<const unsigned int>(round_seq_ptr);
     if (dbg.has_value()) {
       TORCH_CHECK(dbg->numel() >= (int64_t)steps * 16 && dbg->element_size() == 8, "dbg: int64 [steps, 16]");
       r.dbg = reinterpret_cast<unsigned long long*>(dbg->data_ptr());
@@ -269,6 +272,32 @@ void bind_extra(py::module_& m) {
   m.def("cast_bf16_to_f32", [](at::Tensor src, at::Tensor dst) {
     check(bflc::cast_bf16_to_f32(src.data_ptr(), dst.data_ptr<float>(), src.numel(), cur_stream()),
           "cast_bf16_to_f32");
+  });
+  // input pipeline (see k_cast_chunks): flag-driven chunked conversion + the host side that
+  // enqueues labels, the n chunks and their 4-byte tags on a copy stream in one call
+  m.def("cast_u8_to_bf16_chunks", [](at::Tensor src, at::Tensor dst, int64_t chunk_elems, int n_chunks,
+                                     double scale, at::Tensor in_flags, at::Tensor in_seq, at::Tensor cnt,
+                                     at::Tensor ready) {
+    check(bflc::cast_u8_to_bf16_chunks(src.data_ptr<uint8_t>(), dst.data_ptr(), chunk_elems, n_chunks,
+                                       (float)scale, in_flags.data_ptr<int32_t>(), in_seq.data_ptr<int32_t>(),
+                                       reinterpret_cast<unsigned int*>(cnt.data_ptr()),
+                                       reinterpret_cast<unsigned int*>(ready.data_ptr()), cur_stream()),
+          "cast_u8_to_bf16_chunks");
+  });
+  m.def("h2d_pipeline", [](int64_t host_x, int64_t dev_x, int64_t chunk_bytes, int c_begin, int c_end,
+                           int64_t host_y, int64_t dev_y, int64_t y_bytes, int64_t dev_flags,
+                           int64_t host_seq, int64_t stream_ptr) {
+    // chunks [c_begin, c_end); the labels travel with chunk 0 (y_bytes > 0)
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(static_cast<uintptr_t>(stream_ptr));
+    if (y_bytes > 0)
+      check(cudaMemcpyAsync(P<void>(dev_y), P<const void>(host_y), (size_t)y_bytes, cudaMemcpyHostToDevice, s),
+            "h2d labels");
+    for (int c = c_begin; c < c_end; ++c) {
+      check(cudaMemcpyAsync(P<char>(dev_x) + c * chunk_bytes, P<const char>(host_x) + c * chunk_bytes,
+                            (size_t)chunk_bytes, cudaMemcpyHostToDevice, s), "h2d chunk");
+      check(cudaMemcpyAsync(P<int32_t>(dev_flags) + c, P<const void>(host_seq), 4, cudaMemcpyHostToDevice, s),
+            "h2d tag");
+    }
   });
   m.def("cast_u8_to_bf16", [](at::Tensor src, at::Tensor dst, double scale) {
     check(bflc::cast_u8_to_bf16(src.data_ptr<uint8_t>(), dst.data_ptr(), src.numel(), (float)scale,

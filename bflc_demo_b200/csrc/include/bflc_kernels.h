@@ -129,6 +129,8 @@ struct MlpRoundArgs {
   float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
   const int* step_base = nullptr;
   unsigned long long* dbg = nullptr;  // optional [steps][16] %globaltimer stamps (CTA 0)
+  // optional input pipeline: producer of step s waits until x_ready[s] >= *round_seq
+  const unsigned int* x_ready = nullptr; const unsigned int* round_seq = nullptr;
   int plan = -1;     // phase plan override: 0 | 1 | 3 | 4 (see mlp_round_sm100.cu); -1 = env / default
   int epiopt = -1;   // optimizer in the weight-gradient epilogues: 0 | 1; -1 = env / default
 };
@@ -159,6 +161,10 @@ void note_launch();
 cudaError_t cast_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t s);
 cudaError_t cast_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t s);
 cudaError_t cast_u8_to_bf16(const uint8_t* src, void* dst, int64_t n, float scale, cudaStream_t s);
+// Chunked, flag-driven variant for the host->device input pipeline (see k_cast_chunks).
+cudaError_t cast_u8_to_bf16_chunks(const uint8_t* src, void* dst, long long chunk_elems, int n_chunks,
+                                   float scale, const int* in_flags, const int* in_seq,
+                                   unsigned int* cnt, unsigned int* ready, cudaStream_t s);
 cudaError_t quantize_fp8(const void* src_bf16, uint8_t* dst, int64_t n, float inv_scale,
                          cudaStream_t s);
 cudaError_t amax_bf16(const void* src, int64_t n, float* amax_out, cudaStream_t s);
@@ -277,7 +283,7 @@ struct RoundPlan {
   unsigned int consensus_blocks_done;
   unsigned long long digest_acc;
   unsigned int step_barrier;         // phase barrier of the persistent training kernel (zeroed per round)
-  unsigned int pad2;
+  unsigned int round_seq;            // rounds planned so far on this rank (k_plan increments; never reset)
   // %globaltimer (ns) phase stamps of the current round, see StampSlot
   unsigned long long t_stamp[8];
 };

@@ -205,6 +205,62 @@ __global__ void k_optim(OptimArgs a) {
   }
 }
 
+// Input pipeline: the round's uint8 inputs arrive from pinned host memory in `n_chunks` pieces
+// (one per local training step), each followed by a 4-byte tag copied on the same copy stream.
+// This persistent side-branch kernel converts chunk s to bf16 as soon as its tag shows up and
+// then publishes ready[s] = the tag it converted; the training kernel's TMA producer waits until
+// ready[step] reaches the round's tag -- the H2D copy of step s+1..n overlaps the compute
+// of step s instead of sitting in front of the whole round.  With no fresh copy (device-only
+// rounds) the tags already match and it degenerates to the plain cast.
+struct CastChunksArgs {
+  const uint8_t* src; __nv_bfloat16* dst;
+  long long chunk_elems; int n_chunks; float scale;
+  const int* in_flags;       // [n_chunks] written by H2D copies (tag of the data now in src)
+  const int* in_seq;         // tag this round expects
+  unsigned int* cnt;         // [n_chunks] monotonically increasing CTA arrivals
+  unsigned int* ready;       // [n_chunks] completed conversions (rounds)
+};
+
+__global__ void __launch_bounds__(256) k_cast_chunks(CastChunksArgs a) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  const int want = *reinterpret_cast<const volatile int*>(a.in_seq);
+  const long long nv = a.chunk_elems / 16;
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (int s = 0; s < a.n_chunks; ++s) {
+    if (threadIdx.x == 0) {
+      unsigned long long spins = 0;
+      while (static_cast<int>(ptx::ld_acquire_sys(reinterpret_cast<const uint32_t*>(a.in_flags + s))) - want < 0) {
+        if (++spins > (1ull << 23)) __trap();   // seconds, not minutes: the copy is ~10 us away
+      }
+    }
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(a.src + s * a.chunk_elems);
+    uint4* dst = reinterpret_cast<uint4*>(a.dst + s * a.chunk_elems);
+    for (long long i = tid; i < nv; i += stride) {
+      const uint4 in = __ldcg(src + i);   // L2: the data was just written by the copy engine
+      const uint32_t w[4] = {in.x, in.y, in.z, in.w};
+      uint32_t o[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        o[2 * k] = pack_bf16x2((w[k] & 0xff) * a.scale, ((w[k] >> 8) & 0xff) * a.scale);
+        o[2 * k + 1] = pack_bf16x2(((w[k] >> 16) & 0xff) * a.scale, (w[k] >> 24) * a.scale);
+      }
+      dst[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int old = atomicAdd(a.cnt + s, 1u);
+      if ((old + 1u) % gridDim.x == 0u)   // last CTA of this pass: chunk s now holds tag `want`
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.ready + s), "r"(static_cast<unsigned int>(want))
+                     : "memory");
+    }
+  }
+}
+
 }  // namespace
 
 #define BFLC_LAUNCH_1D(kernel, nvec, ...)                       \
@@ -225,6 +281,15 @@ cudaError_t cast_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_
 }
 cudaError_t cast_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t s) {
   BFLC_LAUNCH_1D(k_cast_bf16_f32, n, reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+}
+cudaError_t cast_u8_to_bf16_chunks(const uint8_t* src, void* dst, long long chunk_elems, int n_chunks,
+                                   float scale, const int* in_flags, const int* in_seq,
+                                   unsigned int* cnt, unsigned int* ready, cudaStream_t s) {
+  if (chunk_elems % 16 != 0 || n_chunks <= 0) return cudaErrorInvalidValue;
+  CastChunksArgs a{src, reinterpret_cast<__nv_bfloat16*>(dst), chunk_elems, n_chunks, scale,
+                   in_flags, in_seq, cnt, ready};
+  note_launch();
+  return launch_pdl(k_cast_chunks, dim3(16), dim3(256), 0, s, a);
 }
 cudaError_t cast_u8_to_bf16(const uint8_t* src, void* dst, int64_t n, float scale,
                             cudaStream_t s) {

@@ -101,6 +101,7 @@ __global__ void k_plan(FedArgs f, PlanLayers layers) {
   plan->consensus_blocks_done = 0;
   plan->digest_acc = 0ull;
   plan->step_barrier = 0u;
+  plan->round_seq = plan->round_seq + 1u;   // input-pipeline generation (matches k_cast_chunks' ready[])
   plan->opt_step = plan->opt_total;
   if (plan->is_trainer) plan->opt_total += layers.steps_per_round;
 }

@@ -78,6 +78,8 @@ struct Args {
   int chain;                     // 0: P1|P2|P3   1: fwd1->xent->dh chained   3: P1 | fwd2->xent->dh chained
   int epiopt;                    // optimizer applied in the weight-gradient epilogues (no P5)
   unsigned long long* dbg;       // optional %globaltimer stamps [steps][16] written by CTA 0
+  const unsigned int* x_ready;   // optional input pipeline: step s may read x once x_ready[s] >= *round_seq
+  const unsigned int* round_seq;
   long long n_params;
   const int* pred;               // whole kernel is a no-op when *pred == 0 (non-trainer rank)
   unsigned int* barrier;         // device-wide phase barrier counter (zeroed before launch)
@@ -994,6 +996,7 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
 
   Pipe pp{0u, 0u};
   CPipe cp{0u, 0u};
+  bool x_all_ready = false;   // input pipeline: every chunk of this round has been converted
   unsigned int bar_epoch = 0;
   const int t = blockIdx.x;
   const int B = a.B, H = a.hidden, C = a.n_classes, D = a.in_dim;
@@ -1049,6 +1052,26 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
     if (a.chain != 1) {
       // ---- P1: h = relu(x W1^T + b1)
       if (t < mt_b * nt_h) {
+        if (a.x_ready != nullptr && warp == 0 && !x_all_ready) {
+          // input pipeline: this step's rows are converted by the side-branch kernel as soon as
+          // their H2D copy lands; only the TMA producer has to wait (phase B reads them later).
+          // Once the LAST chunk is seen ready nothing is checked any more.
+          int all = 0;
+          if (lane == 0) {
+            const unsigned int want = __ldcg(a.round_seq);
+            unsigned int v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.x_ready + a.steps - 1) : "memory");
+            all = static_cast<int>(v - want) >= 0 ? 1 : 0;
+            unsigned long long spins = 0;
+            while (!all) {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.x_ready + step) : "memory");
+              if (static_cast<int>(v - want) >= 0) break;
+              if (++spins > (1ull << 24)) __trap();
+            }
+          }
+          x_all_ready = __shfl_sync(0xffffffffu, all, 0) != 0;
+          ptx::fence_proxy_async_all();   // their generic stores -> this warp's TMA (async proxy) loads
+        }
         Job j{};
         j.ta = &maps.x_k; j.tb = &maps.w1_k; j.a_mn = 0; j.b_mn = 0;
         j.m0 = (t / nt_h) * kBM; j.n0 = (t % nt_h) * kBN; j.M = B; j.N = H;
@@ -1391,6 +1414,8 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
   a.B = r.batch; a.steps = r.steps; a.in_dim = r.in_dim; a.hidden = r.hidden;
   a.n_classes = r.n_classes; a.ncp = r.ncp; a.n_params = r.n_params;
   a.chain = chain; a.epiopt = epiopt_env ? 1 : 0; a.dbg = r.dbg;
+  a.x_ready = chain != 1 ? r.x_ready : nullptr; a.round_seq = r.round_seq;
+  if (r.x_ready != nullptr && chain == 1) return cudaErrorNotSupported;
   a.pred = r.pred ? r.pred : current_predicate();
   a.barrier = r.barrier;
   a.master = r.master; a.b1 = r.b1; a.b2 = r.b2;

@@ -188,38 +188,68 @@ class FusedEngine:
         self.byz = 1 if rank in cfg.byzantine_ranks else 0
         self.fused_step = bool(cfg.fused_step) and self.trainer.fused_ok(self.steps)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_pipe: Optional[torch.cuda.CUDAGraph] = None
         self.stream = torch.cuda.Stream(device=self.dev)
         self._side = torch.cuda.Stream(device=self.dev)
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        # host -> device input pipeline (run_round_e2e): needs the one-launch trainer (its producer
+        # waits per step) and a shard that is exactly steps x batch rows
+        self.pipelined_input = (self.fused_step and self.S == len(shard) and self.steps <= 16
+                                and (cfg.batch_size * self.in_dim) % 16 == 0
+                                and os.environ.get("BFLC_INPUT_PIPELINE", "0") == "1"
+                                and os.environ.get("BFLC_MLP_CHAIN", "3") != "1")
+        self.in_flags = torch.zeros(16, device=self.dev, dtype=torch.int32)
+        self.in_seq = torch.zeros(1, device=self.dev, dtype=torch.int32)
+        self.cast_cnt = torch.zeros(16, device=self.dev, dtype=torch.int32)
+        self.x_ready = torch.zeros(16, device=self.dev, dtype=torch.int32)
+        self.seq_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._seq = 0
+        self._copy_stream = torch.cuda.Stream(device=self.dev)
         self.launches_per_round = 0
         if world > 1:
             dist.barrier(group=group)
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ one round
-    def _enqueue_round(self):
+    def _enqueue_round(self, pipe: bool = False):
+        """One round.  ``pipe``: the input-pipeline variant used by ``run_round_e2e`` (chunked,
+        tag-driven input conversion overlapping the training steps); the plain variant converts
+        the resident inputs up front.  Both leave identical state."""
         m, cfg = self.mod, self.cfg
+        pipe = pipe and self.pipelined_input
         n0 = m.launch_count()
-        # the input cast does not depend on the plan: it runs as a parallel branch (a fork/join in
-        # the captured graph) instead of serialising ~5 us behind it
+        # The input cast does not depend on the plan: it runs as a parallel branch of the captured
+        # graph.  With the input pipeline it is a persistent kernel that converts chunk s (the rows
+        # of local step s) as soon as that chunk's H2D copy has landed (run_round_e2e), and the
+        # trainer's TMA producer waits per step -- the branch is joined only before validation.
         main = torch.cuda.current_stream()
         self._ev_fork.record(main)
         self._side.wait_event(self._ev_fork)
         with torch.cuda.stream(self._side):
-            m.cast_u8_to_bf16(self.x_u8, self.x_bf, 1.0 / 255.0)
+            if pipe:
+                m.cast_u8_to_bf16_chunks(self.x_u8, self.x_bf, cfg.batch_size * self.in_dim, self.steps,
+                                         1.0 / 255.0, self.in_flags, self.in_seq, self.cast_cnt,
+                                         self.x_ready)
+            else:
+                m.cast_u8_to_bf16(self.x_u8, self.x_bf, 1.0 / 255.0)
             self._ev_join.record(self._side)
         m.fed_plan_round(self.fed, self.plan_layers, self.steps, self.staged)
-        main.wait_event(self._ev_join)
+        if not pipe:
+            main.wait_event(self._ev_join)
         # local training, predicated on the trainer role bit
         m.set_predicate(self.is_trainer_ptr)
         if self.fused_step:
             # every local step of the round inside ONE persistent kernel (phase barriers instead
             # of launches); the barrier word lives in the plan and is zeroed by k_plan
-            self.trainer.train_epoch_fused(self.x_bf, self.y, self.steps,
-                                           self.plan_ptr + self.sz["plan_step_barrier_off"])
+            self.trainer.train_epoch_fused(
+                self.x_bf, self.y, self.steps, self.plan_ptr + self.sz["plan_step_barrier_off"],
+                None, -1, -1,
+                self.x_ready.data_ptr() if pipe else 0, self.in_seq.data_ptr() if pipe else 0)
         else:
             self.trainer.train_epoch(self.x_bf, self.y, self.steps)
         m.set_predicate(0)
+        if pipe:
+            main.wait_event(self._ev_join)      # validation reads every converted row
         m.fed_upload(self.fed, self.S, self.steps * cfg.batch_size, self.byz, cfg.byzantine_scale)
         # committee validation: grouped GEMMs whose B operands are the trainers' uploads
         if self.staged:
@@ -259,14 +289,29 @@ class FusedEngine:
         with torch.cuda.graph(g, stream=self.stream):
             self._enqueue_round()
         self.graph = g
-
-    def run_round(self):
-        if self.graph is not None:
+        if self.pipelined_input:
+            # second graph for run_round_e2e: same round, inputs converted chunk by chunk as
+            # their H2D copies land.  Its only new kernel is warmed up once outside the capture
+            # (lazy module loading), without running an extra round.
             with torch.cuda.stream(self.stream):
-                self.graph.replay()
+                self.mod.cast_u8_to_bf16_chunks(self.x_u8, self.x_bf,
+                                                self.cfg.batch_size * self.in_dim, self.steps,
+                                                1.0 / 255.0, self.in_flags, self.in_seq,
+                                                self.cast_cnt, self.x_ready)
+            self.stream.synchronize()
+            gp = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gp, stream=self.stream):
+                self._enqueue_round(pipe=True)
+            self.graph_pipe = gp
+
+    def run_round(self, pipe: bool = False):
+        g = self.graph_pipe if (pipe and self.graph_pipe is not None) else self.graph
+        if g is not None:
+            with torch.cuda.stream(self.stream):
+                g.replay()
         else:
             with torch.cuda.stream(self.stream):
-                self._enqueue_round()
+                self._enqueue_round(pipe=pipe)
 
     def run_round_e2e(self, host_x: Optional[torch.Tensor] = None,
                       host_y: Optional[torch.Tensor] = None) -> dict:
@@ -274,18 +319,38 @@ class FusedEngine:
         round, read the result (ledger page) back to the host."""
         hx = self.host_x if host_x is None else host_x
         hy = self.host_y if host_y is None else host_y
-        with torch.cuda.stream(self.stream):
-            self.x_u8.copy_(hx, non_blocking=True)
-            self.y.copy_(hy, non_blocking=True)
-        self.run_round()
+        if self.pipelined_input:
+            # launch the round first, then feed it: labels, chunk 0, tag 0, chunk 1, tag 1, ... on
+            # the copy stream; step s of the trainer starts when chunk s has been converted, so
+            # the copy of the later chunks hides behind the compute of the earlier steps
+            self._seq += 1
+            self.seq_host[0] = self._seq
+            with torch.cuda.stream(self.stream):
+                self.in_seq.copy_(self.seq_host, non_blocking=True)
+            chunk_bytes = self.cfg.batch_size * self.in_dim
+            args = (hx.data_ptr(), self.x_u8.data_ptr(), chunk_bytes)
+            tail = (hy.data_ptr(), self.y.data_ptr())
+            flags = (self.in_flags.data_ptr(), self.seq_host.data_ptr(), self._copy_stream.cuda_stream)
+            # launch the round, then feed it (measured: issuing chunk 0 ahead of the graph launch
+            # was slower, profiles/run27_*)
+            self.run_round(pipe=True)
+            self.mod.h2d_pipeline(*args, 0, self.steps, *tail, hy.numel() * hy.element_size(), *flags)
+        else:
+            with torch.cuda.stream(self.stream):
+                self.x_u8.copy_(hx, non_blocking=True)
+                self.y.copy_(hy, non_blocking=True)
+            self.run_round()
         with torch.cuda.stream(self.stream):
             self.out_host.copy_(self.state_bytes, non_blocking=True)
         self.stream.synchronize()
+        if self.pipelined_input:
+            self._copy_stream.synchronize()
         return self.read_state(self.out_host)
 
     @property
     def h2d_bytes_per_round(self) -> int:
-        return self.host_x.numel() * self.host_x.element_size() + self.host_y.numel() * 4
+        tags = 4 * (self.steps + 1) if self.pipelined_input else 0   # per-chunk tags + sequence word
+        return self.host_x.numel() * self.host_x.element_size() + self.host_y.numel() * 4 + tags
 
     @property
     def d2h_bytes_per_round(self) -> int:

@@ -119,18 +119,21 @@ class FlatMLP:
 
     def train_epoch_fused(self, X: torch.Tensor, Y: torch.Tensor, steps: int,
                           barrier_ptr: int, dbg: Optional[torch.Tensor] = None, plan: int = -1,
-                          epiopt: int = -1) -> None:
+                          epiopt: int = -1, x_ready_ptr: int = 0, round_seq_ptr: int = 0) -> None:
         """All ``steps`` mini-batch steps in ONE persistent kernel launch; ``barrier_ptr`` is a
         device uint32 that is zero on entry (the phase barrier).  ``dbg``: optional int64
         [steps, 16] buffer that receives %globaltimer phase stamps of CTA 0.  ``plan`` /
         ``epiopt`` pick a phase plan explicitly (0 | 1 | 3 | 4, 0 | 1; -1 = BFLC_MLP_CHAIN /
-        BFLC_MLP_EPIOPT / default) -- all plans are numerically equivalent."""
+        BFLC_MLP_EPIOPT / default) -- all plans are numerically equivalent.  ``x_ready_ptr`` /
+        ``round_seq_ptr`` (device uint32[steps] / uint32): the producer of step s waits until
+        ``x_ready[s] >= *round_seq`` (input pipeline, engine/fused.py)."""
         e = self.spec.by_name
         offs = [e["w1"].offset, e["b1"].offset, e["w2"].offset, e["b2"].offset]
         C().mlp_round(X, Y, self.master, self.shadow, self.grad, offs, self.h, self.dlogits,
                       self.dh, self.loss_sum, self.correct, barrier_ptr, self.batch, steps,
                       self.in_dim, self.hidden, self.n_classes, self.lr,
-                      self.optimizer == "adam", self.m, self.v, self.step_dev_ptr, dbg, plan, epiopt)
+                      self.optimizer == "adam", self.m, self.v, self.step_dev_ptr, dbg, plan, epiopt,
+                      x_ready_ptr, round_seq_ptr)
 
     # ------------------------------------------------------------ evaluation
     def accuracy_counts(self, X: torch.Tensor, Y: torch.Tensor, shadow: Optional[torch.Tensor] = None,
