@@ -196,7 +196,7 @@ class FusedEngine:
         # waits per step) and a shard that is exactly steps x batch rows
         self.pipelined_input = (self.fused_step and self.S == len(shard) and self.steps <= 16
                                 and (cfg.batch_size * self.in_dim) % 16 == 0
-                                and os.environ.get("BFLC_INPUT_PIPELINE", "0") == "1"
+                                and os.environ.get("BFLC_INPUT_PIPELINE", "1") != "0"
                                 and os.environ.get("BFLC_MLP_CHAIN", "3") != "1")
         self.in_flags = torch.zeros(16, device=self.dev, dtype=torch.int32)
         self.in_seq = torch.zeros(1, device=self.dev, dtype=torch.int32)
