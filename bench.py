@@ -109,7 +109,8 @@ class ClockSampler:
 def main():
     args = parse()
     if args.impl == "reference":
-        print(json.dumps({"impl": "reference", "unavailable": REFERENCE_UNAVAILABLE}))
+        if int(os.environ.get("RANK", "0")) == 0:      # one line even when launched under torchrun
+            print(json.dumps({"impl": "reference", "unavailable": REFERENCE_UNAVAILABLE}))
         return 0
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and "RANK" not in os.environ:

@@ -28,3 +28,13 @@ def test_native_sources_are_all_built_by_build_py():
     import inspect
     src = inspect.getsource(B)
     assert "kernels" in src and "runtime" in src and "compute_100a" in src and "sm_100a" in src
+
+
+def test_reference_arm_prints_one_line_under_torchrun():
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29577",
+                          os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and json.loads(lines[0])["impl"] == "reference"
