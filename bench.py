@@ -239,6 +239,7 @@ def main():
                  "global_loss": st["global_loss"], "symm": eng.heap.describe(),
                  "launches_per_round": eng.launches_per_round, "fused_step": eng.fused_step,
                  "two_shot": bool(eng.two_shot),
+                 "e2e_input_pipeline": bool(getattr(eng, "pipelined_input", False)),
                  "staged_validation": eng.staged}
         # device-stamped phase breakdown (%globaltimer inside the fed kernels), median of 9 extra
         # rounds per rank, then the max over ranks of each phase
