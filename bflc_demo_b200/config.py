@@ -63,9 +63,10 @@ class FLConfig:
             if c.committee_size > c.clients or c.needed_updates > c.clients:
                 raise ValueError("solo: committee_size and needed_updates must be <= clients")
         else:
-            # implied (never checked) by the reference: COMM <= NEEDED <= CLIENT - COMM
-            if c.committee_size > c.needed_updates:
-                raise ValueError("committee_size > needed_updates: cannot re-elect a committee")
+            # implied (never checked) by the reference: NEEDED <= CLIENT - COMM.  The reference also
+            # has COMM <= NEEDED (H:11-15); a committee larger than the trainer set (BASELINE.json
+            # config #4: committee 5 of 8) is allowed here: re-election takes every scored
+            # trainer and refills from the outgoing committee (consensus_math.hpp step 5).
             if c.needed_updates > c.clients - c.committee_size:
                 raise ValueError("needed_updates > clients - committee_size: not enough trainers")
         if not (c.learning_rate > 0):
@@ -126,18 +127,22 @@ class FLConfig:
         return cls(**base).validate()
 
     @classmethod
-    def for_world(cls, n: int, **kw) -> "FLConfig":
+    def for_world(cls, n: int, committee_size: Optional[int] = None,
+                  needed_updates: Optional[int] = None, **kw) -> "FLConfig":
         """The benchmark family of BASELINE.json: n clients, committee 3 at n=8, 2 at n=4,
-        1 at n=2, solo at n=1; every trainer's update is needed; top-(trainers-1) aggregated
-        (at least 1)."""
+        1 at n=2, solo at n=1 (``committee_size=5`` gives config #4); by default every trainer's
+        update is needed (``needed_updates=k`` < trainers enables first-k-wins admission);
+        top-(needed-1) aggregated (at least the committee size when that many are admitted)."""
         if n == 1:
             base = dict(clients=1, committee_size=1, needed_updates=1, aggregate_count=1, solo=True)
         else:
-            comm = {2: 1, 4: 2, 8: 3}.get(n, max(1, n // 3))
+            comm = committee_size or {2: 1, 4: 2, 8: 3}.get(n, max(1, n // 3))
+            if not (1 <= comm < n):
+                raise ValueError(f"committee_size must be in [1, {n - 1}] for {n} clients")
             trainers = n - comm
-            base = dict(clients=n, committee_size=comm, needed_updates=trainers,
-                        aggregate_count=max(comm if comm <= trainers else 1, trainers - 1, 1))
-            base["aggregate_count"] = min(base["aggregate_count"], trainers)
+            needed = min(needed_updates or trainers, trainers)
+            base = dict(clients=n, committee_size=comm, needed_updates=needed,
+                        aggregate_count=min(max(comm if comm <= needed else 1, needed - 1, 1), needed))
         base.update(kw)
         return cls(**base).validate()
 

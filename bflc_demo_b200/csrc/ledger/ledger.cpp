@@ -186,8 +186,8 @@ std::string LedgerConfig::validate() const {
     if (needed_update_count > client_num) return "needed_update_count > client_num";
     return "";
   }
-  if (comm_count > needed_update_count)
-    return "comm_count > needed_update_count (cannot re-elect a full committee)";
+  // comm_count > needed_update_count is allowed (BASELINE config #4: committee 5 of 8): the
+  // election takes every scored trainer and refills from the outgoing committee.
   if (needed_update_count > client_num - comm_count)
     return "needed_update_count > client_num - comm_count (not enough trainers)";
   return "";

@@ -2,7 +2,13 @@
 Occupancy CSV, split 75/25 with a fixed seed, one-hot labels, contiguous IID shards via
 ``np.array_split``.  sklearn/pandas are not required: the split is a seeded permutation
 (documented deviation: not bit-identical to ``train_test_split(random_state=42)``, same
-proportions).  Falls back to a schema-compatible synthetic table when the CSV is absent."""
+proportions).
+
+The table ships in-tree as ``occupancy_uci.npz`` (the public UCI Occupancy Detection training
+set, artefact A3: 8143 rows x the five features the reference uses + the binary label, stored
+as float32/int8 arrays), so nothing depends on a checkout of the reference.  A CSV in the
+reference's format can still be supplied (``path`` / ``BFLC_OCCUPANCY_CSV``); a
+schema-compatible synthetic table is the last resort."""
 from __future__ import annotations
 
 import csv
@@ -15,23 +21,28 @@ import torch
 from .synthetic import Shard, occupancy_like
 
 FEATURES = ["Temperature", "Humidity", "Light", "CO2", "HumidityRatio"]  # M:35-36
-DEFAULT_CSV = "/root/reference/python-sdk/data/datatraining.txt"
+IN_TREE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "occupancy_uci.npz")
 
 
 def load_table(path: Optional[str] = None) -> Tuple[np.ndarray, np.ndarray, str]:
-    path = path or os.environ.get("BFLC_OCCUPANCY_CSV", DEFAULT_CSV)
+    path = path or os.environ.get("BFLC_OCCUPANCY_CSV", "")
     if path and os.path.exists(path):
         xs, ys = [], []
         with open(path, newline="") as f:
             rd = csv.reader(f)
-            header = next(rd)
-            # the file's header omits the leading row-id column
-            cols = header if len(header) == 7 else header
-            idx = {name.strip('"'): i + (1 if len(cols) == 7 else 0) for i, name in enumerate(cols)}
-            for row in rd:
+            header = [name.strip('"') for name in next(rd)]
+            first = next(rd)
+            # the UCI file's header omits the leading row-id column: data rows are one field longer
+            shift = len(first) - len(header)
+            idx = {name: i + shift for i, name in enumerate(header)}
+            for row in [first, *rd]:
                 xs.append([float(row[idx[k]]) for k in FEATURES])
                 ys.append(int(row[idx["Occupancy"]]))
         return np.asarray(xs, np.float32), np.asarray(ys, np.int64), path
+    if os.path.exists(IN_TREE):
+        with np.load(IN_TREE) as z:
+            assert list(z["features"]) == FEATURES
+            return z["x"].astype(np.float32), z["y"].astype(np.int64), "uci-occupancy (in-tree npz)"
     x, y = occupancy_like()
     return x, y, "synthetic"
 

@@ -9,26 +9,34 @@ from __future__ import annotations
 
 import argparse
 import multiprocessing as mp
+import os
 import random
+import tempfile
 import time
 
 from ..config import FLConfig
 from ..data.occupancy import split_data
 from .client import Client, Sponsor
 from .models import HostModel
+from . import identity
 from .rpc import LedgerServer, RemoteLedger
 
 
-def _server(cfg_json, model_size, q):
-    srv = LedgerServer(FLConfig.from_json(cfg_json), model_size)
+def _server(cfg_json, model_size, q, key_dir, authkey):
+    cfg = FLConfig.from_json(cfg_json)
+    # signed mode: only holders of an enrolled node_<i>.pem can act, and only as client i
+    srv = LedgerServer(cfg, model_size, accounts=identity.load_public_keys(key_dir, cfg.clients),
+                       authkey=authkey)
     q.put(srv.address)
     srv.serve_forever()
 
 
-def run_one_node(node_id, address, cfg_json, rounds, interval):
+def run_one_node(node_id, address, cfg_json, rounds, interval, key_dir, authkey):
     cfg = FLConfig.from_json(cfg_json)
     shards, _, _ = split_data(clients_num=cfg.clients)
-    led = RemoteLedger(address)
+    # set_from_account_signer(node_id), README.md:348-359
+    led = RemoteLedger(address, authkey=authkey, client_id=node_id,
+                       key=identity.load_account(key_dir, node_id))
     me = Client(node_id, led, shards[node_id], HostModel("softmax", 5, 2), lr=cfg.learning_rate,
                 batch_size=cfg.batch_size, max_epoch=rounds - 1)
     print(f"node_{node_id} initializing....", flush=True)
@@ -40,10 +48,10 @@ def run_one_node(node_id, address, cfg_json, rounds, interval):
     led.finish()
 
 
-def run_sponsor(address, cfg_json, rounds, interval):
+def run_sponsor(address, cfg_json, rounds, interval, authkey):
     cfg = FLConfig.from_json(cfg_json)
     _, test, _ = split_data(clients_num=cfg.clients)
-    led = RemoteLedger(address)
+    led = RemoteLedger(address, authkey=authkey)      # default account: read-only observer (M:317)
     sp = Sponsor(led, test, HostModel("softmax", 5, 2), log=lambda s: print(s, flush=True))
     while sp.test_epoch < rounds:
         sp.poll()
@@ -62,14 +70,20 @@ def main(argv=None):
     cj = cfg.to_json()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    srv = ctx.Process(target=_server, args=(cj, HostModel("softmax", 5, 2).size, q), daemon=True)
+    # per-run secrets: one ECDSA key per client (bin/get_batch_accounts.sh) + the socket authkey
+    key_dir = tempfile.mkdtemp(prefix="bflc_accounts_")
+    identity.generate_accounts(cfg.clients, key_dir)
+    authkey = os.urandom(32)
+    srv = ctx.Process(target=_server, args=(cj, HostModel("softmax", 5, 2).size, q, key_dir, authkey),
+                      daemon=True)
     srv.start()
     address = q.get(timeout=60)
-    procs = [ctx.Process(target=run_one_node, args=(i, address, cj, a.rounds, a.interval))
+    procs = [ctx.Process(target=run_one_node,
+                         args=(i, address, cj, a.rounds, a.interval, key_dir, authkey))
              for i in range(cfg.clients)]
     for p in procs:
         p.start()
-    sp = ctx.Process(target=run_sponsor, args=(address, cj, a.rounds, a.interval))
+    sp = ctx.Process(target=run_sponsor, args=(address, cj, a.rounds, a.interval, authkey))
     sp.start()
     sp.join()
     for p in procs:

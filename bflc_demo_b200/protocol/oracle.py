@@ -38,40 +38,6 @@ def true_median(xs: List[float]) -> float:
     return float(np.float32(0.5) * (s[n // 2 - 1] + s[n // 2]))
 
 
-def reference_getmid(xs: List[float]) -> float:
-    """Transliteration of the reference's buggy quickselect median (C:60-115), kept ONLY so a
-    test can demonstrate the input-order dependence that motivates the deviation."""
-    a = list(xs)
-
-    def partition(left, right):
-        pivot = a[left]
-        while left < right:
-            while left < right and a[right] >= pivot:
-                right -= 1
-            a[left] = a[right]
-            while left < right and a[left] <= pivot:
-                left += 1
-            a[right] = a[left]
-        a[left] = pivot
-        return left
-
-    left, right = 0, len(a) - 1
-    mid = (left + right) // 2
-    index = -1
-    while index != mid:
-        index = partition(left, right)
-        if index < mid:
-            left = index + 1
-        elif index > mid:
-            right = index - 1
-        else:
-            break
-    # the parity test uses the *mutated* `right` (C:97,103)
-    if right % 2 == 1:
-        return (a[index] + a[index + 1]) / 2 if index + 1 < len(a) else a[index]
-    return a[index]
-
-
 @dataclass
 class ConsensusResult:
     median: Dict[int, float]

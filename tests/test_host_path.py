@@ -117,31 +117,73 @@ def test_gloo_replicated_four_clients(tmp_path):
     assert res["acc"] > 0.3
 
 
-def test_rpc_ledger_service():
+def test_rpc_ledger_service(tmp_path):
+    """Signed mode: identity is pinned per connection by an ECDSA-signed nonce (C:147, R:348-359);
+    a client can neither name another id nor connect without the per-launch authkey."""
     import threading
+    from bflc_demo_b200.host import identity as I
     from bflc_demo_b200.host.rpc import LedgerServer, RemoteLedger
     cfg = FLConfig.for_world(4)
-    srv = LedgerServer(cfg, 12)
+    I.generate_accounts(4, str(tmp_path))
+    srv = LedgerServer(cfg, 12, accounts=I.load_public_keys(str(tmp_path), 4))
     t = threading.Thread(target=srv.serve_forever, daemon=True)
     t.start()
-    a, b = RemoteLedger(srv.address), RemoteLedger(srv.address)
+    key = [I.load_account(str(tmp_path), i) for i in range(4)]
+    c = [RemoteLedger(srv.address, authkey=srv.authkey, client_id=i, key=key[i]) for i in range(4)]
     for i in range(4):
-        assert (a if i % 2 else b).RegisterNode(i).name == "OK"
-    role, ep = a.QueryState(0)
+        assert c[i].RegisterNode(i).name == "OK"
+    role, ep = c[0].QueryState(0)
     assert ep == 0 and role == 2
-    w, ep = b.QueryGlobalModel()
+    w, ep = c[1].QueryGlobalModel()
     assert np.asarray(w).shape == (12,)
-    assert a.UploadLocalUpdate(2, np.ones(12, np.float32), 10, 0.5, 0).name == "OK"
-    assert a.UploadLocalUpdate(2, np.ones(12, np.float32), 10, 0.5, 0).name == "DUPLICATE"
-    assert b.UploadLocalUpdate(3, np.ones(12, np.float32), 30, 0.7, 0).name == "OK"
-    assert len(a.QueryAllUpdates()) == 2
-    assert a.UploadScores(0, 0, {2: 0.9, 3: 0.1}).name == "OK"
-    assert b.UploadScores(1, 0, {2: 0.8, 3: 0.2}).name == "AGGREGATED"
-    assert a.epoch() == 1 and a.verify_chain()
-    w, _ = a.QueryGlobalModel()
+    assert c[2].UploadLocalUpdate(2, np.ones(12, np.float32), 10, 0.5, 0).name == "OK"
+    assert c[2].UploadLocalUpdate(2, np.ones(12, np.float32), 10, 0.5, 0).name == "DUPLICATE"
+    # impersonation: client 2's connection cannot act for client 3 -- neither through the proxy ...
+    with pytest.raises(PermissionError):
+        c[2].UploadLocalUpdate(3, np.ones(12, np.float32), 30, 0.7, 0)
+    # ... nor by crafting the wire message: the server ignores any id the client sends and
+    # prepends the pinned one (the extra argument makes the call malformed, nothing is stored)
+    with pytest.raises(RuntimeError):
+        c[2]._call("UploadLocalUpdate", 3, np.ones(12, np.float32), 30, 0.7, 0)
+    assert len(c[0].QueryAllUpdates()) == 0          # barrier: 1 of 2 updates so far
+    assert c[3].UploadLocalUpdate(3, np.ones(12, np.float32), 30, 0.7, 0).name == "OK"
+    assert len(c[0].QueryAllUpdates()) == 2
+    # a trainer cannot post score rows (role guard keyed on the pinned id, C:274)
+    assert c[2].UploadScores(2, 0, {2: 1.0, 3: 0.0}).name != "OK"
+    assert c[0].UploadScores(0, 0, {2: 0.9, 3: 0.1}).name == "OK"
+    assert c[1].UploadScores(1, 0, {2: 0.8, 3: 0.2}).name == "AGGREGATED"
+    assert c[0].epoch() == 1 and c[0].verify_chain()
+    w, _ = c[0].QueryGlobalModel()
     np.testing.assert_allclose(np.asarray(w), -cfg.learning_rate * np.ones(12), rtol=1e-5)
     with pytest.raises(RuntimeError):
-        a._call("NoSuchMethod")
+        c[0]._call("NoSuchMethod")
+    # wrong key for a claimed account, unknown account, wrong authkey: all rejected at connect time
+    from cryptography.hazmat.primitives.asymmetric import ec
+    with pytest.raises(PermissionError):
+        RemoteLedger(srv.address, authkey=srv.authkey, client_id=0, key=ec.generate_private_key(ec.SECP256K1()))
+    with pytest.raises(PermissionError):
+        RemoteLedger(srv.address, authkey=srv.authkey, client_id=1, key=key[0])   # key 0 is pinned to id 0
+    with pytest.raises(Exception):
+        RemoteLedger(srv.address, authkey=b"not-the-key", client_id=0, key=key[0])
+    # observers (the sponsor's default account) may read but not transact
+    obs = RemoteLedger(srv.address, authkey=srv.authkey)
+    assert obs.epoch() == 1
+    with pytest.raises(RuntimeError):
+        obs._call("RegisterNode")
+    obs.shutdown()
+
+
+def test_rpc_open_mode_pins_claimed_id():
+    import threading
+    from bflc_demo_b200.host.rpc import LedgerServer, RemoteLedger
+    srv = LedgerServer(FLConfig.for_world(2), 4)
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    a = RemoteLedger(srv.address, authkey=srv.authkey, client_id=0)
+    assert a.RegisterNode(0).name == "OK"
+    with pytest.raises(PermissionError):
+        a.RegisterNode(1)
+    with pytest.raises(PermissionError):
+        RemoteLedger(srv.address, authkey=srv.authkey, client_id=7)       # not a client of this ledger
     a.shutdown()
 
 
