@@ -46,12 +46,16 @@ def parse():
     ap.add_argument("--hidden", type=int, default=256)
     ap.add_argument("--samples", type=int, default=4096, help="samples per client per round")
     ap.add_argument("--batch", type=int, default=512)
-    ap.add_argument("--optimizer", default="sgd")
+    ap.add_argument("--optimizer", default="adam", choices=["sgd", "adam"])
+    ap.add_argument("--dtype", default="fp8", choices=["fp8", "bf16"],
+                    help="fp8 = block-scaled fp8 (MXFP8) forward GEMMs, BASELINE.json config #2")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-fused-step", action="store_true", help="fused arm: one launch per GEMM instead of the persistent training kernel")
     ap.add_argument("--no-stage", action="store_true", help="fused arm: validation GEMMs TMA-load peers' HBM directly")
     ap.add_argument("--broadcast", action="store_true", help="nccl arm: literal average+broadcast")
+    ap.add_argument("--no-baseline", action="store_true",
+                    help="fused arm: skip timing our NCCL+cuBLAS baseline in the same process (vs_baseline = null)")
     ap.add_argument("--two-shot", default="auto", choices=["auto", "on", "off"],
                     help="fused arm: FedAvg as reduce-own-slice + multicast publish (auto: by model size)")
     return ap.parse_args()
@@ -136,25 +140,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cfg = FLConfig.for_world(n, model="mlp", dataset="femnist", hidden=args.hidden,
                              batch_size=args.batch, samples_per_client=args.samples,
-                             optimizer=args.optimizer, learning_rate=0.05, dtype="bf16",
+                             optimizer=args.optimizer,
+                             learning_rate=0.05 if args.optimizer == "sgd" else 1e-3, dtype=args.dtype,
                              cuda_graph=not args.no_graph, ring_slots=1024,
                              fused_step=not args.no_fused_step, stage_candidates=not args.no_stage,
                              two_shot={"auto": None, "on": True, "off": False}[args.two_shot])
     shard = femnist_like(n, args.samples, seed=7, only=rank)[0]
     # a small pool of distinct pinned input sets the e2e loop cycles through
     pool = [femnist_like(n, args.samples, seed=100 + i, only=rank)[0] for i in range(3)]
-
-    if args.impl == "fused":
-        from bflc_demo_b200.engine.fused import FusedEngine
-        eng = FusedEngine(cfg, shard, rank=rank, world=n, device=local_rank, group=group)
-    else:
-        from bflc_demo_b200.engine.nccl_baseline import NcclBaselineEngine
-        eng = NcclBaselineEngine(cfg, shard, rank=rank, world=n, device=local_rank, group=group,
-                                 broadcast=args.broadcast)
-    eng.capture()
-    pool_x = [p.x.reshape(len(p), -1).contiguous().pin_memory() for p in pool]
-    ydt = eng.host_y.dtype
-    pool_y = [p.y.to(ydt).contiguous().pin_memory() for p in pool]
 
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -164,70 +157,105 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, k):
-        """k iterations of fn(i), each device-timed on the engine stream; L2 flush + barrier
-        between iterations, outside the timed interval.  -> list of per-iteration ms."""
-        out = []
-        for i in range(k):
-            if flush is not None:
-                flush.fill_(i & 0xFF)
-            sync_all()
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(eng.stream):
-                e0.record()
-            fn(i)
-            with torch.cuda.stream(eng.stream):
-                e1.record()
-            e1.synchronize()
-            out.append(e0.elapsed_time(e1))
-        return out
-
-    def round_only(i):
-        eng.run_round()
-
-    def round_e2e(i):
-        eng.run_round_e2e(pool_x[i % len(pool_x)], pool_y[i % len(pool_y)])
-
-    W = max(args.warmup, 3)
-    for i in range(W):
-        round_e2e(i)
-    sync_all()
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    launches0 = _launch_count()
-    drain = (lambda: eng.drain_blocks()) if args.impl == "fused" else (lambda: [])
-    ledger_errs = list(drain())
-    t_dev = timed(round_only, args.steps)
-    ledger_errs += drain()
-    launches = _launch_count() - launches0
-    t_e2e = timed(round_e2e, args.steps)
-    ledger_errs += drain()
-    # back-to-back (no flush, no per-round barrier) for context
-    sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(eng.stream):
-        e0.record()
-    for i in range(args.steps):
-        eng.run_round()
-    with torch.cuda.stream(eng.stream):
-        e1.record()
-    e1.synchronize()
-    pipelined_ms = e0.elapsed_time(e1) / args.steps
-    sync_all()
-    clocks = sampler.stop() if sampler else None
-
     def reduce_max(vals):
         t = torch.tensor(vals, device="cuda", dtype=torch.float64)
         if n > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.tolist()
 
-    dev_ms = sum(reduce_max(t_dev))
-    e2e_ms = sum(reduce_max(t_e2e))
-    pipe_ms = reduce_max([pipelined_ms])[0]
+    def measure(eng, drain, want_clocks):
+        """W warm-up rounds, then K device-timed rounds (resident inputs), K e2e rounds (pinned
+        host inputs in, result out, inside the timed interval) and K back-to-back rounds.
+        Every timed round: CUDA events on the engine stream, L2 flush + barrier outside the
+        interval, max over ranks."""
+        pool_x = [p.x.reshape(len(p), -1).contiguous().pin_memory() for p in pool]
+        ydt = eng.host_y.dtype
+        pool_y = [p.y.to(ydt).contiguous().pin_memory() for p in pool]
+
+        def timed(fn, k):
+            out = []
+            for i in range(k):
+                if flush is not None:
+                    flush.fill_(i & 0xFF)
+                sync_all()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(eng.stream):
+                    e0.record()
+                fn(i)
+                with torch.cuda.stream(eng.stream):
+                    e1.record()
+                e1.synchronize()
+                out.append(e0.elapsed_time(e1))
+            return out
+
+        def round_only(i):
+            eng.run_round()
+
+        def round_e2e(i):
+            eng.run_round_e2e(pool_x[i % len(pool_x)], pool_y[i % len(pool_y)])
+
+        for i in range(W):
+            round_e2e(i)
+        sync_all()
+        sampler = ClockSampler(local_rank) if (rank == 0 and want_clocks) else None
+        if sampler:
+            sampler.start()
+        launches0 = _launch_count()
+        errs = list(drain())
+        t_dev = timed(round_only, args.steps)
+        errs += drain()
+        launches = _launch_count() - launches0
+        t_e2e = timed(round_e2e, args.steps)
+        errs += drain()
+        sync_all()   # back-to-back (no flush, no per-round barrier) for context
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(eng.stream):
+            e0.record()
+        for i in range(args.steps):
+            eng.run_round()
+        with torch.cuda.stream(eng.stream):
+            e1.record()
+        e1.synchronize()
+        pipelined_ms = e0.elapsed_time(e1) / args.steps
+        sync_all()
+        clocks = sampler.stop() if sampler else None
+        errs += drain()
+        return dict(dev_ms=sum(reduce_max(t_dev)), e2e_ms=sum(reduce_max(t_e2e)),
+                    pipe_ms=reduce_max([pipelined_ms])[0], launches=int(launches), clocks=clocks,
+                    ledger_errs=errs)
+
+    W = max(args.warmup, 3)
+    base = None
+    if args.impl == "fused" and not args.no_baseline:
+        # The comparator, timed by THIS invocation with the same N / K / W and the same timing
+        # code: OUR NCCL + cuBLAS build of the same round (the reference cannot be installed --
+        # see --impl reference).  bf16 cuBLAS GEMMs: the library path a PyTorch user has.
+        from bflc_demo_b200.engine.nccl_baseline import NcclBaselineEngine
+        beng = NcclBaselineEngine(cfg, shard, rank=rank, world=n, device=local_rank, group=group)
+        beng.capture()
+        bm = measure(beng, lambda: [], False)
+        base = {"impl": "nccl+cublas baseline (ours: torch ops, cuBLASLt epilogues, NCCL all_gather, "
+                        "device-side election, one CUDA graph per role; NOT a reference build)",
+                "dtype": "bf16", "graph_captured": bool(beng.graphs),
+                "value": args.steps / (bm["dev_ms"] / 1e3), "ms_per_step": bm["dev_ms"] / args.steps,
+                "e2e_value": args.steps / (bm["e2e_ms"] / 1e3), "e2e_ms_per_step": bm["e2e_ms"] / args.steps,
+                "pipelined_ms_per_step_no_flush": bm["pipe_ms"]}
+        del beng
+        torch.cuda.empty_cache()
+
+    if args.impl == "fused":
+        from bflc_demo_b200.engine.fused import FusedEngine
+        eng = FusedEngine(cfg, shard, rank=rank, world=n, device=local_rank, group=group)
+    else:
+        from bflc_demo_b200.engine.nccl_baseline import NcclBaselineEngine
+        eng = NcclBaselineEngine(cfg, shard, rank=rank, world=n, device=local_rank, group=group,
+                                 broadcast=args.broadcast)
+    eng.capture()
+    drain = (lambda: eng.drain_blocks()) if args.impl == "fused" else (lambda: [])
+    mres = measure(eng, drain, True)
+    dev_ms, e2e_ms, pipe_ms = mres["dev_ms"], mres["e2e_ms"], mres["pipe_ms"]
+    clocks, launches, ledger_errs = mres["clocks"], mres["launches"], mres["ledger_errs"]
 
     # consistency: the fused engine's host ledger re-executes every device election
     extra = {}
@@ -238,7 +266,7 @@ def main():
                  "chain_ok": eng.host_ledger.verify_chain(), "epoch": st["epoch"],
                  "global_loss": st["global_loss"], "symm": eng.heap.describe(),
                  "launches_per_round": eng.launches_per_round, "fused_step": eng.fused_step,
-                 "two_shot": bool(eng.two_shot),
+                 "fused_upload": bool(eng.fused_upload), "two_shot": bool(eng.two_shot),
                  "e2e_input_pipeline": bool(getattr(eng, "pipelined_input", False)),
                  "staged_validation": eng.staged}
         # device-stamped phase breakdown (%globaltimer inside the fed kernels), median of 9 extra
@@ -262,7 +290,8 @@ def main():
             extra["replicas_bit_identical"] = len(set(digs)) == 1
         gl = eng.launches_per_round * args.steps
     else:
-        extra = {"epoch": eng.epoch, "global_loss": eng.global_loss}
+        extra = {"epoch": eng.epoch, "global_loss": eng.global_loss,
+                 "graph_captured": bool(getattr(eng, "graphs", None))}
         gl = int(launches)
 
     if rank == 0:
@@ -274,8 +303,12 @@ def main():
             "unit": "rounds/s",
             "n_gpus": n, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic (class-conditional FEMNIST-like 28x28 uint8, 62 classes; random-init weights)",
+            "higher_is_better": True, "scaling": "weak",
+            # BASELINE.md publishes no throughput and the reference cannot be installed (see --impl
+            # reference); the comparator is OUR NCCL+cuBLAS build of the same round, timed by this
+            # same invocation (key "baseline"): vs_baseline = value / baseline.value
+            "vs_baseline": (K / (dev_ms / 1e3)) / base["value"] if base else None,
+            "dtype": "mxfp8" if args.dtype == "fp8" else "bf16", "data": "synthetic (class-conditional FEMNIST-like 28x28 uint8, 62 classes; random-init weights)",
             "impl": args.impl if args.impl == "fused" else "nccl-baseline (ours, not a reference build)",
             "config": {"model": f"mlp_784x{args.hidden}x62", "global_batch": trainers * eng.S,
                        "seq_len": None, "parallelism": f"fed-dp{n} (committee {cfg.committee_size}, "
@@ -291,6 +324,7 @@ def main():
                     "h2d_bytes_per_step": eng.h2d_bytes_per_round,
                     "d2h_bytes_per_step": eng.d2h_bytes_per_round},
             "gpu_launches": gl,
+            "baseline": dict(base, vs_baseline_e2e=(K / (e2e_ms / 1e3)) / base["e2e_value"]) if base else None,
             "extra": extra,
         }
         print(json.dumps(line))

@@ -125,6 +125,8 @@ void bind_extra(py::module_& m) {
     d["plan_step_barrier_off"] = offsetof(bflc::RoundPlan, step_barrier);
     d["plan_stamps_off"] = offsetof(bflc::RoundPlan, t_stamp);
     d["plan_round_seq_off"] = offsetof(bflc::RoundPlan, round_seq);
+    d["plan_opt_total_off"] = offsetof(bflc::RoundPlan, opt_total);
+    d["plan_cand_blob_off"] = offsetof(bflc::RoundPlan, cand_blob);
     d["state_epoch_off"] = offsetof(bflc::RoundState, epoch);
     d["state_role_off"] = offsetof(bflc::RoundState, role);
     d["state_global_loss_off"] = offsetof(bflc::RoundState, global_loss);
@@ -144,7 +146,8 @@ void bind_extra(py::module_& m) {
 
   // ------------------------------------------------------------ fed kernels
   m.def("fed_plan_round", [](const py::dict& fd, std::vector<std::pair<int64_t, bool>> layers,
-                             int steps_per_round, bool staged) {
+                             int steps_per_round, bool staged, int64_t blob_stage_ptr, int64_t blob_bytes,
+                             std::vector<int64_t> upq_off) {
     bflc::FedArgs f = make_fed(fd);
     bflc::PlanLayer pl[bflc::kMaxPlanLayers];
     TORCH_CHECK((int)layers.size() <= bflc::kMaxPlanLayers, "too many plan layers");
@@ -152,8 +155,20 @@ void bind_extra(py::module_& m) {
       pl[i].bias_off = layers[i].first;
       pl[i].use_bias = layers[i].second ? 1 : 0;
     }
-    check(bflc::fed_plan_round(f, pl, (int)layers.size(), steps_per_round, staged ? 1 : 0, cur_stream()),
+    bflc::PlanBlobs pb;
+    const bool blobs = blob_bytes > 0;
+    if (blobs) {
+      TORCH_CHECK(upq_off.size() == 2, "upq_off: heap offsets of the two parity upload blobs");
+      pb.stage = P<uint8_t>(blob_stage_ptr); pb.bytes = blob_bytes;
+      pb.upq_off[0] = upq_off[0]; pb.upq_off[1] = upq_off[1];
+    }
+    check(bflc::fed_plan_round(f, pl, (int)layers.size(), steps_per_round, staged ? 1 : 0, cur_stream(),
+                               blobs ? &pb : nullptr),
           "fed_plan_round");
+  }, py::arg("fed"), py::arg("layers"), py::arg("steps_per_round"), py::arg("staged"),
+     py::arg("blob_stage_ptr") = 0, py::arg("blob_bytes") = 0, py::arg("upq_off") = std::vector<int64_t>{});
+  m.def("fed_pull_blobs", [](const py::dict& fd, int64_t off0, int64_t off1, int64_t nbytes, at::Tensor stage) {
+    check(bflc::fed_pull_blobs(make_fed(fd), off0, off1, nbytes, stage.data_ptr(), cur_stream()), "fed_pull_blobs");
   });
   m.def("fed_upload", [](const py::dict& fd, int n_samples, int n_loss_terms, int byz_mode,
                          double byz_scale) {
@@ -192,13 +207,23 @@ void bind_extra(py::module_& m) {
 
   // ------------------------------------------------------------ optimizers
   // whole local-training pass of the 2-layer MLP in one persistent kernel
+  m.def("mx8_mlp_layout", [](int in_dim, int hidden) {
+    const bflc::Mx8MlpLayout l = bflc::mx8_mlp_layout(in_dim, hidden);
+    py::dict d;
+    d["w1q"] = l.w1q; d["w1sf"] = l.w1sf; d["w2q"] = l.w2q; d["w2sf"] = l.w2sf;
+    d["b1"] = l.b1; d["b2"] = l.b2; d["total"] = l.total; d["kb1"] = l.kb1; d["kb2"] = l.kb2;
+    return d;
+  });
   m.def("mlp_round", [](at::Tensor x, at::Tensor labels, at::Tensor master, at::Tensor shadow,
                         at::Tensor grad, std::vector<int64_t> offs, at::Tensor h, at::Tensor dlogits,
                         at::Tensor dh, at::Tensor loss_sum, at::Tensor correct, int64_t barrier_ptr,
                         int batch, int steps, int in_dim, int hidden, int n_classes, double lr,
                         bool adam, const OptT& mm, const OptT& vv, int64_t step_base_ptr,
                         const OptT& dbg, int plan, int epiopt, int64_t x_ready_ptr,
-                        int64_t round_seq_ptr) {
+                        int64_t round_seq_ptr, const OptT& x_q, const OptT& x_sf, const OptT& work_q,
+                        const OptT& h_q, const OptT& h_sf, const std::optional<py::dict>& fed,
+                        std::vector<int64_t> upq_off, int n_samples, int n_loss_terms, int byz_mode,
+                        double byz_scale) {
     TORCH_CHECK(offs.size() == 4, "offs = element offsets of w1, b1, w2, b2 in the flat buffer");
     bflc::MlpRoundArgs r;
     r.batch = batch; r.steps = steps; r.in_dim = in_dim; r.hidden = hidden; r.n_classes = n_classes;
@@ -223,15 +248,38 @@ void bind_extra(py::module_& m) {
     r.plan = plan; r.epiopt = epiopt;
     r.x_ready = P<const unsigned int>(x_ready_ptr); r.round_seq = P<const unsigned int>(round_seq_ptr);
     if (dbg.has_value()) {
-      TORCH_CHECK(dbg->numel() >= (int64_t)steps * 16 && dbg->element_size() == 8, "dbg: int64 [steps, 16]");
+      TORCH_CHECK(dbg->numel() >= (int64_t)steps * 32 && dbg->element_size() == 8, "dbg: int64 [steps, 32]");
       r.dbg = reinterpret_cast<unsigned long long*>(dbg->data_ptr());
     }
+    if (x_q.has_value()) {
+      TORCH_CHECK(x_sf.has_value() && work_q.has_value() && h_q.has_value() && h_sf.has_value(),
+                  "fp8 mode needs x_q, x_sf, work_q, h_q, h_sf");
+      r.fp8 = true;
+      r.x_q = x_q->data_ptr(); r.x_sf = x_sf->data_ptr<uint8_t>();
+      r.work_q = work_q->data_ptr<uint8_t>();
+      r.h_q = h_q->data_ptr<uint8_t>(); r.h_sf = h_sf->data_ptr<uint8_t>();
+    }
+    bflc::FedArgs f;
+    if (fed.has_value()) {
+      f = make_fed(*fed);
+      r.fed = &f;
+      if (upq_off.size() == 2) { r.upq_off[0] = upq_off[0]; r.upq_off[1] = upq_off[1]; }
+      r.n_samples = n_samples; r.n_loss_terms = n_loss_terms; r.byz_mode = byz_mode; r.byz_scale = (float)byz_scale;
+    }
     check(bflc::mlp_round_sm100(r, cur_stream()), "mlp_round_sm100");
-  });
+  }, py::arg("x"), py::arg("labels"), py::arg("master"), py::arg("shadow"), py::arg("grad"), py::arg("offs"),
+     py::arg("h"), py::arg("dlogits"), py::arg("dh"), py::arg("loss_sum"), py::arg("correct"),
+     py::arg("barrier_ptr"), py::arg("batch"), py::arg("steps"), py::arg("in_dim"), py::arg("hidden"),
+     py::arg("n_classes"), py::arg("lr"), py::arg("adam"), py::arg("m"), py::arg("v"),
+     py::arg("step_base_ptr"), py::arg("dbg"), py::arg("plan"), py::arg("epiopt"), py::arg("x_ready_ptr") = 0,
+     py::arg("round_seq_ptr") = 0, py::arg("x_q") = py::none(), py::arg("x_sf") = py::none(),
+     py::arg("work_q") = py::none(), py::arg("h_q") = py::none(), py::arg("h_sf") = py::none(),
+     py::arg("fed") = py::none(), py::arg("upq_off") = std::vector<int64_t>{}, py::arg("n_samples") = 0,
+     py::arg("n_loss_terms") = 0, py::arg("byz_mode") = 0, py::arg("byz_scale") = 0.0);
   // committee validation of every candidate in one launch (fwd1 -> relu -> fwd2 -> argmax)
   m.def("mlp_val", [](at::Tensor x, at::Tensor labels, at::Tensor correct, at::Tensor maps,
                       int64_t dyn1_ptr, int64_t dyn2_ptr, int n_val, int in_dim, int hidden,
-                      int n_classes, int max_cand) {
+                      int n_classes, int max_cand, const OptT& x_sf, int64_t cand_blob_ptr) {
     bflc::MlpValArgs r;
     r.n_val = n_val; r.in_dim = in_dim; r.hidden = hidden; r.n_classes = n_classes;
     r.max_cand = max_cand;
@@ -241,7 +289,21 @@ void bind_extra(py::module_& m) {
     r.dyn2 = P<const bflc::GemmDynamic>(dyn2_ptr);
     r.labels = labels.data_ptr<int32_t>();
     r.correct = reinterpret_cast<unsigned int*>(correct.data_ptr());
+    if (x_sf.has_value()) {
+      r.fp8 = true;
+      r.x_sf = x_sf->data_ptr<uint8_t>();
+      r.cand_blob = P<const uint8_t* const>(cand_blob_ptr);
+    }
     check(bflc::mlp_val_sm100(r, cur_stream()), "mlp_val_sm100");
+  }, py::arg("x"), py::arg("labels"), py::arg("correct"), py::arg("maps"), py::arg("dyn1_ptr"),
+     py::arg("dyn2_ptr"), py::arg("n_val"), py::arg("in_dim"), py::arg("hidden"), py::arg("n_classes"),
+     py::arg("max_cand"), py::arg("x_sf") = py::none(), py::arg("cand_blob_ptr") = 0);
+  m.def("quantize_mlp_blob", [](at::Tensor master, std::vector<int64_t> offs, int in_dim, int hidden,
+                                int n_classes, at::Tensor blob) {
+    TORCH_CHECK(offs.size() == 4, "offs = element offsets of w1, b1, w2, b2");
+    check(bflc::quantize_mlp_blob(master.data_ptr<float>(), offs[0], offs[1], offs[2], offs[3], in_dim, hidden,
+                                  n_classes, blob.data_ptr<uint8_t>(), cur_stream()),
+          "quantize_mlp_blob");
   });
   m.def("optim_step",
         [](bool adam, at::Tensor master, at::Tensor grad, const OptT& shadow, const OptT& mm,
@@ -273,16 +335,29 @@ void bind_extra(py::module_& m) {
     check(bflc::cast_bf16_to_f32(src.data_ptr(), dst.data_ptr<float>(), src.numel(), cur_stream()),
           "cast_bf16_to_f32");
   });
-  // input pipeline (see k_cast_chunks): flag-driven chunked conversion + the host side that
-  // enqueues labels, the n chunks and their 4-byte tags on a copy stream in one call
-  m.def("cast_u8_to_bf16_chunks", [](at::Tensor src, at::Tensor dst, int64_t chunk_elems, int n_chunks,
-                                     double scale, at::Tensor in_flags, at::Tensor in_seq, at::Tensor cnt,
-                                     at::Tensor ready) {
-    check(bflc::cast_u8_to_bf16_chunks(src.data_ptr<uint8_t>(), dst.data_ptr(), chunk_elems, n_chunks,
-                                       (float)scale, in_flags.data_ptr<int32_t>(), in_seq.data_ptr<int32_t>(),
-                                       reinterpret_cast<unsigned int*>(cnt.data_ptr()),
-                                       reinterpret_cast<unsigned int*>(ready.data_ptr()), cur_stream()),
-          "cast_u8_to_bf16_chunks");
+  // input preparation: u8 pixels -> bf16 (+ e4m3 and MXFP8 scale chunks); the chunked variant is
+  // the flag-driven side-branch kernel of the host->device input pipeline (see k_prep_chunks)
+  m.def("prep_inputs", [](at::Tensor src, const OptT& dst_bf16, const OptT& dst_q, const OptT& dst_sf,
+                          double scale) {
+    TORCH_CHECK(src.dim() == 2 && src.is_contiguous(), "src: contiguous u8 [R, K]");
+    check(bflc::prep_inputs_u8(src.data_ptr<uint8_t>(), dst_bf16.has_value() ? dst_bf16->data_ptr() : nullptr,
+                               dst_q.has_value() ? dst_q->data_ptr() : nullptr,
+                               dst_sf.has_value() ? dst_sf->data_ptr<uint8_t>() : nullptr, (int)src.size(0),
+                               (int)src.size(1), (float)scale, cur_stream()),
+          "prep_inputs_u8");
+  });
+  m.def("prep_inputs_chunks", [](at::Tensor src, const OptT& dst_bf16, const OptT& dst_q, const OptT& dst_sf,
+                                 int rows_per_chunk, int n_chunks, double scale, at::Tensor in_flags,
+                                 at::Tensor in_seq, at::Tensor cnt, at::Tensor ready, at::Tensor err) {
+    TORCH_CHECK(src.dim() == 2 && src.is_contiguous(), "src: contiguous u8 [R, K]");
+    check(bflc::prep_inputs_u8_chunks(src.data_ptr<uint8_t>(), dst_bf16.has_value() ? dst_bf16->data_ptr() : nullptr,
+                                      dst_q.has_value() ? dst_q->data_ptr() : nullptr,
+                                      dst_sf.has_value() ? dst_sf->data_ptr<uint8_t>() : nullptr, rows_per_chunk,
+                                      (int)src.size(1), n_chunks, (float)scale, in_flags.data_ptr<int32_t>(),
+                                      in_seq.data_ptr<int32_t>(), reinterpret_cast<unsigned int*>(cnt.data_ptr()),
+                                      reinterpret_cast<unsigned int*>(ready.data_ptr()),
+                                      reinterpret_cast<unsigned int*>(err.data_ptr()), cur_stream()),
+          "prep_inputs_u8_chunks");
   });
   m.def("h2d_pipeline", [](int64_t host_x, int64_t dev_x, int64_t chunk_bytes, int c_begin, int c_end,
                            int64_t host_y, int64_t dev_y, int64_t y_bytes, int64_t dev_flags,

@@ -109,6 +109,19 @@ cudaError_t gemm_make_b_map(const GemmProblem& p, CUtensorMap* out_host);
 cudaError_t gemm_make_operand_map(CUtensorMap* out, const GemmOperand& op, DType dt,
                                   int rows_extent, int K, int batch, int rows_tile);
 
+struct FedArgs;  // symmetric-heap addressing of the federated kernels, defined below
+
+// Byte layout of a "quantised model blob" of the 2-layer MLP: what a trainer publishes for the
+// committee in fp8 mode and what the persistent trainer keeps as its own MXFP8 compute copy.
+//   w1q  e4m3 [hidden][in_dim]      w1sf  scale chunks [hidden/128][kb1][512]
+//   w2q  e4m3 [64][hidden]          w2sf  scale chunks [1][kb2][512]      (classes padded to 64)
+//   b1   fp32 [hidden]              b2    fp32 [64]
+struct Mx8MlpLayout {
+  int w1q = 0, w1sf = 0, w2q = 0, w2sf = 0, b1 = 0, b2 = 0, total = 0;
+  int kb1 = 0, kb2 = 0;   // K-blocks (128 elements) along in_dim / hidden
+};
+Mx8MlpLayout mx8_mlp_layout(int in_dim, int hidden);
+
 // Whole local-training pass of the 2-layer MLP in ONE persistent kernel (mlp_round_sm100.cu).
 struct MlpRoundArgs {
   int batch = 0, steps = 0, in_dim = 0, hidden = 0, n_classes = 0, ncp = 0;
@@ -128,11 +141,27 @@ struct MlpRoundArgs {
   bool adam = false; float* adam_m = nullptr; float* adam_v = nullptr;
   float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
   const int* step_base = nullptr;
-  unsigned long long* dbg = nullptr;  // optional [steps][16] %globaltimer stamps (CTA 0)
+  unsigned long long* dbg = nullptr;  // optional [steps][32] %globaltimer stamps (CTA 0)
   // optional input pipeline: producer of step s waits until x_ready[s] >= *round_seq
   const unsigned int* x_ready = nullptr; const unsigned int* round_seq = nullptr;
-  int plan = -1;     // phase plan override: 0 | 1 | 3 | 4 (see mlp_round_sm100.cu); -1 = env / default
+  int plan = -1;     // phase plan override: 0 | 1 | 3 (see mlp_round_sm100.cu); -1 = env / default
   int epiopt = -1;   // optimizer in the weight-gradient epilogues: 0 | 1; -1 = env / default
+  // ---- block-scaled fp8 forward (fwd1 and fwd2 as tcgen05.mma.kind::mxf8f6f4.block_scale;
+  //      the weight/hidden gradients stay bf16).  Needs plan 3 + epiopt, hidden == 256.
+  bool fp8 = false;
+  const void* x_q = nullptr;          // e4m3 [steps*batch][in_dim]  (quantize_inputs_mx8)
+  const uint8_t* x_sf = nullptr;      // its scale chunks
+  uint8_t* work_q = nullptr;          // Mx8MlpLayout blob: this trainer's quantised weights,
+                                      // refreshed by the optimizer epilogue every step
+  uint8_t* h_q = nullptr; uint8_t* h_sf = nullptr;   // scratch: e4m3 [batch][hidden] + chunks
+  // ---- fused UploadLocalUpdate (needs epiopt): the optimizer epilogue of the LAST step also
+  //      writes the peer-readable upload buffers (fp32 master + bf16 shadow, or the fp8 blob at
+  //      heap offset upq_off[parity]); CTA 0 then pushes {n_samples, avg_cost} into every
+  //      replica and releases FLAG_TRAINED on every peer.  Replaces fed_upload.
+  const FedArgs* fed = nullptr;
+  long long upq_off[2] = {0, 0};
+  int n_samples = 0, n_loss_terms = 0, byz_mode = 0;
+  float byz_scale = 0.f;
 };
 cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream);
 
@@ -143,13 +172,33 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream);
 struct GemmDynamic;
 struct MlpValArgs {
   int n_val = 0, in_dim = 0, hidden = 0, n_classes = 0, max_cand = 0;
-  const void* x = nullptr; long long ldx = 0;     // bf16 [n_val][in_dim]
+  const void* x = nullptr; long long ldx = 0;     // bf16 [n_val][in_dim]  (fp8: e4m3, ldx = in_dim)
   const CUtensorMap* maps = nullptr;
   const GemmDynamic* dyn1 = nullptr; const GemmDynamic* dyn2 = nullptr;
   const int32_t* labels = nullptr; unsigned int* correct = nullptr;
   const int* pred = nullptr;
+  // fp8: candidates are Mx8MlpLayout blobs (their addresses come from the round plan's
+  // cand_blob[]); x_sf = scale chunks of x
+  bool fp8 = false;
+  const uint8_t* x_sf = nullptr;
+  const uint8_t* const* cand_blob = nullptr;   // device array [max_cand]
 };
 cudaError_t mlp_val_sm100(const MlpValArgs& r, cudaStream_t stream);
+
+// x u8 [R][K] (pixels) -> bf16 [R][K] (x * scale), e4m3 [R][K] and MXFP8 scale chunks in one pass
+// (K % 16 == 0).  Any of dst_bf16 / dst_q may be null.
+cudaError_t prep_inputs_u8(const uint8_t* src, void* dst_bf16, void* dst_q, uint8_t* dst_sf, int R,
+                           int K, float scale, cudaStream_t s);
+// chunked, tag-driven variant for the host->device input pipeline (see k_prep_chunks)
+cudaError_t prep_inputs_u8_chunks(const uint8_t* src, void* dst_bf16, void* dst_q, uint8_t* dst_sf,
+                                  int rows_per_chunk, int K, int n_chunks, float scale,
+                                  const int* in_flags, const int* in_seq, unsigned int* cnt,
+                                  unsigned int* ready, unsigned int* err, cudaStream_t s);
+// fp32 master weights of the MLP -> Mx8MlpLayout blob (start of a round: the consensus kernel
+// has just written the new global model into the training buffers)
+cudaError_t quantize_mlp_blob(const float* master, long long off_w1, long long off_b1,
+                              long long off_w2, long long off_b2, int in_dim, int hidden,
+                              int n_classes, uint8_t* blob, cudaStream_t s);
 
 // N-tile width the launcher would choose for a problem (z = batch * split_k)
 int gemm_pick_bn(int N, EpiKind kind, int M, int z);
@@ -161,10 +210,6 @@ void note_launch();
 cudaError_t cast_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t s);
 cudaError_t cast_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t s);
 cudaError_t cast_u8_to_bf16(const uint8_t* src, void* dst, int64_t n, float scale, cudaStream_t s);
-// Chunked, flag-driven variant for the host->device input pipeline (see k_cast_chunks).
-cudaError_t cast_u8_to_bf16_chunks(const uint8_t* src, void* dst, long long chunk_elems, int n_chunks,
-                                   float scale, const int* in_flags, const int* in_seq,
-                                   unsigned int* cnt, unsigned int* ready, cudaStream_t s);
 cudaError_t quantize_fp8(const void* src_bf16, uint8_t* dst, int64_t n, float inv_scale,
                          cudaStream_t s);
 cudaError_t amax_bf16(const void* src, int64_t n, float* amax_out, cudaStream_t s);
@@ -274,6 +319,7 @@ struct RoundPlan {
   int cand_rank[kMaxRanks];       // trainer rank of candidate slot z
   uint32_t parity;
   GemmDynamic dyn[kMaxPlanLayers];
+  const uint8_t* cand_blob[kMaxRanks];  // fp8 MLP: candidate z's Mx8MlpLayout blob (staging slot or peer)
   unsigned int correct[kMaxRanks];  // validation hits per candidate slot (accuracy epilogue)
   float loss_sum;                   // local-training loss accumulator (xent epilogue)
   unsigned int train_correct;
@@ -368,8 +414,14 @@ struct PlanLayer {
 
 // start of round: predicates, candidate list, per-layer GemmDynamic, accumulator reset,
 // and (safety) wait until every rank finished consuming the buffers about to be reused.
+// fp8 MLP: where candidate blobs live (local staging [slot][bytes], or directly each trainer's
+// upload blob at heap offset upq_off[parity])
+struct PlanBlobs {
+  uint8_t* stage = nullptr; long long bytes = 0; long long upq_off[2] = {0, 0};
+};
 cudaError_t fed_plan_round(const FedArgs& f, const PlanLayer* layers, int n_layers,
-                           int steps_per_round, int staged, cudaStream_t s);
+                           int steps_per_round, int staged, cudaStream_t s,
+                           const PlanBlobs* blobs = nullptr);
 // trainer ("UploadLocalUpdate", CommitteePrecompiled.cpp:215-258): copy the trained weights
 // into the peer-readable upload buffers, push {n_samples, avg_cost} to every replica and
 // release FLAG_TRAINED on every peer.  byz_mode 1 = sign-flipped, scaled delta (fault
@@ -389,6 +441,10 @@ cudaError_t fed_consensus_aggregate(const FedArgs& f, int n_val, int weight_by_s
 // trainer's flag is up.  stage_master may be null.
 cudaError_t fed_pull_candidates(const FedArgs& f, void* stage_shadow, float* stage_master,
                                 cudaStream_t s);
+// committee ranks, fp8 MLP: pull each candidate's blob (nbytes at heap offset off0/off1 by
+// epoch parity) into stage + slot * nbytes as soon as its trainer's flag is up
+cudaError_t fed_pull_blobs(const FedArgs& f, long long off0, long long off1, long long nbytes,
+                           void* stage, cudaStream_t s);
 // stream-blocking wait until every trainer of the current epoch released FLAG_TRAINED
 cudaError_t fed_wait_trained(const FedArgs& f, cudaStream_t s);
 

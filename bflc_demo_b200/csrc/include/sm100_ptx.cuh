@@ -242,12 +242,16 @@ __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t want) {
     __nanosleep(20);
   }
 }
-// 16-byte streaming peer load (peer lines are not kept in the local L2 anyway)
-__device__ __forceinline__ float4 ld_nc_f4(const float4* p) {
+// 16-byte streaming load of peer-mapped (or peer-written) memory.  The data is rewritten by
+// other GPUs every second round, so the non-coherent path (ld.global.nc) is not defined for
+// it: a relaxed system-scope load is always served from the point of coherence and never from a
+// stale L1 line; L1::no_allocate because every address is read exactly once.
+__device__ __forceinline__ float4 ld_peer_f4(const float4* p) {
   float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+  asm volatile("ld.relaxed.sys.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
+               : "l"(p)
+               : "memory");
   return v;
 }
 __device__ __forceinline__ float4 ld_f4_relaxed(const float4* p) {

@@ -10,6 +10,7 @@
 #include <cuda_fp8.h>
 
 #include "bflc_kernels.h"
+#include "epi_common.cuh"
 #include "launch.cuh"
 #include "sm100_ptx.cuh"
 
@@ -26,10 +27,7 @@ inline int grid_for(int64_t n_vec) {
   return static_cast<int>(g);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
+using epi::pack_bf16x2;
 
 __global__ void k_cast_f32_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                 int64_t n) {
@@ -205,51 +203,106 @@ __global__ void k_optim(OptimArgs a) {
   }
 }
 
-// Input pipeline: the round's uint8 inputs arrive from pinned host memory in `n_chunks` pieces
-// (one per local training step), each followed by a 4-byte tag copied on the same copy stream.
-// This persistent side-branch kernel converts chunk s to bf16 as soon as its tag shows up and
-// then publishes ready[s] = the tag it converted; the training kernel's TMA producer waits until
-// ready[step] reaches the round's tag -- the H2D copy of step s+1..n overlaps the compute
-// of step s instead of sitting in front of the whole round.  With no fresh copy (device-only
-// rounds) the tags already match and it degenerates to the plain cast.
-struct CastChunksArgs {
-  const uint8_t* src; __nv_bfloat16* dst;
-  long long chunk_elems; int n_chunks; float scale;
+// ------------------------------------------------------------------ input preparation
+// One thread per (row, 32-column group) of a u8 [R][K] pixel matrix: the group becomes 32 bf16
+// values (x * scale: the B operand of dW1 = dh^T x) and, for the block-scaled fp8 forward GEMMs,
+// 32 e4m3 bytes + one UE8M0 scale byte written into the chunk layout the tensor core consumes
+// (epi_common.cuh).  K % 16 == 0, so a group is one or two 16-byte loads.
+__device__ __forceinline__ void prep_group(const uint8_t* __restrict__ src, __nv_bfloat16* dbf, uint8_t* dq,
+                                           uint8_t* dsf, int row, int g, int K, int n_kb, float scale) {
+  const int k0 = g * 32;
+  const int n = K - k0 < 32 ? K - k0 : 32;      // 32 or 16
+  const long long off = static_cast<long long>(row) * K + k0;
+  uint32_t wd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  {
+    const uint4 a = __ldcg(reinterpret_cast<const uint4*>(src + off));   // L2: may have just been DMA'd
+    wd[0] = a.x; wd[1] = a.y; wd[2] = a.z; wd[3] = a.w;
+    if (n > 16) {
+      const uint4 b = __ldcg(reinterpret_cast<const uint4*>(src + off + 16));
+      wd[4] = b.x; wd[5] = b.y; wd[6] = b.z; wd[7] = b.w;
+    }
+  }
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = static_cast<float>((wd[i >> 2] >> (8 * (i & 3))) & 0xffu) * scale;
+  if (dbf != nullptr) {
+    uint4* o = reinterpret_cast<uint4*>(dbf + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i * 8 >= n) break;
+      o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                        pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+    }
+  }
+  if (dq != nullptr) {
+    uint32_t w[8];
+    const int e = epi::mx8_quant32(v, w);
+    uint4* o = reinterpret_cast<uint4*>(dq + off);
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    if (n > 16) o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    dsf[epi::mx8_sf_index(row, g, n_kb)] = static_cast<uint8_t>(e);
+  }
+}
+
+struct PrepArgs {
+  const uint8_t* src; __nv_bfloat16* dbf; uint8_t* dq; uint8_t* dsf;
+  int R, K; float scale;
+  // chunked (input pipeline) variant
+  int rows_per_chunk, n_chunks;
   const int* in_flags;       // [n_chunks] written by H2D copies (tag of the data now in src)
   const int* in_seq;         // tag this round expects
   unsigned int* cnt;         // [n_chunks] monotonically increasing CTA arrivals
   unsigned int* ready;       // [n_chunks] completed conversions (rounds)
+  unsigned int* err;         // set to 1 when a chunk's tag never arrived (host checks it)
 };
 
-__global__ void __launch_bounds__(256) k_cast_chunks(CastChunksArgs a) {
+__global__ void __launch_bounds__(256) k_prep_inputs(PrepArgs a, const int* pred) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  if (pred != nullptr && *pred == 0) return;
+  const int G = (a.K + 31) / 32, n_kb = (a.K + 127) / 128;
+  const long long total = static_cast<long long>(a.R) * G;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += stride)
+    prep_group(a.src, a.dbf, a.dq, a.dsf, static_cast<int>(i / G), static_cast<int>(i % G), a.K, n_kb, a.scale);
+}
+
+// Input pipeline: the round's uint8 inputs arrive from pinned host memory in `n_chunks` pieces
+// (one per local training step), each followed by a 4-byte tag copied on the same copy stream.
+// This persistent side-branch kernel converts chunk s as soon as its tag shows up and then
+// publishes ready[s] = the tag it converted; the training kernel's TMA producer waits until
+// ready[step] reaches the round's tag -- the H2D copy of step s+1..n overlaps the compute
+// of step s instead of sitting in front of the whole round.  With no fresh copy (device-only
+// rounds) the tags already match and it degenerates to the plain conversion.
+// A tag that never arrives (host stalled for seconds between launching the graph and feeding it)
+// does not trap -- that would destroy the context and with it the symmetric heap every peer is
+// spinning on: the kernel backs off with nanosleep for ~10 s, then sets *err, converts whatever
+// is in the buffer and moves on; the host raises after the round.
+__global__ void __launch_bounds__(256) k_prep_chunks(PrepArgs a) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   const int want = *reinterpret_cast<const volatile int*>(a.in_seq);
-  const long long nv = a.chunk_elems / 16;
+  const int G = (a.K + 31) / 32, n_kb = (a.K + 127) / 128;
+  const long long per = static_cast<long long>(a.rows_per_chunk) * G;
   const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (int s = 0; s < a.n_chunks; ++s) {
     if (threadIdx.x == 0) {
       unsigned long long spins = 0;
+      unsigned int ns = 20;
       while (static_cast<int>(ptx::ld_acquire_sys(reinterpret_cast<const uint32_t*>(a.in_flags + s))) - want < 0) {
-        if (++spins > (1ull << 23)) __trap();   // seconds, not minutes: the copy is ~10 us away
+        if (++spins > (1ull << 14)) { __nanosleep(ns); if (ns < 2000) ns *= 2; }
+        if (spins > (1ull << 14) + 5000000ull) {   // ~10 s of 2 us naps
+          if (a.err != nullptr) atomicExch(a.err, 1u);
+          break;
+        }
       }
     }
     __syncthreads();
-    const uint4* src = reinterpret_cast<const uint4*>(a.src + s * a.chunk_elems);
-    uint4* dst = reinterpret_cast<uint4*>(a.dst + s * a.chunk_elems);
-    for (long long i = tid; i < nv; i += stride) {
-      const uint4 in = __ldcg(src + i);   // L2: the data was just written by the copy engine
-      const uint32_t w[4] = {in.x, in.y, in.z, in.w};
-      uint32_t o[8];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        o[2 * k] = pack_bf16x2((w[k] & 0xff) * a.scale, ((w[k] >> 8) & 0xff) * a.scale);
-        o[2 * k + 1] = pack_bf16x2(((w[k] >> 16) & 0xff) * a.scale, (w[k] >> 24) * a.scale);
-      }
-      dst[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
-      dst[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
-    }
+    const int row0 = s * a.rows_per_chunk;
+    for (long long i = tid; i < per; i += stride)
+      prep_group(a.src, a.dbf, a.dq, a.dsf, row0 + static_cast<int>(i / G), static_cast<int>(i % G), a.K, n_kb,
+                 a.scale);
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
@@ -257,6 +310,51 @@ __global__ void __launch_bounds__(256) k_cast_chunks(CastChunksArgs a) {
       if ((old + 1u) % gridDim.x == 0u)   // last CTA of this pass: chunk s now holds tag `want`
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.ready + s), "r"(static_cast<unsigned int>(want))
                      : "memory");
+    }
+  }
+}
+
+// fp32 master weights of the 2-layer MLP -> Mx8MlpLayout blob (e4m3 + scale chunks + fp32 biases).
+// One thread per (row, K-group) of the PADDED problems; padding rows / groups get scale 1.0
+// (0x7F, never NaN) and zero data, so TMA zero-fill and the padded classes contribute nothing.
+struct BlobArgs {
+  const float* master; long long off_w1, off_b1, off_w2, off_b2;
+  int in_dim, hidden, n_classes; uint8_t* blob; Mx8MlpLayout l;
+};
+__device__ __forceinline__ void blob_group(const float* w, int ld, int rows, int K, int row, int g, int n_kb,
+                                           uint8_t* q, uint8_t* sf, int q_rows) {
+  uint8_t* sfp = sf + epi::mx8_sf_index(row, g, n_kb);
+  const int k0 = g * 32;
+  if (k0 >= K || row >= q_rows) { *sfp = 127; return; }
+  const int n = K - k0 < 32 ? K - k0 : 32;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = (row < rows && i < n) ? w[static_cast<long long>(row) * ld + k0 + i] : 0.f;
+  uint32_t o[8];
+  *sfp = static_cast<uint8_t>(epi::mx8_quant32(v, o));
+  uint8_t* qp = q + static_cast<long long>(row) * ld + k0;
+  for (int i = 0; i < n / 4; ++i) reinterpret_cast<uint32_t*>(qp)[i] = o[i];
+}
+__global__ void __launch_bounds__(256) k_quantize_mlp_blob(BlobArgs a) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  const int g1 = a.l.kb1 * 4, g2 = a.l.kb2 * 4;
+  const int r1 = (a.hidden + 127) / 128 * 128;
+  const long long n1 = static_cast<long long>(r1) * g1, n2 = 128LL * g2, n3 = a.hidden + 64;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n1 + n2 + n3; i += stride) {
+    if (i < n1) {
+      blob_group(a.master + a.off_w1, a.in_dim, a.hidden, a.in_dim, static_cast<int>(i / g1), static_cast<int>(i % g1),
+                 a.l.kb1, a.blob + a.l.w1q, a.blob + a.l.w1sf, a.hidden);
+    } else if (i < n1 + n2) {
+      const long long u = i - n1;
+      blob_group(a.master + a.off_w2, a.hidden, a.n_classes, a.hidden, static_cast<int>(u / g2), static_cast<int>(u % g2),
+                 a.l.kb2, a.blob + a.l.w2q, a.blob + a.l.w2sf, 64);
+    } else {
+      const int u = static_cast<int>(i - n1 - n2);
+      float* b = reinterpret_cast<float*>(a.blob + (u < a.hidden ? a.l.b1 + 4 * u : a.l.b2 + 4 * (u - a.hidden)));
+      *b = u < a.hidden ? a.master[a.off_b1 + u]
+                        : (u - a.hidden < a.n_classes ? a.master[a.off_b2 + u - a.hidden] : 0.f);
     }
   }
 }
@@ -282,14 +380,40 @@ cudaError_t cast_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_
 cudaError_t cast_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t s) {
   BFLC_LAUNCH_1D(k_cast_bf16_f32, n, reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
 }
-cudaError_t cast_u8_to_bf16_chunks(const uint8_t* src, void* dst, long long chunk_elems, int n_chunks,
-                                   float scale, const int* in_flags, const int* in_seq,
-                                   unsigned int* cnt, unsigned int* ready, cudaStream_t s) {
-  if (chunk_elems % 16 != 0 || n_chunks <= 0) return cudaErrorInvalidValue;
-  CastChunksArgs a{src, reinterpret_cast<__nv_bfloat16*>(dst), chunk_elems, n_chunks, scale,
-                   in_flags, in_seq, cnt, ready};
+cudaError_t prep_inputs_u8(const uint8_t* src, void* dst_bf16, void* dst_q, uint8_t* dst_sf, int R,
+                           int K, float scale, cudaStream_t s) {
+  if (K % 16 != 0 || R <= 0 || (dst_q != nullptr && dst_sf == nullptr)) return cudaErrorInvalidValue;
+  PrepArgs a{};
+  a.src = src; a.dbf = reinterpret_cast<__nv_bfloat16*>(dst_bf16); a.dq = static_cast<uint8_t*>(dst_q);
+  a.dsf = dst_sf; a.R = R; a.K = K; a.scale = scale;
+  const long long total = static_cast<long long>(R) * ((K + 31) / 32);
   note_launch();
-  return launch_pdl(k_cast_chunks, dim3(16), dim3(256), 0, s, a);
+  return launch_pdl(k_prep_inputs, dim3(grid_for(total)), dim3(kBlock), 0, s, a, current_predicate());
+}
+cudaError_t prep_inputs_u8_chunks(const uint8_t* src, void* dst_bf16, void* dst_q, uint8_t* dst_sf,
+                                  int rows_per_chunk, int K, int n_chunks, float scale,
+                                  const int* in_flags, const int* in_seq, unsigned int* cnt,
+                                  unsigned int* ready, unsigned int* err, cudaStream_t s) {
+  if (K % 16 != 0 || n_chunks <= 0 || rows_per_chunk <= 0 || (dst_q != nullptr && dst_sf == nullptr))
+    return cudaErrorInvalidValue;
+  PrepArgs a{};
+  a.src = src; a.dbf = reinterpret_cast<__nv_bfloat16*>(dst_bf16); a.dq = static_cast<uint8_t*>(dst_q);
+  a.dsf = dst_sf; a.R = rows_per_chunk * n_chunks; a.K = K; a.scale = scale;
+  a.rows_per_chunk = rows_per_chunk; a.n_chunks = n_chunks;
+  a.in_flags = in_flags; a.in_seq = in_seq; a.cnt = cnt; a.ready = ready; a.err = err;
+  note_launch();
+  return launch_pdl(k_prep_chunks, dim3(16), dim3(256), 0, s, a);
+}
+cudaError_t quantize_mlp_blob(const float* master, long long off_w1, long long off_b1,
+                              long long off_w2, long long off_b2, int in_dim, int hidden,
+                              int n_classes, uint8_t* blob, cudaStream_t s) {
+  if (in_dim % 4 != 0 || hidden % 4 != 0 || n_classes > 64) return cudaErrorInvalidValue;
+  BlobArgs a{master, off_w1, off_b1, off_w2, off_b2, in_dim, hidden, n_classes, blob,
+             mx8_mlp_layout(in_dim, hidden)};
+  const long long total = static_cast<long long>((hidden + 127) / 128 * 128) * a.l.kb1 * 4 + 128LL * a.l.kb2 * 4 +
+                          hidden + 64;
+  note_launch();
+  return launch_pdl(k_quantize_mlp_blob, dim3(grid_for(total)), dim3(kBlock), 0, s, a);
 }
 cudaError_t cast_u8_to_bf16(const uint8_t* src, void* dst, int64_t n, float scale,
                             cudaStream_t s) {

@@ -43,6 +43,10 @@ struct PlanLayers {
   int n;
   int steps_per_round;
   int staged;  // 1: validation B operands are the local staging slots filled by k_pull
+  // fp8 MLP: candidates are Mx8MlpLayout blobs -- local staging slot z, or (direct) the trainer's
+  // upload blob at heap offset upq_off[parity]
+  int use_blob;
+  uint8_t* stage_blob; long long blob_bytes; long long upq_off[2];
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -94,7 +98,13 @@ __global__ void k_plan(FedArgs f, PlanLayers layers) {
       d.wait_flag[z] = layers.staged ? nullptr : flags + FLAG_TRAINED + t;
     }
   }
-  for (int z = 0; z < kMaxRanks; ++z) plan->correct[z] = 0;
+  for (int z = 0; z < kMaxRanks; ++z) {
+    plan->correct[z] = 0;
+    const int t = z < n_cand ? plan->cand_rank[z] : f.rank;
+    plan->cand_blob[z] = !layers.use_blob ? nullptr
+                         : layers.staged  ? layers.stage_blob + z * layers.blob_bytes
+                                          : reinterpret_cast<const uint8_t*>(f.peers.base[t]) + layers.upq_off[par];
+  }
   plan->loss_sum = 0.f;
   plan->train_correct = 0;
   plan->upload_blocks_done = 0;
@@ -221,31 +231,37 @@ k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc)
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x == 0) stamp(plan, STAMP_CONS_SCORED);
 
-  // (c) consensus math, redundantly per block (tiny), identical on every rank
+  // (c) consensus math, redundantly per block (tiny), identical on every rank.  The 64 score
+  //     words and 16 meta words are fetched by 80 threads at once (a single thread paid one L2
+  //     round trip per word: ~12 us of the old 25 us kernel), then thread 0 runs the decision
+  //     procedure out of shared memory.
+  {
+    ConsensusIn<kMaxRanks>& in = sh.in;
+    const float* rows = at<float>(me, f.lay.scores_off) + par * kMaxRanks * kMaxRanks;
+    const UploadMeta* meta = at<UploadMeta>(me, f.lay.meta_off) + par * kMaxRanks;
+    const int i = threadIdx.x;
+    if (i < kMaxRanks * kMaxRanks) {
+      const int r = i / kMaxRanks, t = i % kMaxRanks;
+      const bool ok = r < n && t < n && (st->role[r] & ROLE_COMM) && (st->role[t] & ROLE_TRAINER);
+      in.scored[r][t] = ok ? 1 : 0;
+      in.score[r][t] =
+          ok ? __uint_as_float(ptx::ld_relaxed_sys(reinterpret_cast<const uint32_t*>(rows + r * kMaxRanks + t))) : 0.f;
+    } else if (i < kMaxRanks * kMaxRanks + kMaxRanks) {
+      const int r = i - kMaxRanks * kMaxRanks;
+      in.role[r] = r < n ? st->role[r] : 0u;
+      in.admitted[r] = (r < n && (st->role[r] & ROLE_TRAINER)) ? 1 : 0;
+      in.n_samples[r] = r < n ? ptx::ld_relaxed_sys(&meta[r].n_samples) : 0u;
+      in.avg_cost[r] =
+          r < n ? __uint_as_float(ptx::ld_relaxed_sys(reinterpret_cast<const uint32_t*>(&meta[r].avg_cost))) : 0.f;
+    }
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     ConsensusIn<kMaxRanks>& in = sh.in;
     in.n_ranks = n;
     in.n_comm = static_cast<int>(st->n_comm);
     in.n_aggregate = static_cast<int>(st->n_aggregate);
     in.weight_by_score = weight_by_score;
-    const float* rows = at<float>(me, f.lay.scores_off) + par * kMaxRanks * kMaxRanks;
-    const UploadMeta* meta = at<UploadMeta>(me, f.lay.meta_off) + par * kMaxRanks;
-    for (int r = 0; r < kMaxRanks; ++r) {
-      in.role[r] = r < n ? st->role[r] : 0u;
-      in.admitted[r] = (r < n && (st->role[r] & ROLE_TRAINER)) ? 1 : 0;
-      in.n_samples[r] = r < n ? ptx::ld_relaxed_sys(&meta[r].n_samples) : 0u;
-      in.avg_cost[r] =
-          r < n ? __uint_as_float(ptx::ld_relaxed_sys(reinterpret_cast<const uint32_t*>(&meta[r].avg_cost)))
-                : 0.f;
-      for (int t = 0; t < kMaxRanks; ++t) {
-        const bool ok = r < n && t < n && (st->role[r] & ROLE_COMM) && (st->role[t] & ROLE_TRAINER);
-        in.scored[r][t] = ok ? 1 : 0;
-        in.score[r][t] =
-            ok ? __uint_as_float(ptx::ld_relaxed_sys(
-                     reinterpret_cast<const uint32_t*>(rows + r * kMaxRanks + t)))
-               : 0.f;
-      }
-    }
     run_consensus<kMaxRanks>(in, sh.out);
     int k = 0;
     for (int r = 0; r < n; ++r)  // ascending rank = the fixed reduction order
@@ -293,7 +309,7 @@ k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc)
       float4 v[kMaxRanks];
 #pragma unroll
       for (int k = 0; k < kMaxRanks; ++k)
-        if (k < n_sel) v[k] = ptx::ld_nc_f4(src[k] + i);  // all peer loads in flight first
+        if (k < n_sel) v[k] = ptx::ld_peer_f4(src[k] + i);  // all peer loads in flight first
 #pragma unroll
       for (int k = 0; k < kMaxRanks; ++k)
         if (k < n_sel) {
@@ -430,10 +446,10 @@ __global__ void k_p2p_read(const float4* __restrict__ src, float4* __restrict__ 
   const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = tid; i + 3 * stride < n; i += 4 * stride) {
-    const float4 a = ptx::ld_nc_f4(src + i);
-    const float4 b = ptx::ld_nc_f4(src + i + stride);
-    const float4 c = ptx::ld_nc_f4(src + i + 2 * stride);
-    const float4 d = ptx::ld_nc_f4(src + i + 3 * stride);
+    const float4 a = ptx::ld_peer_f4(src + i);
+    const float4 b = ptx::ld_peer_f4(src + i + stride);
+    const float4 c = ptx::ld_peer_f4(src + i + 2 * stride);
+    const float4 d = ptx::ld_peer_f4(src + i + 3 * stride);
     dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
   }
 }
@@ -484,7 +500,7 @@ k_pull(FedArgs f, uint4* stage_shadow, float4* stage_master) {
     const uint4* src = at<const uint4>(f.peers.base[t], f.lay.upload_shadow_off[par]);
     uint4* dst = stage_shadow + static_cast<long long>(z) * nv;
     for (long long i = tid; i < nv; i += stride) {
-      const float4 v = ptx::ld_nc_f4(reinterpret_cast<const float4*>(src) + i);
+      const float4 v = ptx::ld_peer_f4(reinterpret_cast<const float4*>(src) + i);
       dst[i] = *reinterpret_cast<const uint4*>(&v);
     }
   }
@@ -492,8 +508,42 @@ k_pull(FedArgs f, uint4* stage_shadow, float4* stage_master) {
     const long long nv = f.lay.n_params / 4;
     const float4* src = at<const float4>(f.peers.base[t], f.lay.upload_master_off[par]);
     float4* dst = stage_master + static_cast<long long>(z) * nv;
-    for (long long i = tid; i < nv; i += stride) dst[i] = ptx::ld_nc_f4(src + i);
+    for (long long i = tid; i < nv; i += stride) dst[i] = ptx::ld_peer_f4(src + i);
   }
+  __syncthreads();
+  if (threadIdx.x == 0) stamp(plan, STAMP_PULL_END);
+}
+
+// fp8 MLP variant: a candidate is one Mx8MlpLayout blob (e4m3 weights + scale chunks + fp32
+// biases, 227 KB for 784x256x62) at heap offset off[parity] of its trainer.
+__global__ void __launch_bounds__(256)
+k_pull_blob(FedArgs f, long long off0, long long off1, long long nbytes, uint8_t* stage) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  char* me = f.peers.base[f.rank];
+  const RoundState* st = at<RoundState>(me, f.lay.state_off);
+  RoundPlan* plan = at<RoundPlan>(me, f.lay.plan_off);
+  if (!(st->role[f.rank] & ROLE_COMM)) return;
+  const int z = blockIdx.y;
+  if (z >= plan->n_cand) return;
+  if (blockIdx.x == 0 && z == 0 && threadIdx.x == 0) stamp(plan, STAMP_PULL_BEGIN);
+  const int t = plan->cand_rank[z];
+  const uint32_t epoch = st->epoch;
+  if (threadIdx.x == 0)
+    ptx::wait_flag_ge(at<uint32_t>(me, f.lay.flags_off) + FLAG_TRAINED + t, epoch + 1);
+  __syncthreads();
+  const long long nv = nbytes / 16;
+  const float4* src = at<const float4>(f.peers.base[t], (epoch & 1u) ? off1 : off0);
+  float4* dst = reinterpret_cast<float4*>(stage + static_cast<long long>(z) * nbytes);
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long i = tid;
+  for (; i + 3 * stride < nv; i += 4 * stride) {   // four peer loads in flight per thread
+    const float4 a = ptx::ld_peer_f4(src + i), b = ptx::ld_peer_f4(src + i + stride);
+    const float4 c = ptx::ld_peer_f4(src + i + 2 * stride), d = ptx::ld_peer_f4(src + i + 3 * stride);
+    dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+  }
+  for (; i < nv; i += stride) dst[i] = ptx::ld_peer_f4(src + i);
   __syncthreads();
   if (threadIdx.x == 0) stamp(plan, STAMP_PULL_END);
 }
@@ -510,12 +560,17 @@ int fed_grid(long long n_params) {
 }  // namespace
 
 cudaError_t fed_plan_round(const FedArgs& f, const PlanLayer* layers, int n_layers,
-                           int steps_per_round, int staged, cudaStream_t s) {
+                           int steps_per_round, int staged, cudaStream_t s, const PlanBlobs* blobs) {
   if (n_layers > kMaxPlanLayers) return cudaErrorInvalidValue;
   PlanLayers pl{};
   pl.n = n_layers;
   pl.steps_per_round = steps_per_round;
   pl.staged = staged;
+  if (blobs != nullptr) {
+    pl.use_blob = 1;
+    pl.stage_blob = blobs->stage; pl.blob_bytes = blobs->bytes;
+    pl.upq_off[0] = blobs->upq_off[0]; pl.upq_off[1] = blobs->upq_off[1];
+  }
   for (int i = 0; i < n_layers; ++i) pl.l[i] = layers[i];
   note_launch();
   return launch_pdl(k_plan, dim3(1), dim3(32), 0, s, f, pl);
@@ -546,6 +601,17 @@ cudaError_t fed_pull_candidates(const FedArgs& f, void* stage_shadow, float* sta
   return launch_pdl(k_pull, dim3(static_cast<unsigned>(blocks), kMaxRanks), dim3(256), 0, s, f,
                     reinterpret_cast<uint4*>(stage_shadow),
                     reinterpret_cast<float4*>(stage_master));
+}
+
+cudaError_t fed_pull_blobs(const FedArgs& f, long long off0, long long off1, long long nbytes,
+                           void* stage, cudaStream_t s) {
+  if (nbytes % 16 != 0) return cudaErrorInvalidValue;
+  long long blocks = (nbytes / 16 + 256 * 4 - 1) / (256 * 4);
+  if (blocks > 18) blocks = 18;  // x kMaxRanks candidate slots <= 144 blocks: one wave
+  if (blocks < 1) blocks = 1;
+  note_launch();
+  return launch_pdl(k_pull_blob, dim3(static_cast<unsigned>(blocks), kMaxRanks), dim3(256), 0, s, f, off0, off1,
+                    nbytes, static_cast<uint8_t*>(stage));
 }
 
 cudaError_t fed_wait_trained(const FedArgs& f, cudaStream_t s) {

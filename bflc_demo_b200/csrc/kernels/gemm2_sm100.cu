@@ -18,6 +18,7 @@
 #include <cstring>
 
 #include "bflc_kernels.h"
+#include "epi_common.cuh"
 #include "sm100_ptx.cuh"
 
 namespace bflc {
@@ -30,8 +31,8 @@ constexpr int kStages = 6;
 constexpr int kABytes = kBM * 128, kBBytes = (kBN / 2) * 128, kStageBytes = kABytes + kBBytes;
 constexpr int kTileBytes = kStages * kStageBytes;
 constexpr int kBarBytes = 256;
-constexpr int kStgLd = 36;
-constexpr int kStgBytes = 4 * 32 * kStgLd * 4;
+using epi::kStgLd;
+using epi::kStgBytes;
 constexpr int kSmemTotal = kTileBytes + kBarBytes + kStgBytes + kBN * 4 + 1024;
 constexpr int kThreads = 192;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
@@ -80,10 +81,7 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
       ::"r"(ptx::smem_u32(bar)), "h"(static_cast<uint16_t>(3))
       : "memory");
 }
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
+__device__ __forceinline__ uint32_t pack2(float a, float b) { return epi::pack_bf16x2(a, b); }
 __device__ __forceinline__ float gelu_f(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
 }

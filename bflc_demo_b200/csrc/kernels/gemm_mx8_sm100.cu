@@ -25,6 +25,7 @@
 #include <cstring>
 
 #include "bflc_kernels.h"
+#include "epi_common.cuh"
 #include "launch.cuh"
 #include "sm100_ptx.cuh"
 
@@ -34,9 +35,9 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kBK = 128;                 // fp8 elements per K-block (= 128 bytes)
-constexpr int kSfChunk = 512;            // bytes of scale factors per (128 rows, 128 K)
-constexpr int kStgLd = 36;
-constexpr int kStgBytes = 4 * 32 * kStgLd * 4;
+using epi::kSfChunk;                     // bytes of scale factors per (128 rows, 128 K)
+using epi::kStgLd;
+using epi::kStgBytes;
 constexpr int kBarBytes = 256;
 constexpr int kThreads = 192;
 
@@ -63,45 +64,12 @@ struct PM {
   const float* bias; int act;
 };
 
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes),
-        "r"(ptx::smem_u32(bar))
-      : "memory");
-}
-// smem descriptor of a scale-factor chunk for tcgen05.cp: no swizzle, 8-row x 16-byte core
-// matrices stacked every 128 bytes (SBO), a single core matrix along K (LBO unused)
-__device__ __forceinline__ uint64_t sf_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>(128 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  return d;
-}
-__device__ __forceinline__ void utccp_32x128b_warpx4(uint32_t tmem_dst, uint64_t desc) {
-  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(desc) : "memory");
-}
-__device__ __forceinline__ void umma_mx8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate, uint32_t tsfa, uint32_t tsfb) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n"
-      :
-      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
-      : "memory");
-}
-// Block-scaled instruction descriptor: e4m3 x e4m3, K-major, UE8M0 scales, fp32 accumulate.
-//   [4,6) b_sf_id  [7,10) a_format  [10,13) b_format  [17,23) N>>3  [23] scale_format (1 = E8M0)
-//   [24,29) M>>4  [29,31) a_sf_id
-__device__ __forceinline__ constexpr uint32_t make_idesc_mx8(uint32_t M, uint32_t N) {
-  return ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24);
-}
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
+using epi::bulk_g2s;
+using epi::sf_desc;
+using epi::utccp_32x128b_warpx4;
+using epi::umma_mx8;
+using epi::make_idesc_mx8;
+__device__ __forceinline__ uint32_t pack2(float a, float b) { return epi::pack_bf16x2(a, b); }
 __device__ __forceinline__ float gelu_f(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
 }
@@ -292,30 +260,11 @@ k_quantize_mx8(const T* __restrict__ x, long long ldx, int R, int K, float in_sc
   if (row >= R || k0 >= K) { *sfp = 127; return; }
   const int n = min(32, K - k0);
   float v[32];
-  float amax = 0.f;
   const T* xp = x + static_cast<long long>(row) * ldx + k0;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    v[i] = i < n ? to_f<T>(xp[i]) * in_scale : 0.f;
-    amax = fmaxf(amax, fabsf(v[i]));
-  }
-  int e = 127;
-  if (amax > 0.f) {
-    const uint32_t b = __float_as_uint(amax * (1.f / 448.f));
-    e = static_cast<int>((b >> 23) & 0xFF) + ((b & 0x7FFFFF) ? 1 : 0);
-    e = max(1, min(254, e));
-  }
-  *sfp = static_cast<uint8_t>(e);
-  const float inv = __uint_as_float(static_cast<uint32_t>(254 - e) << 23);   // 2^(127 - e)
+  for (int i = 0; i < 32; ++i) v[i] = i < n ? to_f<T>(xp[i]) * in_scale : 0.f;
   uint32_t w[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(v[4 * i] * inv, v[4 * i + 1] * inv),
-                                                 __NV_SATFINITE, __NV_E4M3);
-    const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(v[4 * i + 2] * inv, v[4 * i + 3] * inv),
-                                                 __NV_SATFINITE, __NV_E4M3);
-    w[i] = lo | (hi << 16);
-  }
+  *sfp = static_cast<uint8_t>(epi::mx8_quant32(v, w));
   uint8_t* qp = q + static_cast<long long>(row) * ldq + k0;
   if (k0 + 32 <= ldq) {   // whole group inside the (16-byte padded) row pitch: two 16-byte stores
     reinterpret_cast<uint4*>(qp)[0] = make_uint4(w[0], w[1], w[2], w[3]);

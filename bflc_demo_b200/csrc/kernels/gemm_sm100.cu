@@ -23,6 +23,7 @@
 #include <mutex>
 
 #include "bflc_kernels.h"
+#include "epi_common.cuh"
 #include "launch.cuh"
 #include "sm100_ptx.cuh"
 
@@ -81,33 +82,11 @@ struct SmemLayout {
   static constexpr int kTotal = kTileBytes + kBarBytes + kStgBytes + kBiasBytes + 1024;
 };
 
-constexpr int kStgLd = 36;  // floats per staged row: 16-byte aligned, conflict-free both ways
-
-// sum of column `lane` over the first rmax rows of a staged 32 x 32 sub-tile; the 32 loads are
-// independent (a rolled `tot += stg[...]` loop serialises ~25-cycle smem latencies)
-__device__ __forceinline__ float col_sum32(const float* stg, int lane, int rmax) {
-  float t[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int rr = 0; rr < 32; ++rr) t[rr & 3] += rr < rmax ? stg[rr * kStgLd + lane] : 0.f;
-  return (t[0] + t[1]) + (t[2] + t[3]);
-}
-__device__ __forceinline__ void stage_put(float* stg, int lane, const float (&v)[32]) {
-  float4* rowp = reinterpret_cast<float4*>(stg + lane * kStgLd);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) rowp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-}
-__device__ __forceinline__ void stage_get(const float* stg, int lane, float (&v)[32]) {
-  const float4* rowp = reinterpret_cast<const float4*>(stg + lane * kStgLd);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 t = rowp[j];
-    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-  }
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
+using epi::kStgLd;
+using epi::col_sum32;
+using epi::stage_put;
+using epi::stage_get;
+using epi::pack_bf16x2;
 
 // Staged [32][32] fp32 tile -> global.  Lane (cr, cg) moves 4 consecutive columns of row
 // it*4+cr, so one warp instruction covers 4 rows x 128 B.  DT: 0 fp32, 1 bf16, 2 fp8(e4m3).

@@ -1,22 +1,35 @@
 // One persistent kernel for a trainer's whole local-training pass of the 2-layer MLP:
 // every mini-batch step (forward, softmax-xent, both weight gradients, the hidden gradient
 // and the optimizer) runs inside ONE launch; phases are separated by a device-wide barrier
-// instead of kernel boundaries.
+// instead of kernel boundaries -- and the LAST step's optimizer epilogue is also the
+// UploadLocalUpdate of the protocol (reference: CommitteePrecompiled.cpp:215-258): it writes the
+// peer-readable upload buffers and CTA 0 releases FLAG_TRAINED on every peer.
 //
-//   per step:  P1  h  = relu(x W1^T + b1)                       16 tiles   (K = 784)
-//              P2  dlogits = softmax(h W2^T + b2) - onehot       4 tiles   (+loss, #correct, db2)
-//              P3  dW2 = dlogits^T h   ||   dh = (dlogits W2) * relu'(h) (+db1)   4 + 16 tiles
-//              P4  dW1 = dh^T x                                  26 tiles
-//              P5  SGD / Adam over the flat buffer (+bf16 shadow refresh, grad zeroing)
+//   per step:  P1  h  = relu(x W1^T + b1)                       K = 784
+//              X   per 128 batch rows, 4 CTAs: fwd2 -> softmax-xent -> dh = (dlogits W2) relu'(h)
+//              B   dW1 = dh^T x  ||  dW2 = dlogits^T h, optimizer (SGD / Adam) applied to the fp32
+//                  master straight from the accumulator tile (E_OPT) + compute-copy refresh
 //
-// Each GEMM tile is the same tcgen05 / TMEM / TMA pipeline as gemm_sm100.cu (128 x 64 tiles,
-// 8-stage 128B-swizzled ring, one elected MMA thread, staged coalesced epilogue); the smem
-// ring, its mbarriers and the TMEM allocation persist across tiles, phases and steps.
+// Precision.  bf16 mode: every GEMM is tcgen05.mma.kind::f16 on bf16 shadows.  fp8 mode
+// (BASELINE.json config #2, "block-scaled fp8"): fwd1 and fwd2 are
+// tcgen05.mma.kind::mxf8f6f4.block_scale -- x arrives as e4m3 + UE8M0 scales from the input
+// kernel (elementwise_optim.cu), the E_OPT epilogue re-quantises every updated weight tile
+// (one scale per 32 K-elements, computed with three warp shuffles over the 8 lanes that own a
+// K-group) and the fwd1 epilogue quantises h; scale chunks reach TMEM through tcgen05.cp.
+// The hidden/weight gradients stay bf16, masters and Adam moments fp32.  In fp8 mode fwd1 runs
+// as 128 x 64 tiles (150 KB of TMA ingest per CTA instead of 300 KB).  Measured limits of the
+// block-scaled UMMA on sm_100a: M = 64 per CTA is an illegal instruction, and a scale-factor
+// TMEM address at an odd column (32-wide tiles) faults with `misaligned address`.
+//
+// Each GEMM tile is the same tcgen05 / TMEM / TMA pipeline as gemm_sm100.cu (8-stage
+// 128B-swizzled ring, one elected MMA thread, staged coalesced epilogue); the smem ring, its
+// mbarriers and the TMEM allocation persist across tiles, phases and steps.
 //
 // Why: at this problem size every stand-alone GEMM launch costs 6-12 us of which only a
 // fraction is math (launch, prologue, first-TMA latency, drain) -- six launches per step,
 // 48 per round.  Inside one kernel the fixed costs are paid once and a phase boundary is a
-// ~1 us grid barrier.  (Reference step: python-sdk/main.py:141-148, three sess.run calls.)
+// ~1-2 us grid barrier.  (Reference step: python-sdk/main.py:141-148, three sess.run calls;
+// Adam: the commented alternative at python-sdk/main.py:126.)
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -24,6 +37,7 @@
 #include <cstring>
 
 #include "bflc_kernels.h"
+#include "epi_common.cuh"
 #include "launch.cuh"
 #include "sm100_ptx.cuh"
 
@@ -31,21 +45,32 @@ namespace bflc {
 
 namespace {
 
+using epi::kStgLd;
+using epi::kStgBytes;
+using epi::kSfChunk;
+using epi::stage_put;
+using epi::stage_get;
+using epi::col_sum32;
+using epi::st_sw128;
+__device__ __forceinline__ uint32_t pack2(float a, float b) { return epi::pack_bf16x2(a, b); }
+
 constexpr int kBM = 128, kBN = 64, kStages = 8;
 constexpr int kABytes = kBM * 128, kBBytes = kBN * 128, kStageBytes = kABytes + kBBytes;
 constexpr int kTileBytes = kStages * kStageBytes;
+constexpr int kSfStage = 2 * kSfChunk;              // per ring stage: [SFA chunk | SFB chunk]
+constexpr int kSfBytes = kStages * kSfStage;        // fp8 only; the chain uses the first 4 chunks
 constexpr int kBarBytes = 512;
-constexpr int kStgLd = 36;
-constexpr int kStgBytes = 4 * 32 * kStgLd * 4;
 constexpr int kBiasFloats = 320;   // chain: b1[256] | b2[64]; tile jobs use the first kBN
-constexpr int kSmemTotal = kTileBytes + kBarBytes + kStgBytes + kBiasFloats * 4 + 1024;
+constexpr int kSmemTotal = kTileBytes + kSfBytes + kBarBytes + kStgBytes + kBiasFloats * 4 + 1024;
+static_assert(kSmemTotal <= 227 * 1024, "shared memory budget");
 constexpr int kThreads = 192;
 constexpr int kGrid = 32;
 
 // ---- fused chain (hidden == 256): the same 192 KB of ring memory, re-cut as
-//   3 stages x (x tile 16 KB + W1 tile 32 KB) for fwd1, then after fwd1 has retired
+//   3 stages x (x tile 16 KB + W1 tile 32 KB) for fwd1 (plan 1), then after fwd1 has retired
 //   [0, 64 KB) h as fwd2's A operand | [96, 128 KB) W2 MN-major (dh's B) | [128, 144 KB) dlogits
 //   (dh's A), and a dedicated [144, 176 KB) W2 K-major (fwd2's B) loaded up front.
+//   fp8: h is 2 x 16 KB of e4m3 at [0, 32 KB), W2 K-major 2 x 8 KB at [144, 160 KB).
 constexpr int kCStages = 3;
 constexpr int kCA = kBM * 128, kCB = 256 * 128, kCStage = kCA + kCB;
 constexpr int kOffH = 0;
@@ -55,29 +80,23 @@ constexpr int kOffW2K = kCStages * kCStage;
 static_assert(kOffDL + 16384 <= kOffW2K && kOffW2K + 32768 <= kTileBytes, "chain smem layout");
 constexpr int kChainH = 256;
 constexpr int kDefaultPlan = 3;    // phase plan when neither the caller nor BFLC_MLP_CHAIN picks one
-constexpr int kTmemCols = 512;     // chain: h / dh accumulator [0,256) + logits [256,320)
-// ---- cluster plan (chain == 4): ring cut to 4 stages [0, 96 KB); the upper half is dedicated:
-//   [96, 160 KB) h tile assembled over DSMEM by the 4 fwd1 CTAs of an M-tile | [160, 192 KB) W2
-//   K-major, prefetched at step start.  W2^T slice and dlogits alias the (then dead) ring.
-constexpr int kOffH4 = 96 * 1024, kOffW2K4 = 160 * 1024, kOffW2MN4 = 0, kOffDL4 = 16 * 1024;
-constexpr int kOffHQ4 = 32 * 1024;   // this CTA's own 128 x 64 quarter of h, staged for the bulk copies
-static_assert(kOffW2K4 + 32768 <= kTileBytes, "cluster plan smem layout");
-
-struct ChainLay { int h, w2k, w2mn, dl; };   // byte offsets of the chain operands in this plan
+constexpr int kTmemCols = 512;     // chain: h / dh accumulator [0,256) + logits [256,320) + scales
+constexpr uint32_t kTmemSfa = 320, kTmemSfb = 328;   // fp8: scale-factor columns (4 + up to 4)
 
 enum EpiMode : int { E_BIAS_RELU_BF16 = 0, E_XENT = 1, E_F32 = 2, E_MASK_COLSUM_BF16 = 3,
                      E_OPT = 4 };  // E_OPT: the tile IS the gradient -> optimizer applied in the epilogue
 
-struct Maps {  // 11 TMA descriptors, all bf16, SWIZZLE_128B
-  CUtensorMap x_k, w1_k, h_k, w2_k, dl_mn, h_mn, dl_k, w2_mn, dh_mn, x_mn;
-  CUtensorMap w1_k256;   // W1 with a 256-row box (chain: the whole hidden width in one tile)
+struct Maps {  // TMA descriptors, SWIZZLE_128B
+  CUtensorMap x_k, w1_k, h_k, w2_k, dl_mn, h_mn, dl_k, w2_mn, dh_mn, x_mn;   // bf16
+  CUtensorMap w1_k256;   // W1 with a 256-row box (plan 1: the whole hidden width in one tile)
+  CUtensorMap xq_k, w1q_k, hq_k, w2q_k;   // fp8 (e4m3 as u8): x 128-row box, W1 p1_bn rows, h 128, W2 64
 };
 
 struct Args {
   int B, steps, in_dim, hidden, n_classes, ncp;  // ncp = dlogits row stride (padded classes)
   int chain;                     // 0: P1|P2|P3   1: fwd1->xent->dh chained   3: P1 | fwd2->xent->dh chained
   int epiopt;                    // optimizer applied in the weight-gradient epilogues (no P5)
-  unsigned long long* dbg;       // optional %globaltimer stamps [steps][16] written by CTA 0
+  unsigned long long* dbg;       // optional %globaltimer stamps [steps][32] written by CTA 0
   const unsigned int* x_ready;   // optional input pipeline: step s may read x once x_ready[s] >= *round_seq
   const unsigned int* round_seq;
   long long n_params;
@@ -93,9 +112,16 @@ struct Args {
   __nv_bfloat16* h; __nv_bfloat16* dlogits; __nv_bfloat16* dh;
   const int32_t* labels;
   float* loss_sum; unsigned int* correct;
+  // fp8 forward
+  const uint8_t* x_sf; uint8_t* work_q; uint8_t* h_q; uint8_t* h_sf;
+  Mx8MlpLayout ql;
+  int p1_bn;                     // fp8 fwd1 tile width: 64 (16 CTAs) or 32 (32 CTAs)
+  // fused upload
+  int has_fed; FedArgs f; long long upq_off[2];
+  int n_samples, n_loss_terms, byz_mode; float byz_scale;
 };
 
-struct Job {  // one 128 x 64 output tile
+struct Job {  // one output tile (128 or 64 rows x 64 columns)
   const CUtensorMap* ta; const CUtensorMap* tb;
   int a_mn, b_mn;
   int a_c0, a_c1, b_c0, b_c1;   // TMA coordinates of K-block 0 (c0 = innermost)
@@ -110,8 +136,15 @@ struct Job {  // one 128 x 64 output tile
   const int32_t* labels;        // E_XENT (already offset to this step's rows)
   float grad_scale;
   float bc1, bc2;               // E_OPT + Adam: bias corrections of this step
-  int dsm, dsm_kb;              // E_BIAS_RELU_BF16 in the cluster plan: broadcast into h-tile K-block dsm_kb
-  uint64_t* dsm_bar;            // (local address of) the mbarrier each destination CTA waits on
+  // ---- fp8 operands (K-major e4m3, K-blocks of 128 elements); bn = tile width (64, or 32)
+  int fp8, bn;
+  const uint8_t* sfa; const uint8_t* sfb;   // scale chunk of K-block 0 of this tile's row block
+  uint32_t sfa_col, sfb_col;                // column of the tile's first row inside the 4-column chunk
+  // ---- E_OPT in fp8 mode: where the re-quantised tile goes (byte offsets inside a model blob)
+  int q_off, qsf_off, ldq, q_nkb;
+  int last;                     // last step of the round: E_OPT also publishes the upload
+  unsigned long long* dbg;      // this step's stamp slots (CTA 0): [dbg_slot] accumulator ready, [+1] epilogue done
+  int dbg_slot;
 };
 
 struct Pipe {  // persistent pipeline state of one role
@@ -128,117 +161,133 @@ struct CPipe {
   uint32_t n;    // chains processed (parity of the once-per-chain barriers)
 };
 
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
+template <typename T>
+__device__ __forceinline__ T* heap_at(char* base, long long off) {
+  return reinterpret_cast<T*>(base + off);
 }
-__device__ __forceinline__ void stage_put(float* stg, int lane, const float (&v)[32]) {
-  float4* rowp = reinterpret_cast<float4*>(stg + lane * kStgLd);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) rowp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-}
-__device__ __forceinline__ void stage_get(const float* stg, int lane, float (&v)[32]) {
-  const float4* rowp = reinterpret_cast<const float4*>(stg + lane * kStgLd);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 t = rowp[j];
-    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-  }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
-// sum of column `lane` over the first rmax rows of a staged 32 x 32 sub-tile: all 32 loads are
-// independent and issued back to back (a rolled `tot += stg[...]` loop serialised ~25-cycle smem
-// latencies: 0.4 us per sub-tile, 3+ us per dh tile -- measured with the in-kernel stamps)
-__device__ __forceinline__ float col_sum32(const float* stg, int lane, int rmax) {
-  float t[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int rr = 0; rr < 32; ++rr) t[rr & 3] += rr < rmax ? stg[rr * kStgLd + lane] : 0.f;
-  return (t[0] + t[1]) + (t[2] + t[3]);
-}
-
-// 16-byte chunk `chunk` of row r of a 128-byte-swizzled K-major operand tile (defined below)
-__device__ __forceinline__ void st_sw128(uint8_t* tile, int r, int chunk, uint4 v);
-
-// ---- thread-block cluster helpers (cluster plan, chain == 4)
-__device__ __forceinline__ void dsm_st_v4(uint32_t local_smem_addr, uint32_t cta_rank, uint4 v) {
-  uint32_t ra;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem_addr), "r"(cta_rank));
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(v.x), "r"(v.y), "r"(v.z),
-               "r"(v.w)
-               : "memory");
-}
-// 16-byte-multiple copy local smem -> smem of CTA `cta_rank` of the cluster, completing `bytes` of
-// the transaction count of THAT CTA's mbarrier (both given as this CTA's addresses of the same
-// objects; mapa translates them)
-__device__ __forceinline__ void dsm_bulk_copy(uint32_t dst_local, uint32_t src_local, uint32_t bytes,
-                                              uint32_t bar_local, uint32_t cta_rank) {
-  uint32_t rdst, rbar;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(dst_local), "r"(cta_rank));
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar_local), "r"(cta_rank));
-  asm volatile(
-      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(rdst), "r"(src_local), "r"(bytes), "r"(rbar)
-      : "memory");
-}
-__device__ __forceinline__ void cluster_barrier() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+// Where the last step's optimizer epilogue publishes (resolved from the ledger page: the upload
+// buffers are double-buffered by epoch parity).
+struct UploadDst {
+  float* master;            // fp32 upload (FedAvg operand)
+  __nv_bfloat16* shadow;    // bf16 upload (bf16-mode validation operand); null in fp8 mode
+  uint8_t* blob;            // fp8 mode: Mx8MlpLayout blob the committee validates
+  const float* global;      // Byzantine fault injection: upload global - s * (w - global)
+  float byz_scale;
+};
+template <bool FP8>
+__device__ __forceinline__ UploadDst upload_dst(const Args& a) {
+  char* me = a.f.peers.base[a.f.rank];
+  const RoundState* st = heap_at<const RoundState>(me, a.f.lay.state_off);
+  const uint32_t par = st->epoch & 1u;
+  UploadDst u;
+  u.master = heap_at<float>(me, a.f.lay.upload_master_off[par]);
+  u.shadow = FP8 ? nullptr : heap_at<__nv_bfloat16>(me, a.f.lay.upload_shadow_off[par]);
+  u.blob = FP8 ? heap_at<uint8_t>(me, a.upq_off[par]) : nullptr;
+  u.global = a.byz_mode == 1 ? heap_at<const float>(me, a.f.lay.global_off) : nullptr;
+  u.byz_scale = a.byz_scale;
+  return u;
 }
 
 // ---------------------------------------------------------------- producer / MMA / epilogue
-// `ns` = ring depth in use (8, or 4 in the cluster plan where the upper half of the ring memory
-// holds the DSMEM-assembled h tile and the prefetched W2)
-__device__ __forceinline__ void produce_tile(const Job& j, uint8_t* smem, uint64_t* full_bar,
-                                             uint64_t* empty_bar, Pipe& pp, uint32_t ns) {
+template <bool FP8>
+__device__ __forceinline__ void produce_tile(const Job& j, uint8_t* smem, uint8_t* sf_smem,
+                                             uint64_t* full_bar, uint64_t* empty_bar, Pipe& pp) {
   for (int i = 0; i < j.n_kb; ++i, ++pp.it) {
-    const int s = pp.it % ns;
-    const uint32_t ph = (pp.it / ns) & 1;
+    const int s = pp.it % kStages;
+    const uint32_t ph = (pp.it / kStages) & 1;
     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
     uint8_t* sa = smem + s * kStageBytes;
     uint8_t* sb = sa + kABytes;
     if (ptx::elect_one()) {
-      ptx::mbar_expect_tx(&full_bar[s], kStageBytes);
-      if (!j.a_mn) {
-        ptx::tma_load_3d(sa, j.ta, &full_bar[s], j.a_c0 + i * 64, j.a_c1, 0);
+      if (FP8 && j.fp8) {
+        // e4m3 tiles (K-block = 128 bytes) + the two 512-byte scale chunks of this K-block
+        ptx::mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(kABytes + j.bn * 128 + kSfStage));
+        ptx::tma_load_3d(sa, j.ta, &full_bar[s], j.a_c0 + i * 128, j.a_c1, 0);
+        ptx::tma_load_3d(sb, j.tb, &full_bar[s], j.b_c0 + i * 128, j.b_c1, 0);
+        epi::bulk_g2s(sf_smem + s * kSfStage, j.sfa + static_cast<long long>(i) * kSfChunk, kSfChunk, &full_bar[s]);
+        epi::bulk_g2s(sf_smem + s * kSfStage + kSfChunk, j.sfb + static_cast<long long>(i) * kSfChunk, kSfChunk,
+                      &full_bar[s]);
       } else {
-        ptx::tma_load_3d(sa, j.ta, &full_bar[s], j.a_c0, j.a_c1 + i * 64, 0);
-        ptx::tma_load_3d(sa + 64 * 128, j.ta, &full_bar[s], j.a_c0 + 64, j.a_c1 + i * 64, 0);
+        ptx::mbar_expect_tx(&full_bar[s], kStageBytes);
+        if (!j.a_mn) {
+          ptx::tma_load_3d(sa, j.ta, &full_bar[s], j.a_c0 + i * 64, j.a_c1, 0);
+        } else {
+          ptx::tma_load_3d(sa, j.ta, &full_bar[s], j.a_c0, j.a_c1 + i * 64, 0);
+          ptx::tma_load_3d(sa + 64 * 128, j.ta, &full_bar[s], j.a_c0 + 64, j.a_c1 + i * 64, 0);
+        }
+        if (!j.b_mn)
+          ptx::tma_load_3d(sb, j.tb, &full_bar[s], j.b_c0 + i * 64, j.b_c1, 0);
+        else
+          ptx::tma_load_3d(sb, j.tb, &full_bar[s], j.b_c0, j.b_c1 + i * 64, 0);
       }
-      if (!j.b_mn)
-        ptx::tma_load_3d(sb, j.tb, &full_bar[s], j.b_c0 + i * 64, j.b_c1, 0);
-      else
-        ptx::tma_load_3d(sb, j.tb, &full_bar[s], j.b_c0, j.b_c1 + i * 64, 0);
     }
     __syncwarp();
   }
 }
 
-__device__ __forceinline__ void mma_tile(const Job& j, uint8_t* smem, uint64_t* full_bar,
+template <bool FP8>
+__device__ __forceinline__ void mma_tile(const Job& j, uint8_t* smem, uint8_t* sf_smem, uint64_t* full_bar,
                                          uint64_t* empty_bar, uint64_t* accum_bar,
-                                         uint32_t tmem_base, Pipe& pp, uint32_t ns) {
-  const uint32_t idesc = ptx::make_idesc(1u, j.a_mn ? 1u : 0u, j.b_mn ? 1u : 0u, kBM, kBN);
+                                         uint32_t tmem_base, Pipe& pp) {
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024, v1, SWIZZLE_128B
   const uint32_t base_lo = ptx::smem_u32(smem) >> 4;
-  const uint32_t lbo_a = j.a_mn ? (8192u >> 4) : 1u, lbo_b = j.b_mn ? (8192u >> 4) : 1u;
-  const uint32_t lo_a0 = base_lo | (lbo_a << 16);
-  const uint32_t lo_b0 = (base_lo + (kABytes >> 4)) | (lbo_b << 16);
-  const uint32_t ks_a = (j.a_mn ? 2048u : 32u) >> 4, ks_b = (j.b_mn ? 2048u : 32u) >> 4;
-  for (int i = 0; i < j.n_kb; ++i, ++pp.it) {
-    const int s = pp.it % ns;
-    const uint32_t ph = (pp.it / ns) & 1;
-    ptx::mbar_wait(&full_bar[s], ph);
-    ptx::tc_fence_after_sync();
-    const uint32_t so = static_cast<uint32_t>(s) * (kStageBytes >> 4);
-    if (ptx::elect_one()) {
+  if (FP8 && j.fp8) {
+    const uint32_t idesc0 = epi::make_idesc_mx8(kBM, static_cast<uint32_t>(j.bn));
+    const uint32_t lo_a0 = base_lo | (1u << 16);
+    const uint32_t lo_b0 = (base_lo + (kABytes >> 4)) | (1u << 16);
+    const uint32_t tsfa = tmem_base + kTmemSfa, tsfb = tmem_base + kTmemSfb;
+    for (int i = 0; i < j.n_kb; ++i, ++pp.it) {
+      const int s = pp.it % kStages;
+      const uint32_t ph = (pp.it / kStages) & 1;
+      ptx::mbar_wait(&full_bar[s], ph);
+      ptx::tc_fence_after_sync();
+      const uint32_t so = static_cast<uint32_t>(s) * (kStageBytes >> 4);
+      if (ptx::elect_one()) {
+        // tcgen05.cp and tcgen05.mma execute in issue order: the one scale region in TMEM is
+        // rewritten per K-block without any extra barrier
+        const uint32_t sfs = ptx::smem_u32(sf_smem + s * kSfStage);
+        epi::utccp_32x128b_warpx4(tsfa, epi::sf_desc(sfs));
+        epi::utccp_32x128b_warpx4(tsfb, epi::sf_desc(sfs + kSfChunk));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (lo_a0 + so + k * ks_a);
-        const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (lo_b0 + so + k * ks_b);
-        ptx::umma_f16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        for (uint32_t k = 0; k < 4; ++k) {
+          const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (lo_a0 + so + k * 2u);
+          const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (lo_b0 + so + k * 2u);
+          epi::umma_mx8(tmem_base, ad, bd, epi::idesc_mx8_k(idesc0, k), (i > 0 || k > 0) ? 1u : 0u,
+                        tsfa + j.sfa_col, tsfb + j.sfb_col);
+        }
+        ptx::umma_commit(&empty_bar[s]);
       }
-      ptx::umma_commit(&empty_bar[s]);
+      __syncwarp();
     }
-    __syncwarp();
+  } else {
+    const uint32_t idesc = ptx::make_idesc(1u, j.a_mn ? 1u : 0u, j.b_mn ? 1u : 0u, kBM, kBN);
+    const uint32_t lbo_a = j.a_mn ? (8192u >> 4) : 1u, lbo_b = j.b_mn ? (8192u >> 4) : 1u;
+    const uint32_t lo_a0 = base_lo | (lbo_a << 16);
+    const uint32_t lo_b0 = (base_lo + (kABytes >> 4)) | (lbo_b << 16);
+    const uint32_t ks_a = (j.a_mn ? 2048u : 32u) >> 4, ks_b = (j.b_mn ? 2048u : 32u) >> 4;
+    for (int i = 0; i < j.n_kb; ++i, ++pp.it) {
+      const int s = pp.it % kStages;
+      const uint32_t ph = (pp.it / kStages) & 1;
+      ptx::mbar_wait(&full_bar[s], ph);
+      ptx::tc_fence_after_sync();
+      const uint32_t so = static_cast<uint32_t>(s) * (kStageBytes >> 4);
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (lo_a0 + so + k * ks_a);
+          const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (lo_b0 + so + k * ks_b);
+          ptx::umma_f16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty_bar[s]);
+      }
+      __syncwarp();
+    }
   }
   if (ptx::elect_one()) ptx::umma_commit(accum_bar);
   __syncwarp();
@@ -246,11 +295,11 @@ __device__ __forceinline__ void mma_tile(const Job& j, uint8_t* smem, uint64_t* 
 }
 
 // SGD / Adam on n (<= 4) consecutive parameters starting at flat index pi, gradient in g[]:
-// fp32 master, bf16 shadow (and the Adam moments) are updated in place.  Coherent loads: other
-// CTAs of this kernel wrote these buffers in earlier phases.
+// fp32 master, bf16 shadow (and the Adam moments) are updated in place; the new values are
+// returned in w[].  Coherent loads: other CTAs of this kernel wrote these buffers in earlier phases.
 __device__ __forceinline__ void opt_apply(const Args& a, long long pi, int n, const float* g,
-                                          float bc1, float bc2) {
-  float w[4], m[4], v[4];
+                                          float bc1, float bc2, float (&w)[4]) {
+  float m[4], v[4];
   const bool vec = n == 4 && (pi & 3) == 0;
   if (vec) {
     const float4 w4 = __ldcg(reinterpret_cast<const float4*>(a.master + pi));
@@ -294,29 +343,25 @@ __device__ __forceinline__ void opt_apply(const Args& a, long long pi, int n, co
   }
 }
 
-// epilogue warps 2..5; `warp` is the hardware warp index
-__device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int warp, int lane,
-                                              uint64_t* accum_bar, uint32_t tmem_base,
-                                              float* stage_base, float* sbias, Pipe& pp, uint8_t* smem) {
+// E_OPT: the accumulator tile IS the weight gradient.  Per (row, 4 columns) thread: optimizer on
+// the fp32 master (+ moments), bf16 shadow refresh; fp8 mode: the updated 32-element K-group
+// (8 neighbouring lanes) is re-quantised -- group amax by three shuffles, one UE8M0 byte, four
+// e4m3 bytes per thread; on the last step the values (optionally Byzantine-transformed) also go
+// to the upload buffers the committee and the FedAvg kernel read.
+template <bool FP8>
+__device__ __forceinline__ void epilogue_opt(const Job& j, const Args& a, int warp, int lane,
+                                             uint64_t* accum_bar, uint32_t tmem_base, float* stage_base,
+                                             Pipe& pp) {
   const int q = warp & 3;
   float* stg = stage_base + (warp - 2) * (32 * kStgLd);
   const int row_base = j.m0 + q * 32;
-  const int row = row_base + lane;
-  const bool row_ok = row < j.M;
   const int cr = lane >> 3, cg = (lane & 7) * 4;
-  {
-    const int et = threadIdx.x - 64;
-    // coherent (L2) loads: the biases are rewritten by the optimizer phase of this same kernel
-    for (int i = et; i < kBN; i += 128)
-      sbias[i] = (j.bias != nullptr && j.n0 + i < j.N) ? __ldcg(j.bias + j.n0 + i) : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-  }
+  const long long pbase = reinterpret_cast<float*>(j.d) - a.master;
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-  if (j.mode == E_OPT && !a.adam) {
-    // SGD in the epilogue: this thread's share of the parameter tile is fetched while the MMAs
-    // are still running, so the update costs no exposed load latency
-    const long long pbase = reinterpret_cast<float*>(j.d) - a.master;
-    float4 wpre[kBN / 32][8];
+  // SGD: this thread's share of the parameter tile is fetched while the MMAs are still running,
+  // so the update costs no exposed load latency
+  float4 wpre[kBN / 32][8];
+  if (!a.adam) {
 #pragma unroll
     for (int c = 0; c < kBN / 32; ++c)
 #pragma unroll
@@ -326,43 +371,124 @@ __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int w
                           ? __ldcg(reinterpret_cast<const float4*>(a.master + pbase + static_cast<long long>(rw) * j.ldd + col))
                           : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    ptx::mbar_wait(accum_bar, pp.tile & 1);
-    ptx::tc_fence_after_sync();
-    ++pp.tile;
-#pragma unroll
-    for (int c = 0; c < kBN / 32; ++c) {
-      const int nc = j.n0 + c * 32;
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
-      ptx::tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
-      stage_put(stg, lane, v);
-      __syncwarp();
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + cr, rw = row_base + rr, col = nc + cg;
-        if (rw >= j.M || col + 3 >= j.N) continue;
-        const float4 g = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cg);
-        float4 w = wpre[c][it];
-        w.x -= a.lr * g.x; w.y -= a.lr * g.y; w.z -= a.lr * g.z; w.w -= a.lr * g.w;
-        const long long pi = pbase + static_cast<long long>(rw) * j.ldd + col;
-        *reinterpret_cast<float4*>(a.master + pi) = w;
-        *reinterpret_cast<uint2*>(a.shadow + pi) = make_uint2(pack2(w.x, w.y), pack2(w.z, w.w));
-      }
-      __syncwarp();
-    }
-    ptx::tc_fence_before_sync();
-    return;
   }
+  const bool up = j.last && a.has_fed;
+  UploadDst ud{};
+  if (up) ud = upload_dst<FP8>(a);
+  uint8_t* qblob = (FP8 && up) ? ud.blob : a.work_q;
   ptx::mbar_wait(accum_bar, pp.tile & 1);
   ptx::tc_fence_after_sync();
   ++pp.tile;
+  if (j.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) j.dbg[j.dbg_slot] = globaltimer_ns();
+#pragma unroll
+  for (int c = 0; c < kBN / 32; ++c) {
+    const int nc = j.n0 + c * 32;
+    uint32_t r[32];
+    ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+    ptx::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+    stage_put(stg, lane, v);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + cr, rw = row_base + rr, col = nc + cg;
+      const bool valid = rw < j.M && col + 3 < j.N;
+      const long long pi = pbase + static_cast<long long>(rw) * j.ldd + col;
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        const float4 g = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cg);
+        if (a.adam) {
+          w = __ldcg(reinterpret_cast<const float4*>(a.master + pi));
+          float4 m = __ldcg(reinterpret_cast<const float4*>(a.adam_m + pi));
+          float4 s = __ldcg(reinterpret_cast<const float4*>(a.adam_v + pi));
+          const float b1 = a.beta1, b2 = a.beta2, c1 = 1.f - a.beta1, c2 = 1.f - a.beta2;
+          m.x = b1 * m.x + c1 * g.x; m.y = b1 * m.y + c1 * g.y; m.z = b1 * m.z + c1 * g.z; m.w = b1 * m.w + c1 * g.w;
+          s.x = b2 * s.x + c2 * g.x * g.x; s.y = b2 * s.y + c2 * g.y * g.y;
+          s.z = b2 * s.z + c2 * g.z * g.z; s.w = b2 * s.w + c2 * g.w * g.w;
+          w.x -= a.lr * (m.x / j.bc1) / (sqrtf(s.x / j.bc2) + a.eps);
+          w.y -= a.lr * (m.y / j.bc1) / (sqrtf(s.y / j.bc2) + a.eps);
+          w.z -= a.lr * (m.z / j.bc1) / (sqrtf(s.z / j.bc2) + a.eps);
+          w.w -= a.lr * (m.w / j.bc1) / (sqrtf(s.w / j.bc2) + a.eps);
+          *reinterpret_cast<float4*>(a.adam_m + pi) = m;
+          *reinterpret_cast<float4*>(a.adam_v + pi) = s;
+        } else {
+          w = wpre[c][it];
+          w.x -= a.lr * g.x; w.y -= a.lr * g.y; w.z -= a.lr * g.z; w.w -= a.lr * g.w;
+        }
+        *reinterpret_cast<float4*>(a.master + pi) = w;
+        *reinterpret_cast<uint2*>(a.shadow + pi) = make_uint2(pack2(w.x, w.y), pack2(w.z, w.w));
+        if (up) {
+          if (ud.global != nullptr) {   // Byzantine client (fault injection)
+            const float4 g0 = __ldcg(reinterpret_cast<const float4*>(ud.global + pi));
+            w.x = g0.x - ud.byz_scale * (w.x - g0.x); w.y = g0.y - ud.byz_scale * (w.y - g0.y);
+            w.z = g0.z - ud.byz_scale * (w.z - g0.z); w.w = g0.w - ud.byz_scale * (w.w - g0.w);
+          }
+          *reinterpret_cast<float4*>(ud.master + pi) = w;
+          if (!FP8) *reinterpret_cast<uint2*>(ud.shadow + pi) = make_uint2(pack2(w.x, w.y), pack2(w.z, w.w));
+        }
+      }
+      // fp8: park the updated values in the staging tile (over the gradient this thread just
+      // consumed); they are re-quantised row-wise below
+      if (FP8) *reinterpret_cast<float4*>(stg + rr * kStgLd + cg) = w;
+    }
+    if (FP8) {
+      // One thread per row of the staged 32 x 32 sub-tile: its 32 columns are exactly one K-group
+      // of the weight matrix -> amax, UE8M0 byte and 32 e4m3 bytes without any shuffle, two
+      // 16-byte stores (the shuffle-per-4-columns version cost 3.7 us per step, measured).
+      __syncwarp();
+      const int rw = row_base + lane;
+      const int nv = j.N - nc < 32 ? j.N - nc : 32;          // valid columns of this group (multiple of 4)
+      if (rw < j.M && nv > 0) {
+        float v[32];
+        stage_get(stg, lane, v);
+        uint32_t w8[8];
+        const int e = epi::mx8_quant32(v, w8);
+        uint4* qd = reinterpret_cast<uint4*>(qblob + j.q_off + static_cast<long long>(rw) * j.ldq + nc);
+        qd[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+        if (nv > 16) qd[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+        qblob[j.qsf_off + epi::mx8_sf_index(rw, nc >> 5, j.q_nkb)] = static_cast<uint8_t>(e);
+      }
+    }
+    __syncwarp();
+  }
+  ptx::tc_fence_before_sync();
+  if (j.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) j.dbg[j.dbg_slot + 1] = globaltimer_ns();
+}
+
+// epilogue warps 2..5; `warp` is the hardware warp index
+template <bool FP8>
+__device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int warp, int lane,
+                                              uint64_t* accum_bar, uint32_t tmem_base,
+                                              float* stage_base, float* sbias, Pipe& pp) {
+  const int q = warp & 3;
+  float* stg = stage_base + (warp - 2) * (32 * kStgLd);
+  {
+    const int et = threadIdx.x - 64;
+    // coherent (L2) loads: the biases are rewritten by the optimizer phase of this same kernel
+    for (int i = et; i < kBN; i += 128)
+      sbias[i] = (j.bias != nullptr && j.n0 + i < j.N) ? __ldcg(j.bias + j.n0 + i) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+  if (j.mode == E_OPT) {
+    epilogue_opt<FP8>(j, a, warp, lane, accum_bar, tmem_base, stage_base, pp);
+    return;
+  }
+  const int row_base = j.m0 + q * 32;
+  const int row = row_base + lane;
+  const bool row_ok = row < j.M;
+  const int n_chunks = (FP8 && j.fp8) ? j.bn / 32 : kBN / 32;
+  const int cr = lane >> 3, cg = (lane & 7) * 4;
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  ptx::mbar_wait(accum_bar, pp.tile & 1);
+  ptx::tc_fence_after_sync();
+  ++pp.tile;
+  if (j.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) j.dbg[j.dbg_slot] = globaltimer_ns();
 
   if (j.mode != E_XENT) {
 #pragma unroll 1
-    for (int c = 0; c < kBN / 32; ++c) {
+    for (int c = 0; c < n_chunks; ++c) {
       const int nc = j.n0 + c * 32;
       if (nc >= j.N) break;
       uint32_t r[32];
@@ -374,15 +500,14 @@ __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int w
       if (j.mode == E_BIAS_RELU_BF16) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
-        if (j.dsm) {
-          // cluster plan: stage this CTA's 128 x 64 quarter of h as one swizzled 16 KB A-operand
-          // K-block in local smem (the ring is dead: the accumulator barrier has fired)
-          const int rl = q * 32 + lane;
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-            st_sw128(smem + kOffHQ4, rl, c * 4 + jj,
-                     make_uint4(pack2(v[8 * jj], v[8 * jj + 1]), pack2(v[8 * jj + 2], v[8 * jj + 3]),
-                                pack2(v[8 * jj + 4], v[8 * jj + 5]), pack2(v[8 * jj + 6], v[8 * jj + 7])));
+        if (FP8 && j.fp8 && row_ok) {
+          // fwd2's A operand: this thread's 32 columns of h are exactly one K-group
+          uint32_t w[8];
+          const int e = epi::mx8_quant32(v, w);
+          uint4* hq = reinterpret_cast<uint4*>(a.h_q + static_cast<long long>(row) * a.hidden + nc);
+          hq[0] = make_uint4(w[0], w[1], w[2], w[3]);
+          hq[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          a.h_sf[epi::mx8_sf_index(row, nc >> 5, a.ql.kb2)] = static_cast<uint8_t>(e);
         }
       } else if (j.mode == E_MASK_COLSUM_BF16) {
         // coalesced (L2-coherent) load of the mask tile through the staging buffer
@@ -413,11 +538,7 @@ __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int w
         if (rw >= j.M || col >= j.N) continue;
         const float4 x = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cg);
         const long long off = static_cast<long long>(rw) * j.ldd + col;
-        if (j.mode == E_OPT) {
-          const float g[4] = {x.x, x.y, x.z, x.w};
-          const int nn = j.N - col < 4 ? j.N - col : 4;
-          opt_apply(a, (reinterpret_cast<float*>(j.d) - a.master) + off, nn, g, j.bc1, j.bc2);
-        } else if (j.mode == E_F32) {
+        if (j.mode == E_F32) {
           float* d = reinterpret_cast<float*>(j.d) + off;
           if (col + 3 < j.N) *reinterpret_cast<float4*>(d) = x;
           else {
@@ -434,21 +555,6 @@ __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int w
         if (nc + lane < j.N) atomicAdd(j.colsum + nc + lane, tot);
       }
       __syncwarp();
-    }
-    if (j.dsm) {
-      // ... and push it into K-block `dsm_kb` of the fwd2 A-operand tile of all four CTAs of the
-      // cluster with the bulk-copy engine (smem -> distributed smem); every copy completes
-      // 16 KB of the transaction the destination's mbarrier was armed with at step start, so
-      // the chain phase needs neither a grid barrier nor a TMA reload of h.
-      ptx::fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) {
-        const uint32_t src = ptx::smem_u32(smem + kOffHQ4);
-        const uint32_t dst = ptx::smem_u32(smem + kOffH4 + j.dsm_kb * 16384);
-        const uint32_t bar = ptx::smem_u32(j.dsm_bar);
-#pragma unroll
-        for (uint32_t rk = 0; rk < 4; ++rk) dsm_bulk_copy(dst, src, 16384u, bar, rk);
-      }
     }
   } else {
     // softmax cross-entropy over the N (<= 64) logits of each row
@@ -514,53 +620,60 @@ __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int w
     }
   }
   ptx::tc_fence_before_sync();
+  if (j.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) j.dbg[j.dbg_slot + 1] = globaltimer_ns();
 }
 
 // ---------------------------------------------------------------- fused chain of one 128-row tile
-//   fwd1  acc[128 x 256] = x W1^T            (TMA ring, 13 K-blocks)            TMEM cols [0,256)
+//   fwd1  acc[128 x 256] = x W1^T            (plan 1 only: TMA ring, 13 K-blocks)  TMEM cols [0,256)
 //   E1    h = relu(acc + b1) -> bf16 -> smem (128B-swizzled K-major = fwd2's A operand) + global
+//         (plan 3: h was produced by P1 and arrives by TMA -- bf16, or e4m3 + scale chunks)
 //   fwd2  logits[128 x 64] = h W2^T          (A, B from smem)                    TMEM cols [256,320)
 //   E2    softmax-xent per row (one thread owns a row) -> dlogits -> smem (dh's A operand) + global
-//   dh    acc[128 x 256] = dlogits W2        (B = W2 MN-major)                   TMEM cols [0,256)
+//   dh    acc[128 x 64 slice] = dlogits W2   (B = W2 MN-major)                   TMEM cols [0,64)
 //   E3    dh = acc * relu'(h) -> bf16 global, db1
-// h never makes the global -> TMA round trip and the three GEMMs cost one grid barrier, not three.
-__device__ __forceinline__ void st_sw128(uint8_t* tile, int r, int chunk, uint4 v) {
-  *reinterpret_cast<uint4*>(tile + r * 128 + ((chunk ^ (r & 7)) << 4)) = v;
-}
-
-__device__ __forceinline__ void chain_produce(const Maps& maps, const Args& a, uint8_t* smem,
+// logits / dlogits never make the global -> TMA round trip; the three GEMMs cost one grid barrier.
+template <bool FP8>
+__device__ __forceinline__ void chain_produce(const Maps& maps, const Args& a, uint8_t* smem, uint8_t* sf_smem,
                                               const ChainBars& cb, CPipe& cp, int r0, int m0, int mode,
-                                              int slice, const ChainLay& L) {
+                                              int slice) {
   const uint32_t par = cp.n & 1;
   const int row0 = r0 + m0;
   const bool f1 = mode == 1;
-  if (mode == 4) {
-    // cluster plan: h arrives over DSMEM, W2 was prefetched at step start; only this CTA's
-    // 8 KB slice of W2^T is left to fetch (into ring memory that is dead by now)
-    if (ptx::elect_one()) {
-      ptx::mbar_expect_tx(cb.w2mn, 8192);
-      ptx::tma_load_3d(smem + L.w2mn, &maps.w2_mn, cb.w2mn, slice * 64, 0, 0);
-    }
-    __syncwarp();
-    ++cp.n;
-    return;
-  }
   if (!f1) {
     // h was produced by P1: TMA drops its 128 x 256 tile straight into the swizzled A-operand
     // slots; both W2 forms can be fetched at once (no fwd1 stages to alias).  This CTA computes
     // only hidden columns [64*slice, 64*slice+64) of dh: one 8 KB chunk of W2^T.
     if (ptx::elect_one()) {
-      ptx::mbar_expect_tx(cb.w2k, 32768);
-      ptx::mbar_expect_tx(&cb.full[0], 65536);
-      ptx::mbar_expect_tx(cb.w2mn, 8192);
-      // in the order the chain consumes them: h and W2 (fwd2) first, W2^T (dh) last
+      if (FP8) {
+        // e4m3: two K-blocks of 128 hidden units each, plus their scale chunks
+        ptx::mbar_expect_tx(cb.w2k, 2 * 8192 + 2 * kSfChunk);
+        ptx::mbar_expect_tx(&cb.full[0], 2 * 16384 + 2 * kSfChunk);
+        ptx::mbar_expect_tx(cb.w2mn, 8192);
 #pragma unroll
-      for (int kb = 0; kb < 4; ++kb)
-        ptx::tma_load_3d(smem + L.h + kb * 16384, &maps.h_k, &cb.full[0], kb * 64, m0, 0);
+        for (int kb = 0; kb < 2; ++kb) {
+          ptx::tma_load_3d(smem + kOffH + kb * 16384, &maps.hq_k, &cb.full[0], kb * 128, m0, 0);
+          epi::bulk_g2s(sf_smem + kb * kSfChunk,
+                        a.h_sf + (static_cast<long long>(m0 >> 7) * a.ql.kb2 + kb) * kSfChunk, kSfChunk, &cb.full[0]);
+        }
 #pragma unroll
-      for (int kb = 0; kb < 4; ++kb)
-        ptx::tma_load_3d(smem + L.w2k + kb * 8192, &maps.w2_k, cb.w2k, kb * 64, 0, 0);
-      ptx::tma_load_3d(smem + L.w2mn, &maps.w2_mn, cb.w2mn, slice * 64, 0, 0);
+        for (int kb = 0; kb < 2; ++kb) {
+          ptx::tma_load_3d(smem + kOffW2K + kb * 8192, &maps.w2q_k, cb.w2k, kb * 128, 0, 0);
+          epi::bulk_g2s(sf_smem + (2 + kb) * kSfChunk, a.work_q + a.ql.w2sf + kb * kSfChunk, kSfChunk, cb.w2k);
+        }
+        ptx::tma_load_3d(smem + kOffW2MN, &maps.w2_mn, cb.w2mn, slice * 64, 0, 0);
+      } else {
+        ptx::mbar_expect_tx(cb.w2k, 32768);
+        ptx::mbar_expect_tx(&cb.full[0], 65536);
+        ptx::mbar_expect_tx(cb.w2mn, 8192);
+        // in the order the chain consumes them: h and W2 (fwd2) first, W2^T (dh) last
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+          ptx::tma_load_3d(smem + kOffH + kb * 16384, &maps.h_k, &cb.full[0], kb * 64, m0, 0);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+          ptx::tma_load_3d(smem + kOffW2K + kb * 8192, &maps.w2_k, cb.w2k, kb * 64, 0, 0);
+        ptx::tma_load_3d(smem + kOffW2MN, &maps.w2_mn, cb.w2mn, slice * 64, 0, 0);
+      }
     }
     __syncwarp();
     ++cp.n;
@@ -597,8 +710,9 @@ __device__ __forceinline__ void chain_produce(const Maps& maps, const Args& a, u
   ++cp.n;
 }
 
-__device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, const ChainBars& cb,
-                                          uint32_t tmem_base, CPipe& cp, int mode, const ChainLay& L) {
+template <bool FP8>
+__device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, uint8_t* sf_smem, const ChainBars& cb,
+                                          uint32_t tmem_base, CPipe& cp, int mode) {
   const bool f1 = mode == 1;
   const uint32_t par = cp.n & 1;
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -628,21 +742,35 @@ __device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, const Ch
   }
   // fwd2: 128 x 64 x 256, A = h (smem: written by the epilogue warps, or by TMA), B = W2 K-major
   ptx::mbar_wait(cb.w2k, par);
-  // h tile: written by this CTA's epilogue warps (1), by TMA (3), or by the cluster over DSMEM
-  // before the cluster barrier every thread of this CTA has already passed (4)
   ptx::mbar_wait(f1 ? cb.h_ready : &cb.full[0], par);
   ptx::tc_fence_after_sync();
   if (ptx::elect_one()) {
-    const uint32_t id2 = ptx::make_idesc(1u, 0u, 0u, kBM, 64);
-    const uint32_t lo_a0 = (base_lo + (static_cast<uint32_t>(L.h) >> 4)) | (1u << 16);
-    const uint32_t lo_b0 = (base_lo + (static_cast<uint32_t>(L.w2k) >> 4)) | (1u << 16);
+    const uint32_t lo_a0 = (base_lo + (static_cast<uint32_t>(kOffH) >> 4)) | (1u << 16);
+    const uint32_t lo_b0 = (base_lo + (static_cast<uint32_t>(kOffW2K) >> 4)) | (1u << 16);
+    if (FP8) {
+      const uint32_t idq = epi::make_idesc_mx8(kBM, 64);
+      const uint32_t tsfa = tmem_base + kTmemSfa, tsfb = tmem_base + kTmemSfb;
+      const uint32_t sfs = ptx::smem_u32(sf_smem);
 #pragma unroll
-    for (uint32_t kb = 0; kb < 4; ++kb)
+      for (uint32_t kb = 0; kb < 2; ++kb) {
+        epi::utccp_32x128b_warpx4(tsfa, epi::sf_desc(sfs + kb * kSfChunk));
+        epi::utccp_32x128b_warpx4(tsfb, epi::sf_desc(sfs + (2 + kb) * kSfChunk));
 #pragma unroll
-      for (uint32_t k = 0; k < 4; ++k)
-        ptx::umma_f16(tmem_base + 256, (static_cast<uint64_t>(hi) << 32) | (lo_a0 + kb * (16384u >> 4) + k * 2u),
-                      (static_cast<uint64_t>(hi) << 32) | (lo_b0 + kb * (8192u >> 4) + k * 2u), id2,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+        for (uint32_t k = 0; k < 4; ++k)
+          epi::umma_mx8(tmem_base + 256, (static_cast<uint64_t>(hi) << 32) | (lo_a0 + kb * (16384u >> 4) + k * 2u),
+                        (static_cast<uint64_t>(hi) << 32) | (lo_b0 + kb * (8192u >> 4) + k * 2u),
+                        epi::idesc_mx8_k(idq, k), (kb > 0 || k > 0) ? 1u : 0u, tsfa, tsfb);
+      }
+    } else {
+      const uint32_t id2 = ptx::make_idesc(1u, 0u, 0u, kBM, 64);
+#pragma unroll
+      for (uint32_t kb = 0; kb < 4; ++kb)
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k)
+          ptx::umma_f16(tmem_base + 256, (static_cast<uint64_t>(hi) << 32) | (lo_a0 + kb * (16384u >> 4) + k * 2u),
+                        (static_cast<uint64_t>(hi) << 32) | (lo_b0 + kb * (8192u >> 4) + k * 2u), id2,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+    }
     ptx::umma_commit(cb.acc_l);
   }
   __syncwarp();
@@ -652,8 +780,8 @@ __device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, const Ch
   ptx::tc_fence_after_sync();
   if (ptx::elect_one()) {
     const uint32_t id3 = ptx::make_idesc(1u, 0u, 1u, kBM, f1 ? 256 : 64);   // !f1: one 64-column slice
-    const uint32_t lo_a0 = (base_lo + (static_cast<uint32_t>(L.dl) >> 4)) | (1u << 16);
-    const uint32_t lo_b0 = (base_lo + (static_cast<uint32_t>(L.w2mn) >> 4)) | ((8192u >> 4) << 16);
+    const uint32_t lo_a0 = (base_lo + (static_cast<uint32_t>(kOffDL) >> 4)) | (1u << 16);
+    const uint32_t lo_b0 = (base_lo + (static_cast<uint32_t>(kOffW2MN) >> 4)) | ((8192u >> 4) << 16);
 #pragma unroll
     for (uint32_t k = 0; k < 4; ++k)
       ptx::umma_f16(tmem_base, (static_cast<uint64_t>(hi) << 32) | (lo_a0 + k * 2u),
@@ -664,18 +792,15 @@ __device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, const Ch
   ++cp.n;
 }
 
+template <bool FP8>
 __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, const ChainBars& cb,
                                                uint32_t tmem_base, int warp, int lane, float* stage_base,
                                                float* sb, CPipe& cp, int m0, int r0, int mode, int slice,
-                                               const ChainLay& L, unsigned long long* dbg) {
+                                               unsigned long long* dbg) {
   const bool f1 = mode == 1;
   const uint32_t par = cp.n & 1;
   auto stampc = [&](int slot) {
-    if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) {
-      unsigned long long tns;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
-      dbg[slot] = tns;
-    }
+    if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) dbg[slot] = globaltimer_ns();
   };
   const int q = warp & 3;
   const int rl = q * 32 + lane;        // row inside the tile == TMEM lane
@@ -697,62 +822,80 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
   uint32_t mk[2] = {0u, 0u};     // !f1: relu mask of this CTA's 64 hidden columns
   if (!f1) {
     // h tile came in by TMA: only the relu mask is needed (read back through the swizzle)
-    ptx::mbar_wait(&cb.full[0], par);   // plan 3: the TMA of the h tile; plan 4: the cluster's pushes
-    const uint8_t* hs = smem + L.h;
-#pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      const int c = 2 * slice + cc;
-      uint32_t m = 0;
+    ptx::mbar_wait(&cb.full[0], par);
+    const uint8_t* hs = smem + kOffH;
+    if (FP8) {
+      // e4m3: K-block (slice / 2) holds hidden units [128 * (slice / 2), +128), one byte each
+      const uint8_t* tile = hs + (slice >> 1) * 16384;
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
-        const int chunk = (c & 1) * 4 + jj;
-        const uint4 u = *reinterpret_cast<const uint4*>(hs + (c >> 1) * 16384 + rl * 128 + ((chunk ^ (rl & 7)) << 4));
+        const uint4 u = epi::ld_sw128(tile, rl, (slice & 1) * 4 + jj);
         const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+        uint32_t m = 0;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          // bf16 > 0  <=>  sign clear and not zero
-          m |= (((wds[e] & 0xFFFFu) != 0u && (wds[e] & 0x8000u) == 0u) ? 1u : 0u) << (jj * 8 + e * 2);
-          m |= (((wds[e] >> 16) != 0u && (wds[e] & 0x80000000u) == 0u) ? 1u : 0u) << (jj * 8 + e * 2 + 1);
-        }
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const uint32_t byte = (wds[e] >> (8 * b)) & 0xFFu;   // e4m3 > 0  <=>  sign clear, not zero
+            m |= ((byte != 0u && (byte & 0x80u) == 0u) ? 1u : 0u) << (e * 4 + b);
+          }
+        mk[jj >> 1] |= m << ((jj & 1) * 16);
       }
-      mk[cc] = m;
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * slice + cc;
+        uint32_t m = 0;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint4 u = epi::ld_sw128(hs + (c >> 1) * 16384, rl, (c & 1) * 4 + jj);
+          const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            // bf16 > 0  <=>  sign clear and not zero
+            m |= (((wds[e] & 0xFFFFu) != 0u && (wds[e] & 0x8000u) == 0u) ? 1u : 0u) << (jj * 8 + e * 2);
+            m |= (((wds[e] >> 16) != 0u && (wds[e] & 0x80000000u) == 0u) ? 1u : 0u) << (jj * 8 + e * 2 + 1);
+          }
+        }
+        mk[cc] = m;
+      }
     }
     stampc(6);
   } else {
-  ptx::mbar_wait(cb.acc_h, par);
-  ptx::tc_fence_after_sync();
-  stampc(6);
-  {
-    uint8_t* hs = smem + kOffH;
-    __nv_bfloat16* hg = a.h + static_cast<long long>(row) * a.hidden;
+    ptx::mbar_wait(cb.acc_h, par);
+    ptx::tc_fence_after_sync();
+    stampc(6);
+    {
+      uint8_t* hs = smem + kOffH;
+      __nv_bfloat16* hg = a.h + static_cast<long long>(row) * a.hidden;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
-      ptx::tmem_ld_wait();
-      uint32_t pk[16];
-      uint32_t m = 0;
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        uint32_t pk[16];
+        uint32_t m = 0;
 #pragma unroll
-      for (int k = 0; k < 32; k += 2) {
-        const float v0 = fmaxf(__uint_as_float(r[k]) + sb[c * 32 + k], 0.f);
-        const float v1 = fmaxf(__uint_as_float(r[k + 1]) + sb[c * 32 + k + 1], 0.f);
-        m |= (v0 > 0.f ? 1u : 0u) << k;
-        m |= (v1 > 0.f ? 1u : 0u) << (k + 1);
-        pk[k >> 1] = pack2(v0, v1);
-      }
-      mask[c] = m;
-      uint8_t* tile = hs + (c >> 1) * 16384;
+        for (int k = 0; k < 32; k += 2) {
+          const float v0 = fmaxf(__uint_as_float(r[k]) + sb[c * 32 + k], 0.f);
+          const float v1 = fmaxf(__uint_as_float(r[k + 1]) + sb[c * 32 + k + 1], 0.f);
+          m |= (v0 > 0.f ? 1u : 0u) << k;
+          m |= (v1 > 0.f ? 1u : 0u) << (k + 1);
+          pk[k >> 1] = pack2(v0, v1);
+        }
+        mask[c] = m;
+        uint8_t* tile = hs + (c >> 1) * 16384;
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const uint4 v = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
-        st_sw128(tile, rl, (c & 1) * 4 + jj, v);
-        if (row_ok) reinterpret_cast<uint4*>(hg + c * 32)[jj] = v;
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint4 v = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+          st_sw128(tile, rl, (c & 1) * 4 + jj, v);
+          if (row_ok) reinterpret_cast<uint4*>(hg + c * 32)[jj] = v;
+        }
       }
     }
-  }
-  ptx::fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor core
-  ptx::tc_fence_before_sync();
-  ptx::mbar_arrive(cb.h_ready);
+    ptx::fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor core
+    ptx::tc_fence_before_sync();
+    ptx::mbar_arrive(cb.h_ready);
   }
   stampc(7);
 
@@ -804,7 +947,7 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
     const float gs = 1.f / static_cast<float>(a.B);
     // the 4 slice-CTAs of an M-tile all need dlogits in smem, but the bookkeeping is done once:
     const bool do_colsum = f1 || slice == 1, do_global = f1 || slice == 2, do_loss = f1 || slice == 3;
-    uint8_t* dls = smem + L.dl;
+    uint8_t* dls = smem + kOffDL;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       float v[32];
@@ -840,7 +983,7 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int rt = q * 32 + it * 4 + (lane >> 3), ch = lane & 7;
-        const uint4 u = *reinterpret_cast<const uint4*>(dls + rt * 128 + ((ch ^ (rt & 7)) << 4));
+        const uint4 u = epi::ld_sw128(dls, rt, ch);
         if (m0 + rt < a.B && ch * 8 < a.ncp)
           *reinterpret_cast<uint4*>(a.dlogits + static_cast<long long>(m0 + rt) * a.ncp + ch * 8) = u;
       }
@@ -860,10 +1003,10 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
   ptx::tc_fence_after_sync();
   stampc(10);
   {
-    // The h tile in [0, 64 KB) is dead (fwd2 retired before acc_l, the mask is in registers): it
-    // becomes a 128 x 512-byte bf16 staging tile so that dh leaves the SM one whole row (4 full
-    // lines) per store instruction instead of 32 scattered 16-byte pieces.
-    uint8_t* ds = smem + L.h;
+    // The h tile at kOffH is dead (fwd2 retired before acc_l, the mask is in registers): it
+    // becomes a bf16 staging tile so that dh leaves the SM in whole rows per store instruction
+    // instead of 32 scattered 16-byte pieces.
+    uint8_t* ds = smem + kOffH;
     if (!f1) {
       // 64-column slice: 128-byte staging rows, 4 whole rows per store instruction
 #pragma unroll
@@ -888,37 +1031,37 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int rt = q * 32 + it * 4 + (lane >> 3), ch = lane & 7;
-        const uint4 u = *reinterpret_cast<const uint4*>(ds + rt * 128 + ((ch ^ (rt & 7)) << 4));
+        const uint4 u = epi::ld_sw128(ds, rt, ch);
         if (m0 + rt < a.B)
           *reinterpret_cast<uint4*>(a.dh + static_cast<long long>(m0 + rt) * a.hidden + slice * 64 + ch * 8) = u;
       }
     } else {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
-      ptx::tmem_ld_wait();
-      float v[32];
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        float v[32];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) v[k] = ((mask[c] >> k) & 1u) ? __uint_as_float(r[k]) : 0.f;
+        for (int k = 0; k < 32; ++k) v[k] = ((mask[c] >> k) & 1u) ? __uint_as_float(r[k]) : 0.f;
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj)
-        *reinterpret_cast<uint4*>(ds + rl * 512 + (((c * 4 + jj) ^ (rl & 7)) << 4)) =
-            make_uint4(pack2(v[8 * jj], v[8 * jj + 1]), pack2(v[8 * jj + 2], v[8 * jj + 3]),
-                       pack2(v[8 * jj + 4], v[8 * jj + 5]), pack2(v[8 * jj + 6], v[8 * jj + 7]));
-      stage_put(stg, lane, v);
-      __syncwarp();
-      const float tot = col_sum32(stg, lane, 32);
-      atomicAdd(a.gb1 + c * 32 + lane, tot);
-      __syncwarp();
-    }
+        for (int jj = 0; jj < 4; ++jj)
+          *reinterpret_cast<uint4*>(ds + rl * 512 + (((c * 4 + jj) ^ (rl & 7)) << 4)) =
+              make_uint4(pack2(v[8 * jj], v[8 * jj + 1]), pack2(v[8 * jj + 2], v[8 * jj + 3]),
+                         pack2(v[8 * jj + 4], v[8 * jj + 5]), pack2(v[8 * jj + 6], v[8 * jj + 7]));
+        stage_put(stg, lane, v);
+        __syncwarp();
+        const float tot = col_sum32(stg, lane, 32);
+        atomicAdd(a.gb1 + c * 32 + lane, tot);
+        __syncwarp();
+      }
 #pragma unroll 8
-    for (int rr = 0; rr < 32; ++rr) {
-      const int rt = q * 32 + rr;
-      if (m0 + rt >= a.B) break;
-      const uint4 u = *reinterpret_cast<const uint4*>(ds + rt * 512 + ((lane ^ (rt & 7)) << 4));
-      *reinterpret_cast<uint4*>(a.dh + static_cast<long long>(m0 + rt) * a.hidden + lane * 8) = u;
-    }
+      for (int rr = 0; rr < 32; ++rr) {
+        const int rt = q * 32 + rr;
+        if (m0 + rt >= a.B) break;
+        const uint4 u = *reinterpret_cast<const uint4*>(ds + rt * 512 + ((lane ^ (rt & 7)) << 4));
+        *reinterpret_cast<uint4*>(a.dh + static_cast<long long>(m0 + rt) * a.hidden + lane * 8) = u;
+      }
     }
   }
   ptx::tc_fence_before_sync();
@@ -926,17 +1069,19 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
   ++cp.n;
 }
 
-// Device-wide barrier between phases.  All kGrid CTAs are co-resident (one per SM), the counter
+// Device-wide barrier between phases.  All CTAs are co-resident (one per SM), the counter
 // only grows.  Writers: bar.sync orders every thread's writes before thread 0's gpu-scope
 // fence (cumulative release); readers: acquire, then a proxy fence so the next phase's TMA
-// (async proxy) observes what other CTAs stored with ordinary instructions.
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch) {
+// (async proxy) observes what other CTAs stored with ordinary instructions.  `sys`: the writes
+// of this phase are about to be published to peer GPUs (last step's upload) -- fence at system
+// scope instead.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch, bool sys = false) {
   ++epoch;
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (threadIdx.x == 0) {
     ptx::fence_proxy_async_all();
-    __threadfence();
+    if (sys) __threadfence_system(); else __threadfence();
     atomicAdd(counter, 1u);
     const unsigned int target = epoch * gridDim.x;
     unsigned long long spins = 0;
@@ -952,18 +1097,20 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   ptx::tc_fence_after_sync();
 }
 
+template <bool FP8>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kTileBytes);
+  uint8_t* sf_smem = smem + kTileBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kTileBytes + kSfBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* accum_bar = empty_bar + kStages;
   uint64_t* cbar = accum_bar + 1;      // chain barriers: full[3] empty[3] + 7 single-use
   ChainBars cb{cbar, cbar + kCStages, cbar + 6, cbar + 7, cbar + 8, cbar + 9, cbar + 10, cbar + 11, cbar + 12};
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cbar + 13);
-  float* stage_base = reinterpret_cast<float*>(smem + kTileBytes + kBarBytes);
+  float* stage_base = reinterpret_cast<float*>(smem + kTileBytes + kSfBytes + kBarBytes);
   float* sbias = stage_base + 4 * 32 * kStgLd;
 
   ptx::pdl_launch_dependents();
@@ -1005,28 +1152,27 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
   const int nt_d = (D + kBN - 1) / kBN;                 // N-tiles over in_dim
   const int mt_h = (H + kBM - 1) / kBM;                 // M-tiles over hidden (dW1)
   const int kb_d = (D + 63) / 64, kb_h = (H + 63) / 64, kb_b = (B + 63) / 64, kb_c = (C + 63) / 64;
+  const int p1_bn = FP8 ? a.p1_bn : kBN;                // fwd1 tile width
+  const int p1_nt = (H + p1_bn - 1) / p1_bn;
+  const int p1_tiles = mt_b * p1_nt;
 
-  const uint32_t ns = a.chain == 4 ? 4u : static_cast<uint32_t>(kStages);
   auto run = [&](const Job& j) {
-    if (warp == 0) produce_tile(j, smem, full_bar, empty_bar, pp, ns);
-    else if (warp == 1) mma_tile(j, smem, full_bar, empty_bar, accum_bar, tmem_base, pp, ns);
-    else epilogue_tile(j, a, warp, lane, accum_bar, tmem_base, stage_base, sbias, pp, smem);
+    if (warp == 0) produce_tile<FP8>(j, smem, sf_smem, full_bar, empty_bar, pp);
+    else if (warp == 1) mma_tile<FP8>(j, smem, sf_smem, full_bar, empty_bar, accum_bar, tmem_base, pp);
+    else epilogue_tile<FP8>(j, a, warp, lane, accum_bar, tmem_base, stage_base, sbias, pp);
   };
 
   // Phase plan of one step (a.chain, a.epiopt pick the variant; all are numerically equivalent):
   //   chain 1:  [fwd1 -> xent -> dh chained per M-tile]                       | B
-  //   chain 3:  P1 fwd1 (16 tiles) | [fwd2 -> xent -> dh chained per M-tile]  | B
+  //   chain 3:  P1 fwd1 | [fwd2 -> xent -> dh chained per M-tile]             | B
   //   chain 0:  P1 | P2 xent | P3 dh                                          | B
   //   B = dW1 || dW2 (+ SGD/Adam in the epilogue and a bias CTA when epiopt, else a flat P5)
   auto stamp = [&](int step, int slot) {
-    if (a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) {
-      unsigned long long tns;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
-      a.dbg[step * 16 + slot] = tns;
-    }
+    if (a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) a.dbg[step * 32 + slot] = globaltimer_ns();
   };
   for (int step = 0; step < a.steps; ++step) {
     const int r0 = step * B;
+    const bool last = step == a.steps - 1;
     float bc1 = 1.f, bc2 = 1.f;
     if (a.adam) {
       const int tt = (a.step_base ? *a.step_base : 0) + step + 1;
@@ -1035,23 +1181,9 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
     }
     const bool eo = a.epiopt != 0;
     stamp(step, 0);
-    const ChainLay L = a.chain == 4 ? ChainLay{kOffH4, kOffW2K4, kOffW2MN4, kOffDL4}
-                                    : ChainLay{kOffH, kOffW2K, kOffW2MN, kOffDL};
-    const bool in_chain_cta = a.chain >= 3 && t < mt_b * 4;
-    if (a.chain == 4 && in_chain_cta && warp == 0) {
-      // cluster plan: W2 (fwd2's B operand) is stable since the last barrier -- fetch it under P1
-      if (ptx::elect_one()) {
-        ptx::mbar_expect_tx(&cb.full[0], 65536);   // 4 x 16 KB of h, pushed by the cluster's fwd1 CTAs
-        ptx::mbar_expect_tx(cb.w2k, 32768);
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb)
-          ptx::tma_load_3d(smem + L.w2k + kb * 8192, &maps.w2_k, cb.w2k, kb * 64, 0, 0);
-      }
-      __syncwarp();
-    }
     if (a.chain != 1) {
       // ---- P1: h = relu(x W1^T + b1)
-      if (t < mt_b * nt_h) {
+      if (t < p1_tiles) {
         if (a.x_ready != nullptr && warp == 0 && !x_all_ready) {
           // input pipeline: this step's rows are converted by the side-branch kernel as soon as
           // their H2D copy lands; only the TMA producer has to wait (phase B reads them later).
@@ -1066,42 +1198,49 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
             while (!all) {
               asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.x_ready + step) : "memory");
               if (static_cast<int>(v - want) >= 0) break;
-              if (++spins > (1ull << 24)) __trap();
+              if (++spins > (1ull << 28)) __trap();   // the input kernel gives up (error word) long before this
+              __nanosleep(32);
             }
           }
           x_all_ready = __shfl_sync(0xffffffffu, all, 0) != 0;
           ptx::fence_proxy_async_all();   // their generic stores -> this warp's TMA (async proxy) loads
         }
         Job j{};
-        j.ta = &maps.x_k; j.tb = &maps.w1_k; j.a_mn = 0; j.b_mn = 0;
-        j.m0 = (t / nt_h) * kBM; j.n0 = (t % nt_h) * kBN; j.M = B; j.N = H;
-        j.a_c0 = 0; j.a_c1 = r0 + j.m0; j.b_c0 = 0; j.b_c1 = j.n0; j.n_kb = kb_d;
-        j.mode = E_BIAS_RELU_BF16; j.d = a.h; j.ldd = H; j.bias = a.b1;
-        j.dsm = a.chain == 4 ? 1 : 0; j.dsm_kb = t % nt_h; j.dsm_bar = &cb.full[0];
+        j.mode = E_BIAS_RELU_BF16; j.d = a.h; j.ldd = H; j.bias = a.b1; j.M = B; j.N = H;
+        j.dbg = a.dbg != nullptr ? a.dbg + step * 32 : nullptr; j.dbg_slot = 16;
+        j.m0 = (t / p1_nt) * kBM; j.n0 = (t % p1_nt) * p1_bn; j.bn = p1_bn;
+        if (FP8) {
+          // e4m3 x tile against a p1_bn-row tile of e4m3 W1; scale chunks are per 128-row block,
+          // the W1 tile's rows start at TMEM column (row % 128) / 32 of the 4-column chunk
+          const int kbq = a.ql.kb1;
+          const int xr = r0 + j.m0;
+          j.fp8 = 1; j.n_kb = kbq;
+          j.ta = &maps.xq_k; j.tb = &maps.w1q_k;
+          j.a_c0 = 0; j.a_c1 = xr; j.b_c0 = 0; j.b_c1 = j.n0;
+          j.sfa = a.x_sf + static_cast<long long>(xr >> 7) * kbq * kSfChunk;
+          j.sfa_col = 0;
+          j.sfb = a.work_q + a.ql.w1sf + static_cast<long long>(j.n0 >> 7) * kbq * kSfChunk;
+          j.sfb_col = static_cast<uint32_t>((j.n0 & 127) >> 5);
+        } else {
+          j.ta = &maps.x_k; j.tb = &maps.w1_k; j.a_mn = 0; j.b_mn = 0;
+          j.a_c0 = 0; j.a_c1 = r0 + j.m0; j.b_c0 = 0; j.b_c1 = j.n0; j.n_kb = kb_d;
+        }
         run(j);
       }
-      if (a.chain == 4) {
-        // The four fwd1 CTAs of an M-tile are one thread-block cluster and are exactly the four
-        // chain CTAs of that M-tile: no device-wide barrier -- each chain CTA just waits on its
-        // own mbarrier for the four 16 KB pushes.  The CTA-wide barrier only makes sure this
-        // CTA's fwd1 MMAs have retired before the chain reuses ring memory.
-        if (in_chain_cta) __syncthreads();
-      } else {
-        grid_barrier(a.barrier, bar_epoch);
-      }
+      grid_barrier(a.barrier, bar_epoch);
       stamp(step, 1);
     }
     if (a.chain != 0) {
       // ---- chained tail (or whole) of the forward/backward pass per 128-row tile
-      // chain 1: one CTA per M-tile; chain 3/4: four CTAs per M-tile, each redoes fwd2 + xent
+      // chain 1: one CTA per M-tile; chain 3: four CTAs per M-tile, each redoes fwd2 + xent
       // (cheap) and owns a 64-column slice of dh, so the long dh epilogue runs 4-wide
       const int xs = a.chain == 1 ? 1 : 4;
       if (t < mt_b * xs) {
         const int m0 = (t / xs) * kBM, slice = t % xs;
-        if (warp == 0) chain_produce(maps, a, smem, cb, cp, r0, m0, a.chain, slice, L);
-        else if (warp == 1) chain_mma(a, smem, cb, tmem_base, cp, a.chain, L);
-        else chain_epilogue(a, smem, cb, tmem_base, warp, lane, stage_base, sbias, cp, m0, r0, a.chain,
-                            slice, L, a.dbg != nullptr ? a.dbg + step * 16 : nullptr);
+        if (warp == 0) chain_produce<FP8>(maps, a, smem, sf_smem, cb, cp, r0, m0, a.chain, slice);
+        else if (warp == 1) chain_mma<FP8>(a, smem, sf_smem, cb, tmem_base, cp, a.chain);
+        else chain_epilogue<FP8>(a, smem, cb, tmem_base, warp, lane, stage_base, sbias, cp, m0, r0, a.chain,
+                                 slice, a.dbg != nullptr ? a.dbg + step * 32 : nullptr);
       }
       grid_barrier(a.barrier, bar_epoch);
       stamp(step, 2);
@@ -1136,7 +1275,9 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
       j.m0 = (t / nt_d) * kBM; j.n0 = (t % nt_d) * kBN; j.M = H; j.N = D;
       j.a_c0 = j.m0; j.a_c1 = 0; j.b_c0 = j.n0; j.b_c1 = r0; j.n_kb = kb_b;
       j.mode = eo ? E_OPT : E_F32; j.d = eo ? a.master + (a.gw1 - a.grad) : a.gw1; j.ldd = D;
-      j.bc1 = bc1; j.bc2 = bc2;
+      j.bc1 = bc1; j.bc2 = bc2; j.last = last ? 1 : 0;
+      j.dbg = a.dbg != nullptr ? a.dbg + step * 32 : nullptr; j.dbg_slot = 18;
+      j.q_off = a.ql.w1q; j.qsf_off = a.ql.w1sf; j.ldq = D; j.q_nkb = a.ql.kb1;
       run(j);
     } else if (t < mt_h * nt_d + nt_h) {
       const int u = t - mt_h * nt_d;
@@ -1145,19 +1286,32 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
       j.m0 = 0; j.n0 = u * kBN; j.M = C; j.N = H;
       j.a_c0 = 0; j.a_c1 = 0; j.b_c0 = j.n0; j.b_c1 = 0; j.n_kb = kb_b;
       j.mode = eo ? E_OPT : E_F32; j.d = eo ? a.master + (a.gw2 - a.grad) : a.gw2; j.ldd = H;
-      j.bc1 = bc1; j.bc2 = bc2;
+      j.bc1 = bc1; j.bc2 = bc2; j.last = last ? 1 : 0;
+      j.q_off = a.ql.w2q; j.qsf_off = a.ql.w2sf; j.ldq = H; j.q_nkb = a.ql.kb2;
       run(j);
     } else if (eo && t == mt_h * nt_d + nt_h) {
       // biases: their gradients were accumulated by column sums earlier in the step; consume + re-zero
+      const bool up = last && a.has_fed;
+      UploadDst ud{};
+      if (up) ud = upload_dst<FP8>(a);
       for (int i = threadIdx.x; i < H + C; i += blockDim.x) {
         float* gp = i < H ? a.gb1 + i : a.gb2 + (i - H);
         const float g = __ldcg(gp);
         *gp = 0.f;
-        opt_apply(a, gp - a.grad, 1, &g, bc1, bc2);
+        float w[4];
+        const long long pi = gp - a.grad;
+        opt_apply(a, pi, 1, &g, bc1, bc2, w);
+        if (up) {
+          float wu = w[0];
+          if (ud.global != nullptr) { const float g0 = __ldcg(ud.global + pi); wu = g0 - ud.byz_scale * (wu - g0); }
+          ud.master[pi] = wu;
+          if (!FP8) ud.shadow[pi] = __float2bfloat16(wu);
+          else *reinterpret_cast<float*>(ud.blob + (i < H ? a.ql.b1 + 4 * i : a.ql.b2 + 4 * (i - H))) = wu;
+        }
       }
     }
     stamp(step, 3);
-    grid_barrier(a.barrier, bar_epoch);
+    grid_barrier(a.barrier, bar_epoch, last && a.has_fed);
     stamp(step, 4);
     if (eo) continue;   // the optimizer ran in the epilogues
     // ---- P5: optimizer over the flat buffer (all threads of all CTAs)
@@ -1167,7 +1321,8 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
       for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv; i += stride) {
         const float4 g4 = __ldcg(reinterpret_cast<const float4*>(a.grad) + i);
         const float g[4] = {g4.x, g4.y, g4.z, g4.w};
-        opt_apply(a, 4 * i, 4, g, bc1, bc2);
+        float w[4];
+        opt_apply(a, 4 * i, 4, g, bc1, bc2, w);
         reinterpret_cast<float4*>(a.grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
@@ -1175,186 +1330,31 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
     stamp(step, 5);
   }
 
-  __syncthreads();
-  if (warp == 1) {
-    ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  // ---- UploadLocalUpdate, second half: every CTA's upload stores were fenced at system scope
+  // before the last barrier; CTA 0 pushes the meta record into every replica's ledger page and
+  // raises FLAG_TRAINED on every peer (C:246-253).
+  if (a.has_fed && a.epiopt && blockIdx.x == 0) {
+    char* me = a.f.peers.base[a.f.rank];
+    const RoundState* st = heap_at<const RoundState>(me, a.f.lay.state_off);
+    RoundPlan* plan = heap_at<RoundPlan>(me, a.f.lay.plan_off);
+    const uint32_t epoch = st->epoch;
+    const uint32_t par = epoch & 1u;
+    if (threadIdx.x == 0) atomicMax(&plan->t_stamp[STAMP_UPLOAD_BEGIN], globaltimer_ns());
+    if (threadIdx.x < a.f.n_ranks) {
+      const int r = threadIdx.x;
+      UploadMeta* meta = heap_at<UploadMeta>(a.f.peers.base[r], a.f.lay.meta_off) + par * kMaxRanks + a.f.rank;
+      UploadMeta m;
+      m.n_samples = static_cast<uint32_t>(a.n_samples);
+      m.avg_cost = __ldcg(a.loss_sum) / static_cast<float>(a.n_loss_terms > 0 ? a.n_loss_terms : 1);
+      *meta = m;
+      __threadfence_system();
+      ptx::st_release_sys(heap_at<uint32_t>(a.f.peers.base[r], a.f.lay.flags_off) + FLAG_TRAINED + a.f.rank,
+                          epoch + 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMax(&plan->t_stamp[STAMP_UPLOAD_END], globaltimer_ns());
   }
-}
 
-// ---------------------------------------------------------------- committee validation chain
-// One CTA per (128 validation rows, candidate z): fwd1 -> relu -> fwd2 -> argmax == label, with
-// candidate z's weights addressed through device-resident tensor maps (local staging slots or a
-// peer GPU's upload buffer) selected by the round plan -- "QueryAllUpdates" + scoring
-// (reference C:299-311, M:226-247) without materialising logits or hidden activations.
-constexpr int kValSmem = kOffW2K + 32768 + kBarBytes + kBiasFloats * 4 + 1024;
-
-struct ValArgs {
-  int n_val, in_dim, n_classes;
-  const CUtensorMap* maps;               // table indexed by dyn{1,2}->map_index[z]
-  const GemmDynamic* dyn1; const GemmDynamic* dyn2;
-  const int32_t* labels; unsigned int* correct;
-  const int* pred;
-};
-
-__global__ void __launch_bounds__(kThreads, 1)
-mlp_val_kernel(const __grid_constant__ CUtensorMap tmX, const ValArgs v) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kOffW2K + 32768);
-  uint64_t* empty = full + kCStages;
-  uint64_t* w2k = empty + kCStages;
-  uint64_t* acc_h = w2k + 1;
-  uint64_t* h_ready = acc_h + 1;
-  uint64_t* acc_l = h_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_l + 1);
-  float* sb = reinterpret_cast<float*>(smem + kOffW2K + 32768 + kBarBytes);
-
-  ptx::pdl_launch_dependents();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int z = blockIdx.y, m0 = blockIdx.x * kBM;
-  if (warp == 0 && lane == 0) {
-    ptx::tma_prefetch_desc(&tmX);
-    for (int s = 0; s < kCStages; ++s) {
-      ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], 1);
-    }
-    ptx::mbar_init(w2k, 1); ptx::mbar_init(acc_h, 1); ptx::mbar_init(acc_l, 1);
-    ptx::mbar_init(h_ready, 128);
-    ptx::fence_mbar_init();
-  }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, kTmemCols);
-  ptx::tc_fence_before_sync();
-  __syncthreads();
-  ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-  ptx::pdl_wait();
-  const bool inactive = (v.pred != nullptr && *v.pred == 0) || z >= v.dyn1->active_batches;
-  if (inactive) {
-    if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
-    return;
-  }
-  const int kb_d = (v.in_dim + 63) / 64;
-  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-  const uint32_t base_lo = ptx::smem_u32(smem) >> 4;
-
-  if (warp == 0) {
-    if (v.dyn1->wait_flag[z] != nullptr) {   // candidate z's trainer has published its upload
-      if (lane == 0) ptx::wait_flag_ge(v.dyn1->wait_flag[z], v.dyn1->wait_value);
-      __syncwarp();
-    }
-    const CUtensorMap* m1 = v.maps + v.dyn1->map_index[z];
-    const CUtensorMap* m2 = v.maps + v.dyn2->map_index[z];
-    if (ptx::elect_one()) {
-      ptx::mbar_expect_tx(w2k, 32768);
-#pragma unroll
-      for (int kb = 0; kb < 4; ++kb) ptx::tma_load_3d(smem + kOffW2K + kb * 8192, m2, w2k, kb * 64, 0, 0);
-    }
-    __syncwarp();
-    for (int i = 0; i < kb_d; ++i) {
-      const int s = i % kCStages;
-      const uint32_t ph = (i / kCStages) & 1;
-      ptx::mbar_wait(&empty[s], ph ^ 1);
-      if (ptx::elect_one()) {
-        uint8_t* sa = smem + s * kCStage;
-        ptx::mbar_expect_tx(&full[s], kCStage);
-        ptx::tma_load_3d(sa, &tmX, &full[s], i * 64, m0, 0);
-        ptx::tma_load_3d(sa + kCA, m1, &full[s], i * 64, 0, 0);
-      }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    const uint32_t id1 = ptx::make_idesc(1u, 0u, 0u, kBM, 256);
-    for (int i = 0; i < kb_d; ++i) {
-      const int s = i % kCStages;
-      const uint32_t ph = (i / kCStages) & 1;
-      ptx::mbar_wait(&full[s], ph);
-      ptx::tc_fence_after_sync();
-      if (ptx::elect_one()) {
-        const uint32_t lo_a = (base_lo + static_cast<uint32_t>(s) * (kCStage >> 4)) | (1u << 16);
-        const uint32_t lo_b = lo_a + (kCA >> 4);
-#pragma unroll
-        for (uint32_t k = 0; k < 4; ++k)
-          ptx::umma_f16(tmem_base, (static_cast<uint64_t>(hi) << 32) | (lo_a + k * 2u),
-                        (static_cast<uint64_t>(hi) << 32) | (lo_b + k * 2u), id1, (i > 0 || k > 0) ? 1u : 0u);
-        ptx::umma_commit(&empty[s]);
-      }
-      __syncwarp();
-    }
-    if (ptx::elect_one()) ptx::umma_commit(acc_h);
-    __syncwarp();
-    ptx::mbar_wait(w2k, 0);
-    ptx::mbar_wait(h_ready, 0);
-    ptx::tc_fence_after_sync();
-    if (ptx::elect_one()) {
-      const uint32_t id2 = ptx::make_idesc(1u, 0u, 0u, kBM, 64);
-      const uint32_t lo_a0 = (base_lo + (kOffH >> 4)) | (1u << 16);
-      const uint32_t lo_b0 = (base_lo + (kOffW2K >> 4)) | (1u << 16);
-#pragma unroll
-      for (uint32_t kb = 0; kb < 4; ++kb)
-#pragma unroll
-        for (uint32_t k = 0; k < 4; ++k)
-          ptx::umma_f16(tmem_base + 256, (static_cast<uint64_t>(hi) << 32) | (lo_a0 + kb * (16384u >> 4) + k * 2u),
-                        (static_cast<uint64_t>(hi) << 32) | (lo_b0 + kb * (8192u >> 4) + k * 2u), id2,
-                        (kb > 0 || k > 0) ? 1u : 0u);
-      ptx::umma_commit(acc_l);
-    }
-    __syncwarp();
-  } else {
-    const int q = warp & 3, rl = q * 32 + lane, row = m0 + rl;
-    const bool row_ok = row < v.n_val;
-    const int C = v.n_classes;
-    {
-      const int et = threadIdx.x - 64;
-      const float* b1 = v.dyn1->bias[z];
-      const float* b2 = v.dyn2->bias[z];
-      for (int i = et; i < kChainH; i += 128) sb[i] = b1 != nullptr ? b1[i] : 0.f;
-      if (et < 64) sb[kChainH + et] = (b2 != nullptr && et < C) ? b2[et] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    ptx::mbar_wait(acc_h, 0);
-    ptx::tc_fence_after_sync();
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
-      ptx::tmem_ld_wait();
-      uint32_t pk[16];
-#pragma unroll
-      for (int k = 0; k < 32; k += 2)
-        pk[k >> 1] = pack2(fmaxf(__uint_as_float(r[k]) + sb[c * 32 + k], 0.f),
-                           fmaxf(__uint_as_float(r[k + 1]) + sb[c * 32 + k + 1], 0.f));
-      uint8_t* tile = smem + kOffH + (c >> 1) * 16384;
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj)
-        st_sw128(tile, rl, (c & 1) * 4 + jj, make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]));
-    }
-    ptx::fence_proxy_async_smem();
-    ptx::tc_fence_before_sync();
-    ptx::mbar_arrive(h_ready);
-    ptx::mbar_wait(acc_l, 0);
-    ptx::tc_fence_after_sync();
-    const int32_t label = row_ok ? v.labels[row] : -1;
-    float vmax = -INFINITY;
-    int amax = -1;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(taddr + 256 + c * 32, r);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const int n = c * 32 + k;
-        const float x = __uint_as_float(r[k]) + sb[kChainH + n];
-        if (n < C && x > vmax) { vmax = x; amax = n; }
-      }
-    }
-    const unsigned cnt = __popc(__ballot_sync(0xffffffffu, row_ok && amax == label));
-    if (lane == 0 && cnt) atomicAdd(v.correct + z, cnt);
-    ptx::tc_fence_before_sync();
-  }
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after_sync();
@@ -1364,37 +1364,58 @@ mlp_val_kernel(const __grid_constant__ CUtensorMap tmX, const ValArgs v) {
 
 }  // namespace
 
+Mx8MlpLayout mx8_mlp_layout(int in_dim, int hidden) {
+  Mx8MlpLayout l;
+  l.kb1 = (in_dim + 127) / 128;
+  l.kb2 = (hidden + 127) / 128;
+  const int rb1 = (hidden + 127) / 128;
+  int cur = 0;
+  auto take = [&](int bytes) { const int o = cur; cur += (bytes + 127) / 128 * 128; return o; };
+  l.w1q = take(hidden * in_dim);
+  l.w1sf = take(rb1 * l.kb1 * kSfChunk);
+  l.w2q = take(64 * hidden);
+  l.w2sf = take(l.kb2 * kSfChunk);
+  l.b1 = take(hidden * 4);
+  l.b2 = take(64 * 4);
+  l.total = cur;
+  return l;
+}
+
 cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
   bind_context_once();
   if (r.hidden % 8 || r.in_dim % 8 || r.n_params % 4 || r.batch % 8 || r.ncp % 8 || r.n_classes > 64)
     return cudaErrorInvalidValue;
   const int mt_b = (r.batch + kBM - 1) / kBM, nt_h = (r.hidden + kBN - 1) / kBN;
   const int nt_d = (r.in_dim + kBN - 1) / kBN, mt_h = (r.hidden + kBM - 1) / kBM;
-  // phase plan: r.plan / r.epiopt when >= 0, else BFLC_MLP_CHAIN = 0 | 1 | 3 | 4 and
+  // phase plan: r.plan / r.epiopt when >= 0, else BFLC_MLP_CHAIN = 0 | 1 | 3 and
   // BFLC_MLP_EPIOPT = 0 | 1 (see the kernel), else the defaults
   static const int chain_env0 = [] { const char* e = std::getenv("BFLC_MLP_CHAIN"); return e ? std::atoi(e) : kDefaultPlan; }();
   static const bool epiopt_env0 = [] { const char* e = std::getenv("BFLC_MLP_EPIOPT"); return !(e && e[0] == '0'); }();
   const int chain_env = r.plan >= 0 ? r.plan : chain_env0;
-  const bool epiopt_env = r.epiopt >= 0 ? r.epiopt != 0 : epiopt_env0;
+  const bool epiopt = r.epiopt >= 0 ? r.epiopt != 0 : epiopt_env0;
   const bool chain_ok = r.hidden == kChainH && r.ncp == 64 && r.n_classes <= 64;
-  // the cluster plan needs nt_h == 4 (one cluster of 4 CTAs per M-tile) and <= 8 M-tiles
-  // EXPERIMENTAL: measured +1.8 % only (the step is gated by the slowest cluster's tail, not by
-  // the barrier it removes) and its numerics check still fails -> opt-in for development only.
-  static const bool plan4_env = [] { const char* e = std::getenv("BFLC_MLP_EXPERIMENTAL"); return e && e[0] == '1'; }();
-  const bool cluster_ok = plan4_env && chain_ok && nt_h == 4 && mt_b * 4 <= kGrid;
-  const int chain = !chain_ok ? 0
-                    : chain_env == 0 ? 0 : chain_env == 1 ? 1 : (chain_env == 4 && cluster_ok) ? 4 : 3;
-  const int need = std::max(std::max(mt_b * nt_h, mt_h * nt_d + nt_h + 1), chain == 3 ? mt_b * 4 : 0);
+  const int chain = !chain_ok ? 0 : chain_env == 0 ? 0 : chain_env == 1 ? 1 : 3;
+  const bool fp8 = r.fp8;
+  if (fp8 && (chain != 3 || !epiopt || r.batch % 128 || r.in_dim % 16 || !r.x_q || !r.x_sf || !r.work_q ||
+              !r.h_q || !r.h_sf))
+    return cudaErrorNotSupported;
+  if (r.fed != nullptr && !epiopt) return cudaErrorNotSupported;
+  // fp8 fwd1 tile width.  64: a tile's W1 rows start at column 0 or 2 of the 4-column scale chunk
+  // in TMEM.  (32-wide tiles would start at odd columns: `misaligned address` on sm_100a, measured.)
+  const int p1_bn = kBN;
+  const int p1_tiles = mt_b * ((r.hidden + p1_bn - 1) / p1_bn);
+  const int need = std::max(std::max(p1_tiles, mt_h * nt_d + nt_h + 1), chain == 3 ? mt_b * 4 : 0);
   if (need > kGrid * 4) return cudaErrorInvalidValue;
   const int grid = need > kGrid ? need : kGrid;
   if (grid > 148) return cudaErrorInvalidValue;
 
   Maps m;
+  std::memset(&m, 0, sizeof(m));
   const long long rows_x = static_cast<long long>(r.steps) * r.batch;
   auto mk = [&](CUtensorMap* out, const void* ptr, long long ld, bool mn, int rows_extent, int K,
-                int rows_tile) {
+                int rows_tile, DType dt = DType::BF16) {
     GemmOperand op{ptr, ld, 0, mn};
-    return gemm_make_operand_map(out, op, DType::BF16, rows_extent, K, 1, rows_tile);
+    return gemm_make_operand_map(out, op, dt, rows_extent, K, 1, rows_tile);
   };
   cudaError_t e;
   // K-major: (rows_extent = M|N, K);  MN-major: memory [K][M|N]
@@ -1409,11 +1430,19 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
   if ((e = mk(&m.dh_mn, r.dh, r.hidden, true, r.hidden, r.batch, kBM)) != cudaSuccess) return e;
   if ((e = mk(&m.x_mn, r.x, r.in_dim, true, r.in_dim, (int)rows_x, kBN)) != cudaSuccess) return e;
   if ((e = mk(&m.w1_k256, r.w1_shadow, r.in_dim, false, r.hidden, r.in_dim, chain == 1 ? 256 : kBN)) != cudaSuccess) return e;
+  const Mx8MlpLayout ql = mx8_mlp_layout(r.in_dim, r.hidden);
+  if (fp8) {
+    const DType q = DType::FP8_E4M3;
+    if ((e = mk(&m.xq_k, r.x_q, r.in_dim, false, (int)rows_x, r.in_dim, kBM, q)) != cudaSuccess) return e;
+    if ((e = mk(&m.w1q_k, r.work_q + ql.w1q, r.in_dim, false, r.hidden, r.in_dim, p1_bn, q)) != cudaSuccess) return e;
+    if ((e = mk(&m.hq_k, r.h_q, r.hidden, false, r.batch, r.hidden, kBM, q)) != cudaSuccess) return e;
+    if ((e = mk(&m.w2q_k, r.work_q + ql.w2q, r.hidden, false, 64, r.hidden, 64, q)) != cudaSuccess) return e;
+  }
 
   Args a{};
   a.B = r.batch; a.steps = r.steps; a.in_dim = r.in_dim; a.hidden = r.hidden;
   a.n_classes = r.n_classes; a.ncp = r.ncp; a.n_params = r.n_params;
-  a.chain = chain; a.epiopt = epiopt_env ? 1 : 0; a.dbg = r.dbg;
+  a.chain = chain; a.epiopt = epiopt ? 1 : 0; a.dbg = r.dbg;
   a.x_ready = chain != 1 ? r.x_ready : nullptr; a.round_seq = r.round_seq;
   if (r.x_ready != nullptr && chain == 1) return cudaErrorNotSupported;
   a.pred = r.pred ? r.pred : current_predicate();
@@ -1427,55 +1456,22 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
   a.dlogits = reinterpret_cast<__nv_bfloat16*>(r.dlogits);
   a.dh = reinterpret_cast<__nv_bfloat16*>(r.dh);
   a.labels = r.labels; a.loss_sum = r.loss_sum; a.correct = r.correct;
+  a.x_sf = r.x_sf; a.work_q = r.work_q; a.h_q = r.h_q; a.h_sf = r.h_sf; a.ql = ql; a.p1_bn = p1_bn;
+  a.has_fed = r.fed != nullptr ? 1 : 0;
+  if (r.fed != nullptr) a.f = *r.fed;
+  a.upq_off[0] = r.upq_off[0]; a.upq_off[1] = r.upq_off[1];
+  a.n_samples = r.n_samples; a.n_loss_terms = r.n_loss_terms; a.byz_mode = r.byz_mode; a.byz_scale = r.byz_scale;
 
-  static bool configured = false;
-  if (!configured) {
-    e = cudaFuncSetAttribute(mlp_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+  static bool configured[2] = {false, false};
+  if (!configured[fp8 ? 1 : 0]) {
+    e = fp8 ? cudaFuncSetAttribute(mlp_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal)
+            : cudaFuncSetAttribute(mlp_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[fp8 ? 1 : 0] = true;
   }
   note_launch();
-  if (chain == 4) {
-    // clusters of 4 consecutive CTAs (cluster c = M-tile c for c < mt_b), plus the PDL attribute
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((grid + 3) / 4 * 4);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmemTotal;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    return cudaLaunchKernelEx(&cfg, mlp_round_kernel, m, a);
-  }
-  return launch_pdl(mlp_round_kernel, dim3(grid), dim3(kThreads), kSmemTotal, stream, m, a);
-}
-
-cudaError_t mlp_val_sm100(const MlpValArgs& r, cudaStream_t stream) {
-  bind_context_once();
-  if (r.hidden != kChainH || r.n_classes > 64 || r.in_dim % 8 || r.n_val <= 0 || r.max_cand <= 0)
-    return cudaErrorInvalidValue;
-  CUtensorMap tx;
-  GemmOperand op{r.x, r.ldx, 0, false};
-  cudaError_t e = gemm_make_operand_map(&tx, op, DType::BF16, r.n_val, r.in_dim, 1, kBM);
-  if (e != cudaSuccess) return e;
-  ValArgs v{};
-  v.n_val = r.n_val; v.in_dim = r.in_dim; v.n_classes = r.n_classes;
-  v.maps = r.maps; v.dyn1 = r.dyn1; v.dyn2 = r.dyn2;
-  v.labels = r.labels; v.correct = r.correct;
-  v.pred = r.pred ? r.pred : current_predicate();
-  static bool configured = false;
-  if (!configured) {
-    e = cudaFuncSetAttribute(mlp_val_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kValSmem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  note_launch();
-  return launch_pdl(mlp_val_kernel, dim3((r.n_val + kBM - 1) / kBM, r.max_cand), dim3(kThreads), kValSmem,
-                    stream, tx, v);
+  if (fp8) return launch_pdl(mlp_round_kernel<true>, dim3(grid), dim3(kThreads), kSmemTotal, stream, m, a);
+  return launch_pdl(mlp_round_kernel<false>, dim3(grid), dim3(kThreads), kSmemTotal, stream, m, a);
 }
 
 }  // namespace bflc

@@ -64,8 +64,8 @@ struct Reader {
   const std::string& buf;
   size_t pos = 0;
   explicit Reader(const std::string& b) : buf(b) {}
-  void need(size_t n) const {
-    if (pos + n > buf.size()) throw std::runtime_error("ledger snapshot truncated");
+  void need(size_t n) const {   // overflow-safe: pos <= buf.size() always holds
+    if (n > buf.size() - pos) throw std::runtime_error("ledger snapshot truncated");
   }
   template <typename T>
   T pod() {
@@ -78,7 +78,7 @@ struct Reader {
   template <typename T>
   std::vector<T> vec() {
     const uint64_t n = pod<uint64_t>();
-    need(n * sizeof(T));
+    if (n > (buf.size() - pos) / sizeof(T)) throw std::runtime_error("ledger snapshot truncated");
     std::vector<T> v(n);
     if (n) std::memcpy(v.data(), buf.data() + pos, n * sizeof(T));
     pos += n * sizeof(T);
@@ -433,9 +433,14 @@ std::string Ledger::AppendDeviceRound(const DeviceRound& r) {
   const int n = cfg_.client_num;
   if (r.epoch != epoch_)
     return "epoch mismatch: device " + std::to_string(r.epoch) + " host " + std::to_string(epoch_);
-  if (static_cast<int>(r.role_before.size()) < n || static_cast<int>(r.role_after.size()) < n ||
-      static_cast<int>(r.score_rows.size()) < n)
+  // the device path keeps its masks in 32-bit words (kMaxRanks = 8 today)
+  if (n > 32) return "device rounds support at most 32 clients";
+  const size_t un = static_cast<size_t>(n);
+  if (r.role_before.size() < un || r.role_after.size() < un || r.score_rows.size() < un ||
+      r.scored_mask.size() < un || r.n_samples.size() < un || r.avg_cost.size() < un)
     return "short device record";
+  for (size_t c = 0; c < un; ++c)
+    if (r.score_rows[c].size() < un) return "short score row in device record";
   CIn in;
   std::memset(&in, 0, sizeof(in));
   COut out;
@@ -578,21 +583,32 @@ std::unique_ptr<Ledger> Ledger::restore(const std::string& blob) {
   Ledger& L = *LP;
   L.epoch_ = r.pod<int32_t>();
   L.global_ = r.vec<float>(); L.registered_ = r.vec<int>();
+  // every client id in the blob indexes fixed [kCMaxRanks] arrays later (aggregate_locked): a
+  // crafted snapshot must not be able to name an id outside [0, client_num)
+  auto id = [&](int k) {
+    if (k < 0 || k >= c.client_num) throw std::runtime_error("ledger snapshot: client id out of range");
+    return k;
+  };
+  if (static_cast<int64_t>(L.global_.size()) != c.model_size)
+    throw std::runtime_error("ledger snapshot: model size mismatch");
+  for (int k : L.registered_) id(k);
   for (uint64_t n = r.pod<uint64_t>(), i = 0; i < n; ++i) {
-    const int k = r.pod<int32_t>();
+    const int k = id(r.pod<int32_t>());
     L.role_[k] = r.pod<uint32_t>();
   }
   for (uint64_t n = r.pod<uint64_t>(), i = 0; i < n; ++i) {
     LocalUpdate u;
-    u.sender = r.pod<int32_t>(); u.delta = r.vec<float>(); u.meta.n_samples = r.pod<uint32_t>();
+    u.sender = id(r.pod<int32_t>()); u.delta = r.vec<float>(); u.meta.n_samples = r.pod<uint32_t>();
     u.meta.avg_cost = r.pod<float>(); u.arrival = r.pod<uint64_t>();
+    if (static_cast<int64_t>(u.delta.size()) != c.model_size)
+      throw std::runtime_error("ledger snapshot: update size mismatch");
     L.updates_.emplace(u.sender, std::move(u));
   }
   for (uint64_t n = r.pod<uint64_t>(), i = 0; i < n; ++i) {
-    const int c2 = r.pod<int32_t>();
+    const int c2 = id(r.pod<int32_t>());
     std::map<int, float> row;
     for (uint64_t m = r.pod<uint64_t>(), j = 0; j < m; ++j) {
-      const int t = r.pod<int32_t>();
+      const int t = id(r.pod<int32_t>());
       row[t] = r.pod<float>();
     }
     L.scores_[c2] = std::move(row);

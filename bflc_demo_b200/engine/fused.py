@@ -3,16 +3,23 @@ CUDA graph each round; who trains and who validates is decided by data in the HB
 page (role bits), not by launch topology.
 
   round graph (all ranks; 7-8 launches):
-    fed_plan_round  ||  cast u8->bf16  QueryState (local read of the ledger page); this round's
-                                       inputs on a parallel graph branch
-    [trainer]  mlp_round               the whole local epoch in ONE persistent kernel
-                                       (csrc/kernels/mlp_round_sm100.cu; per-GEMM launches with
-                                       ``fused_step=False``: models/mlp.py)
-    fed_upload                         UploadLocalUpdate (publish + release flags on peers)
-    [committee] fed_pull_candidates    QueryAllUpdates: each candidate's weights cross NVLink once
+    fed_plan_round  ||  prep_inputs    QueryState (local read of the ledger page); this round's
+                                       inputs (u8 -> bf16, + e4m3 and scale chunks in fp8 mode) and
+                                       the MXFP8 copy of the new global weights on a parallel branch
+    [trainer]  mlp_round               the whole local epoch in ONE persistent kernel whose last
+                                       optimizer epilogue IS UploadLocalUpdate (writes the upload
+                                       buffers, releases FLAG_TRAINED on every peer)
+                                       (csrc/kernels/mlp_round_sm100.cu; per-GEMM launches +
+                                       fed_upload with ``fused_step=False``: models/mlp.py)
+    [committee] fed_pull_*             QueryAllUpdates: each candidate's weights cross NVLink once
+                                       (fp8: one 227 KB blob per candidate)
                 mlp_val                validation of every candidate in one launch (or two grouped
                                        GEMMs whose TMA pulls the trainers' HBM directly)
     fed_consensus_aggregate            UploadScores + Aggregate + QueryGlobalModel
+
+``cfg.dtype``: "bf16", or "fp8" = BASELINE.json config #2: fwd1/fwd2 of training and the whole
+committee validation run block-scaled fp8 (tcgen05.mma.kind::mxf8f6f4.block_scale), gradients
+bf16, master weights / Adam moments fp32.
 
 No NCCL call and no host synchronisation inside a round.  The host C++ ledger drains the
 device block ring afterwards and re-executes every election (``Ledger.AppendDeviceRound``).
@@ -80,7 +87,16 @@ class FusedEngine:
         self.S = (len(shard) // cfg.batch_size) * cfg.batch_size  # drop remainder (M:141)
         self.steps = (self.S // cfg.batch_size) * cfg.local_epochs
         self.n_val = min(cfg.val_samples or len(shard), len(shard))
-        self.layout = HeapLayout(self.n_params, cfg.ring_slots)
+        # block-scaled fp8: needs the persistent trainer's shape family (hidden 256, <= 64 classes)
+        self.fp8 = cfg.dtype == "fp8"
+        if self.fp8 and not (cfg.hidden == 256 and shard.n_classes <= 64 and cfg.fused_step
+                             and cfg.batch_size % 128 == 0 and self.in_dim % 16 == 0
+                             and len(shard) % 128 == 0):
+            raise ValueError("dtype='fp8' (MXFP8) needs hidden == 256, <= 64 classes, batch % 128 == 0, "
+                             "in_dim % 16 == 0, shard rows % 128 == 0 and the fused step")
+        self.ql = self.mod.mx8_mlp_layout(self.in_dim, cfg.hidden) if self.fp8 else None
+        self.blob_bytes = (self.ql["total"] + 4095) // 4096 * 4096 if self.fp8 else 0
+        self.layout = HeapLayout(self.n_params, cfg.ring_slots, extra_bytes=2 * self.blob_bytes)
         self.heap = SymmetricHeap(self.layout.total_bytes, rank=rank, world=world, device=device,
                                   group=group, want_multicast=cfg.use_multicast)
         self.fed = self.layout.fed_dict(rank, world, self.heap.peer_ptrs, self.heap.mc_ptr)
@@ -123,11 +139,28 @@ class FusedEngine:
         self.trainer = FlatMLP(self.spec, self.work_master, self.work_shadow, self.grad,
                                cfg.batch_size, optimizer=cfg.optimizer, lr=cfg.learning_rate,
                                loss_sum=self.loss_sum, correct=self.train_correct,
-                               step_dev_ptr=plan_ptr + sz["plan_opt_step_off"])
+                               step_dev_ptr=plan_ptr + sz["plan_opt_step_off"], fp8=self.fp8)
+        # upload buffers start as the genesis model (the fused upload never touches the padding
+        # elements between tensors; FedAvg must not sum garbage there)
+        for par in (0, 1):
+            hv(o[f"upload_master{par}"], [P], torch.float32).copy_(init)
+            hv(o[f"upload_shadow{par}"], [P], torch.bfloat16).copy_(init.to(torch.bfloat16))
+        self.upq_off = [o["extra"], o["extra"] + self.blob_bytes] if self.fp8 else []
+        if self.fp8:
+            for off in self.upq_off:
+                self.trainer.quantize_weights(self.global_master, hv(off, [self.blob_bytes], torch.uint8))
+            self.trainer.quantize_weights()
 
         # ---- data ------------------------------------------------------------------------
         self.x_u8 = torch.empty(len(shard), self.in_dim, device=self.dev, dtype=torch.uint8)
         self.x_bf = torch.empty(len(shard), self.in_dim, device=self.dev, dtype=torch.bfloat16)
+        if self.fp8:
+            from ..models.mlp import sf_bytes
+            self.x_q = torch.zeros(len(shard), self.in_dim, device=self.dev, dtype=torch.uint8)
+            self.x_sf = torch.full((sf_bytes(len(shard), self.in_dim),), 127, device=self.dev,
+                                   dtype=torch.uint8)
+        else:
+            self.x_q = self.x_sf = None
         self.y = torch.empty(len(shard), device=self.dev, dtype=torch.int32)
         self.host_x = x0.contiguous().pin_memory()
         self.host_y = shard.y.to(torch.int32).contiguous().pin_memory()
@@ -158,24 +191,36 @@ class FusedEngine:
         #    GEMM's TMA producer pulls tiles across NVLink itself -- no staging pass, but every
         #    M-tile CTA re-reads the weights remotely (good only for few M-tiles).
         self.staged = bool(cfg.stage_candidates) and world > 1
-        self.cand_shadow = torch.zeros(world, P, device=self.dev, dtype=torch.bfloat16)
+        if self.fp8:
+            self.cand_q = torch.zeros(world, self.blob_bytes, device=self.dev, dtype=torch.uint8)
+            self.cand_shadow = None
+        else:
+            self.cand_q = None
+            self.cand_shadow = torch.zeros(world, P, device=self.dev, dtype=torch.bfloat16)
         blob = bytearray(2 * 2 * K * 128)
+
+        def b_map(base, e, kind, layer):
+            if self.fp8:   # e4m3 rows inside an Mx8MlpLayout blob; W2 is padded to 64 rows
+                rows = e.shape[0] if layer == 0 else 64
+                return self.mod.gemm_b_map(base + self.ql["w1q" if layer == 0 else "w2q"], rows,
+                                           e.shape[1], e.shape[1], False, True, kind, self.val_bn[layer])
+            return self.mod.gemm_b_map(base + e.offset * 2, e.shape[0], e.shape[1], e.shape[1], False,
+                                       False, kind, self.val_bn[layer])
+
         for layer, (e, kind) in enumerate(((e1, G.EPI_GENERIC), (e2, G.EPI_ARGMAX))):
             if self.staged:
                 for zslot in range(world):
-                    base = self.cand_shadow.data_ptr() + (zslot * P + e.offset) * 2
-                    m = self.mod.gemm_b_map(base, e.shape[0], e.shape[1], e.shape[1], False, False,
-                                            kind, self.val_bn[layer])
+                    base = (self.cand_q.data_ptr() + zslot * self.blob_bytes if self.fp8
+                            else self.cand_shadow.data_ptr() + zslot * P * 2)
                     idx = layer * K + zslot
-                    blob[idx * 128:(idx + 1) * 128] = m
+                    blob[idx * 128:(idx + 1) * 128] = b_map(base, e, kind, layer)
                 continue
             for par in range(2):
                 for r in range(world):
-                    base = self.heap.peer_ptrs[r] + o[f"upload_shadow{par}"] + e.offset * 2
-                    m = self.mod.gemm_b_map(base, e.shape[0], e.shape[1], e.shape[1], False, False, kind,
-                                            self.val_bn[layer])
+                    base = self.heap.peer_ptrs[r] + (self.upq_off[par] if self.fp8
+                                                     else o[f"upload_shadow{par}"])
                     idx = (layer * 2 + par) * K + r
-                    blob[idx * 128:(idx + 1) * 128] = m
+                    blob[idx * 128:(idx + 1) * 128] = b_map(base, e, kind, layer)
         self.b_maps = torch.frombuffer(blob, dtype=torch.uint8).to(self.dev)
         self.plan_layers = [(self.spec.offset("b1"), True), (self.spec.offset("b2"), True)]
         self.dyn_ptr = [plan_ptr + sz["plan_dyn_off"] + i * sz["GemmDynamic"] for i in range(2)]
@@ -187,6 +232,11 @@ class FusedEngine:
                          else world > 1 and (P * 4 > (64 << 20) or world >= 8))
         self.byz = 1 if rank in cfg.byzantine_ranks else 0
         self.fused_step = bool(cfg.fused_step) and self.trainer.fused_ok(self.steps)
+        # UploadLocalUpdate inside the trainer's last optimizer epilogue (needs E_OPT)
+        self.fused_upload = self.fused_step and os.environ.get("BFLC_MLP_EPIOPT", "1") != "0"
+        if self.fp8 and not (self.fused_step and self.fused_upload):
+            raise ValueError("dtype='fp8' needs the persistent trainer with the optimizer epilogue")
+        self._rounds = 0
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_pipe: Optional[torch.cuda.CUDAGraph] = None
         self.stream = torch.cuda.Stream(device=self.dev)
@@ -202,6 +252,8 @@ class FusedEngine:
         self.in_seq = torch.zeros(1, device=self.dev, dtype=torch.int32)
         self.cast_cnt = torch.zeros(16, device=self.dev, dtype=torch.int32)
         self.x_ready = torch.zeros(16, device=self.dev, dtype=torch.int32)
+        self.in_err = torch.zeros(1, device=self.dev, dtype=torch.int32)
+        self._ev_wq = torch.cuda.Event()
         self.seq_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._seq = 0
         self._copy_stream = torch.cuda.Stream(device=self.dev)
@@ -225,44 +277,73 @@ class FusedEngine:
         main = torch.cuda.current_stream()
         self._ev_fork.record(main)
         self._side.wait_event(self._ev_fork)
+        B = cfg.batch_size
         with torch.cuda.stream(self._side):
+            if self.fp8:
+                # the consensus kernel of the previous round rewrote the training weights: refresh
+                # this trainer's MXFP8 copy (e4m3 + scale chunks) before step 0
+                self.trainer.quantize_weights()
+                self._ev_wq.record(self._side)
             if pipe:
-                m.cast_u8_to_bf16_chunks(self.x_u8, self.x_bf, cfg.batch_size * self.in_dim, self.steps,
-                                         1.0 / 255.0, self.in_flags, self.in_seq, self.cast_cnt,
-                                         self.x_ready)
+                m.prep_inputs_chunks(self.x_u8, self.x_bf, self.x_q, self.x_sf, B, self.steps,
+                                     1.0 / 255.0, self.in_flags, self.in_seq, self.cast_cnt,
+                                     self.x_ready, self.in_err)
             else:
-                m.cast_u8_to_bf16(self.x_u8, self.x_bf, 1.0 / 255.0)
+                m.prep_inputs(self.x_u8, self.x_bf, self.x_q, self.x_sf, 1.0 / 255.0)
             self._ev_join.record(self._side)
-        m.fed_plan_round(self.fed, self.plan_layers, self.steps, self.staged)
+        if self.fp8:
+            m.fed_plan_round(self.fed, self.plan_layers, self.steps, self.staged,
+                             self.cand_q.data_ptr(), self.blob_bytes, self.upq_off)
+        else:
+            m.fed_plan_round(self.fed, self.plan_layers, self.steps, self.staged)
         if not pipe:
             main.wait_event(self._ev_join)
+        elif self.fp8:
+            main.wait_event(self._ev_wq)
         # local training, predicated on the trainer role bit
         m.set_predicate(self.is_trainer_ptr)
         if self.fused_step:
             # every local step of the round inside ONE persistent kernel (phase barriers instead
-            # of launches); the barrier word lives in the plan and is zeroed by k_plan
+            # of launches); the barrier word lives in the plan and is zeroed by k_plan.  With
+            # fused_upload its last optimizer epilogue publishes the update (UploadLocalUpdate).
+            up = dict(fed=self.fed, upq_off=self.upq_off, n_samples=self.S,
+                      n_loss_terms=self.steps * B, byz_mode=self.byz,
+                      byz_scale=cfg.byzantine_scale) if self.fused_upload else {}
             self.trainer.train_epoch_fused(
                 self.x_bf, self.y, self.steps, self.plan_ptr + self.sz["plan_step_barrier_off"],
                 None, -1, -1,
-                self.x_ready.data_ptr() if pipe else 0, self.in_seq.data_ptr() if pipe else 0)
+                self.x_ready.data_ptr() if pipe else 0, self.in_seq.data_ptr() if pipe else 0,
+                x_q=self.x_q, x_sf=self.x_sf, **up)
         else:
             self.trainer.train_epoch(self.x_bf, self.y, self.steps)
         m.set_predicate(0)
         if pipe:
             main.wait_event(self._ev_join)      # validation reads every converted row
-        m.fed_upload(self.fed, self.S, self.steps * cfg.batch_size, self.byz, cfg.byzantine_scale)
+        if not (self.fused_step and self.fused_upload):
+            m.fed_upload(self.fed, self.S, self.steps * B, self.byz, cfg.byzantine_scale)
         # committee validation: grouped GEMMs whose B operands are the trainers' uploads
         if self.staged:
-            m.fed_pull_candidates(self.fed, self.cand_shadow, None)
-        xv, yv = self.x_bf[: self.n_val], self.y[: self.n_val]
+            if self.fp8:
+                m.fed_pull_blobs(self.fed, self.upq_off[0], self.upq_off[1], self.blob_bytes, self.cand_q)
+            else:
+                m.fed_pull_candidates(self.fed, self.cand_shadow, None)
         H = cfg.hidden
-        if self.val_chain:
+        if self.fp8:
             m.set_predicate(self.is_comm_ptr)
-            m.mlp_val(xv, yv, self.val_correct, self.b_maps, self.dyn_ptr[0], self.dyn_ptr[1],
-                      self.n_val, self.in_dim, H, self.spec.by_name["w2"].shape[0], self.world)
+            m.mlp_val(self.x_q[: self.n_val], self.y[: self.n_val], self.val_correct, self.b_maps,
+                      self.dyn_ptr[0], self.dyn_ptr[1], self.n_val, self.in_dim, H,
+                      self.spec.by_name["w2"].shape[0], self.world, self.x_sf,
+                      self.plan_ptr + self.sz["plan_cand_blob_off"])
             m.set_predicate(0)
         else:
-            self._validate_two_gemms(xv, yv, H)
+            xv, yv = self.x_bf[: self.n_val], self.y[: self.n_val]
+            if self.val_chain:
+                m.set_predicate(self.is_comm_ptr)
+                m.mlp_val(xv, yv, self.val_correct, self.b_maps, self.dyn_ptr[0], self.dyn_ptr[1],
+                          self.n_val, self.in_dim, H, self.spec.by_name["w2"].shape[0], self.world)
+                m.set_predicate(0)
+            else:
+                self._validate_two_gemms(xv, yv, H)
         m.fed_consensus_aggregate(self.fed, self.n_val, cfg.weight_by_score, self.two_shot,
                                   cfg.use_multicast and self.heap.has_multicast)
         self.launches_per_round = int(m.launch_count() - n0)
@@ -283,6 +364,7 @@ class FusedEngine:
         with torch.cuda.stream(self.stream):
             self._enqueue_round()
         self.stream.synchronize()
+        self._rounds += 1          # the warm-up is a real round (epoch advanced)
         if not self.cfg.cuda_graph:
             return
         g = torch.cuda.CUDAGraph()
@@ -294,10 +376,10 @@ class FusedEngine:
             # their H2D copies land.  Its only new kernel is warmed up once outside the capture
             # (lazy module loading), without running an extra round.
             with torch.cuda.stream(self.stream):
-                self.mod.cast_u8_to_bf16_chunks(self.x_u8, self.x_bf,
-                                                self.cfg.batch_size * self.in_dim, self.steps,
-                                                1.0 / 255.0, self.in_flags, self.in_seq,
-                                                self.cast_cnt, self.x_ready)
+                self.mod.prep_inputs_chunks(self.x_u8, self.x_bf, self.x_q, self.x_sf,
+                                            self.cfg.batch_size, self.steps, 1.0 / 255.0,
+                                            self.in_flags, self.in_seq, self.cast_cnt, self.x_ready,
+                                            self.in_err)
             self.stream.synchronize()
             gp = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gp, stream=self.stream):
@@ -305,6 +387,13 @@ class FusedEngine:
             self.graph_pipe = gp
 
     def run_round(self, pipe: bool = False):
+        # the device BlockRecord ring has ring_slots entries and the consensus kernel overwrites
+        # slot epoch % ring_slots: drain into the host ledger before records can be lost
+        self._rounds += 1
+        if self._rounds - self.drained >= max(self.cfg.ring_slots // 2, 1):
+            errs = self.drain_blocks()
+            if errs:
+                raise RuntimeError(f"host/device ledgers disagree: {errs[:2]}")
         g = self.graph_pipe if (pipe and self.graph_pipe is not None) else self.graph
         if g is not None:
             with torch.cuda.stream(self.stream):
@@ -392,6 +481,9 @@ class FusedEngine:
         """Pull finished BlockRecords off the device ring into the host C++ ledger, which
         re-executes each election.  Returns the list of mismatches ([] = replicas agree)."""
         torch.cuda.synchronize()
+        if getattr(self, "in_err", None) is not None and int(self.in_err.item()):
+            raise RuntimeError("input pipeline: a chunk's H2D tag never arrived (host stalled > 10 s "
+                               "between launching the round and feeding it); the round ran on stale inputs")
         st = self.read_state()
         ring = bytes(self.ring_bytes.cpu().numpy())
         rs = self.sz["BlockRecord"]
@@ -438,7 +530,7 @@ class FusedEngine:
         """Sponsor-style test accuracy of the current global model (M:285-306)."""
         x = shard.x.reshape(len(shard), -1).to(self.dev)
         xb = torch.empty(x.shape, device=self.dev, dtype=torch.bfloat16)
-        self.mod.cast_u8_to_bf16(x.contiguous(), xb, 1.0 / 255.0)
+        self.mod.prep_inputs(x.contiguous(), xb, None, None, 1.0 / 255.0)
         cnt = self.trainer.accuracy_counts(xb, shard.y.to(self.dev, torch.int32),
                                            shadow=self.global_shadow, master=self.global_master)
         return float(cnt.item()) / len(shard)

@@ -136,6 +136,12 @@ class GenericFedEngine:
     # ------------------------------------------------------------------ one round
     def run_round(self) -> dict:
         m, cfg = self.mod, self.cfg
+        # ring backpressure: drain the device BlockRecord ring before slots can be overwritten
+        self._rounds = getattr(self, "_rounds", 0) + 1
+        if self._rounds - self.drained >= max(cfg.ring_slots // 2, 1):
+            errs = self.drain_blocks()
+            if errs:
+                raise RuntimeError(f"host/device ledgers disagree: {errs[:2]}")
         m.fed_plan_round(self.fed, [], self.steps, False)
         st = self.read_state()  # host learns roles/epoch (D2H of the 104-byte ledger page)
         role = st["roles"][self.rank]

@@ -26,6 +26,12 @@ from ..ops import gemm as G
 from .flat import ParamSpec
 
 
+def sf_bytes(rows: int, K: int) -> int:
+    """Bytes of the MXFP8 scale-chunk array of a [rows, K] operand: one 512-byte chunk per
+    (128 rows, 128 K) -- csrc/include/epi_common.cuh."""
+    return -(-rows // 128) * -(-K // 128) * 512
+
+
 def mlp_spec(in_dim: int = 784, hidden: int = 256, n_classes: int = 62) -> ParamSpec:
     return ParamSpec([("w1", (hidden, in_dim)), ("b1", (hidden,)),
                       ("w2", (n_classes, hidden)), ("b2", (n_classes,))])
@@ -43,7 +49,7 @@ class FlatMLP:
     def __init__(self, spec: ParamSpec, master: torch.Tensor, shadow: torch.Tensor,
                  grad: torch.Tensor, batch: int, *, optimizer: str = "sgd", lr: float = 1e-3,
                  loss_sum: Optional[torch.Tensor] = None, correct: Optional[torch.Tensor] = None,
-                 step_dev_ptr: int = 0):
+                 step_dev_ptr: int = 0, fp8: bool = False):
         self.spec, self.master, self.shadow, self.grad = spec, master, shadow, grad
         self.p = spec.views(master)
         self.s = spec.views(shadow)
@@ -69,6 +75,14 @@ class FlatMLP:
         self.side = torch.cuda.Stream(device=dev)
         self._ev_fork = torch.cuda.Event()
         self._ev_join = torch.cuda.Event()
+        # block-scaled fp8 forward (persistent trainer only): this trainer's quantised weights
+        # (an Mx8MlpLayout blob, refreshed by the optimizer epilogue) and the per-step e4m3 h
+        self.fp8 = bool(fp8)
+        self.ql = C().mx8_mlp_layout(self.in_dim, self.hidden) if self.fp8 else None
+        if self.fp8:
+            self.work_q = torch.zeros(self.ql["total"], device=dev, dtype=torch.uint8)
+            self.h_q = torch.zeros(batch, self.hidden, device=dev, dtype=torch.uint8)
+            self.h_sf = torch.full((sf_bytes(batch, self.hidden),), 127, device=dev, dtype=torch.uint8)
 
     # -------------------------------------------------------------- training
     def forward_backward(self, x: torch.Tensor, y: torch.Tensor) -> None:
@@ -117,23 +131,46 @@ class FlatMLP:
         need = max(mt_b * nt_h, mt_h * nt_d + nt_h + 1)
         return (need <= 128 and B % 8 == 0 and H % 8 == 0 and D % 8 == 0 and self.n_classes <= 64)
 
+    def offsets(self):
+        e = self.spec.by_name
+        return [e["w1"].offset, e["b1"].offset, e["w2"].offset, e["b2"].offset]
+
+    def quantize_weights(self, master: Optional[torch.Tensor] = None,
+                         blob: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fp32 master weights -> MXFP8 blob (e4m3 + UE8M0 scale chunks + fp32 biases).  Run at
+        the start of every round: the consensus kernel has just rewritten the training buffers."""
+        blob = self.work_q if blob is None else blob
+        C().quantize_mlp_blob(self.master if master is None else master, self.offsets(), self.in_dim,
+                              self.hidden, self.n_classes, blob)
+        return blob
+
     def train_epoch_fused(self, X: torch.Tensor, Y: torch.Tensor, steps: int,
                           barrier_ptr: int, dbg: Optional[torch.Tensor] = None, plan: int = -1,
-                          epiopt: int = -1, x_ready_ptr: int = 0, round_seq_ptr: int = 0) -> None:
+                          epiopt: int = -1, x_ready_ptr: int = 0, round_seq_ptr: int = 0,
+                          x_q: Optional[torch.Tensor] = None, x_sf: Optional[torch.Tensor] = None,
+                          fed: Optional[dict] = None, upq_off=(), n_samples: int = 0,
+                          n_loss_terms: int = 0, byz_mode: int = 0, byz_scale: float = 0.0) -> None:
         """All ``steps`` mini-batch steps in ONE persistent kernel launch; ``barrier_ptr`` is a
         device uint32 that is zero on entry (the phase barrier).  ``dbg``: optional int64
-        [steps, 16] buffer that receives %globaltimer phase stamps of CTA 0.  ``plan`` /
+        [steps, 32] buffer that receives %globaltimer phase stamps of CTA 0.  ``plan`` /
         ``epiopt`` pick a phase plan explicitly (0 | 1 | 3 | 4, 0 | 1; -1 = BFLC_MLP_CHAIN /
         BFLC_MLP_EPIOPT / default) -- all plans are numerically equivalent.  ``x_ready_ptr`` /
         ``round_seq_ptr`` (device uint32[steps] / uint32): the producer of step s waits until
-        ``x_ready[s] >= *round_seq`` (input pipeline, engine/fused.py)."""
-        e = self.spec.by_name
-        offs = [e["w1"].offset, e["b1"].offset, e["w2"].offset, e["b2"].offset]
-        C().mlp_round(X, Y, self.master, self.shadow, self.grad, offs, self.h, self.dlogits,
+        ``x_ready[s] >= *round_seq`` (input pipeline, engine/fused.py).
+
+        ``x_q`` / ``x_sf`` (fp8 trainers): the e4m3 copy of X and its scale chunks
+        (``prep_inputs``); fwd1 / fwd2 then run block-scaled fp8.  ``fed`` (+ ``upq_off``,
+        ``n_samples``, ...): fuse UploadLocalUpdate into the last step (the optimizer epilogue
+        writes the upload buffers, CTA 0 releases FLAG_TRAINED on every peer)."""
+        C().mlp_round(X, Y, self.master, self.shadow, self.grad, self.offsets(), self.h, self.dlogits,
                       self.dh, self.loss_sum, self.correct, barrier_ptr, self.batch, steps,
                       self.in_dim, self.hidden, self.n_classes, self.lr,
                       self.optimizer == "adam", self.m, self.v, self.step_dev_ptr, dbg, plan, epiopt,
-                      x_ready_ptr, round_seq_ptr)
+                      x_ready_ptr, round_seq_ptr,
+                      x_q if self.fp8 else None, x_sf if self.fp8 else None,
+                      self.work_q if self.fp8 else None, self.h_q if self.fp8 else None,
+                      self.h_sf if self.fp8 else None, fed, list(upq_off), n_samples, n_loss_terms,
+                      byz_mode, byz_scale)
 
     # ------------------------------------------------------------ evaluation
     def accuracy_counts(self, X: torch.Tensor, Y: torch.Tensor, shadow: Optional[torch.Tensor] = None,

@@ -8,6 +8,10 @@ Checks:
   two_shot    two-shot (slice-reduce + publish) aggregation gives the same digest as one-shot
   multicast   the same through NVLS multimem stores when the heap has a multicast mapping
   generic     LeNet-5 through the model-agnostic engine (validation on peers' HBM)
+  fedavg      the aggregated global model is RIGHT, not just identical: after every round each rank
+              recomputes sum_k w_k * upload_k (selected set + weights from the host ledger's block,
+              uploads read out of the trainers' HBM, ascending rank order, fp32 fma) in PyTorch and
+              compares it with the device result -- bf16 and fp8 engines
 """
 import json
 import os
@@ -87,6 +91,38 @@ def main():
                              loss=r["loss"], multicast=r["symm"]["multicast"],
                              multicast_error=r["symm"]["multicast_error"], notes=r["symm"]["notes"])
         out["two_shot"] = res
+    if "fedavg" in which:
+        res = {}
+        for dt in ("bf16", "fp8"):
+            cfg = FLConfig.for_world(world, hidden=256, batch_size=128, samples_per_client=512,
+                                     learning_rate=0.05, dtype=dt)
+            shard = femnist_like(world, 512, seed=3, only=rank)[0]
+            eng = FusedEngine(cfg, shard, rank=rank, world=world, device=lr)
+            eng.capture()
+            o, P = eng.layout.offsets, eng.n_params
+            worst, exact, errs = 0.0, True, []
+            for _ in range(4):
+                eng.run_round()
+                torch.cuda.synchronize(); dist.barrier()
+                errs += eng.drain_blocks()
+                blk = eng.host_ledger.blocks()[-1]
+                par = blk["epoch"] & 1
+                ref = torch.zeros(P, device="cuda", dtype=torch.float64)
+                for t, w in zip(blk["selected"], blk["weight"]):
+                    up = eng.heap.view(o[f"upload_master{par}"], [P], torch.float32, rank=t)
+                    # fp32 fma(w, v, acc): the product is exact in fp64, one rounding back to fp32
+                    ref = (ref + up.double() * float(w)).float().double()
+                d = (eng.global_master.double() - ref).abs().max().item()
+                worst = max(worst, d / max(ref.abs().max().item(), 1e-30))
+                exact = exact and bool((eng.global_master.double() == ref).all())
+                torch.cuda.synchronize(); dist.barrier()
+            g = gather(dict(worst=worst, exact=exact, errs=errs, n_sel=len(blk["selected"])))
+            res[dt] = dict(worst_rel=max(i["worst"] for i in g), bit_exact=all(i["exact"] for i in g),
+                           errs=sum((i["errs"] for i in g), []), n_selected=g[0]["n_sel"])
+            torch.cuda.synchronize(); dist.barrier()
+            del eng
+            torch.cuda.synchronize(); dist.barrier()
+        out["fedavg"] = res
     if "generic" in which:
         from bflc_demo_b200.engine.generic import GenericFedEngine
         from bflc_demo_b200.models.nets import LeNet5

@@ -40,6 +40,18 @@ def test_fused_engine_multi_gpu():
         assert mode["identical"] and mode["errs"] == [] and mode["chain_ok"]
 
 
+def test_fedavg_result_equals_weighted_mean_of_uploads():
+    """The global model every replica holds == sum_k w_k * upload_k recomputed in PyTorch from the
+    trainers' HBM and the host ledger's block (replicas being identical is checked elsewhere;
+    this checks they are RIGHT), for the bf16 and the fp8 engine."""
+    n, res = _run(["fedavg"])
+    for dt in ("bf16", "fp8"):
+        r = res["fedavg"][dt]
+        assert r["errs"] == [] and r["n_selected"] >= 1
+        assert r["worst_rel"] < 1e-6, r          # (bit_exact is reported; fp64 emulation of fma can
+                                                 #  double-round a rare element by one ulp)
+
+
 def test_generic_engine_and_byzantine_multi_gpu():
     n, res = _run(["generic", "byzantine"])
     g = res["generic_lenet5"]

@@ -243,3 +243,39 @@ def test_consensus_math_matches_oracle(data):
     for t in ref.selected:
         assert abs(got["weight"][t] - ref.weight[t]) < 1e-6
     assert abs(got["global_loss"] - ref.global_loss) < 1e-4
+
+
+def test_device_round_and_snapshot_inputs_are_validated():
+    """Untrusted inputs of the host ledger: a short device record is refused (no out-of-bounds
+    read), and a corrupted snapshot either restores or raises -- it never names a client id
+    outside [0, client_num) (those ids index fixed arrays in the aggregation)."""
+    led, orc = make()
+    for i in range(8):
+        led.RegisterNode(i); orc.RegisterNode(i)
+    roles = led.roles()
+    rec = dict(epoch=0, role_before=roles, role_after=roles, score_rows=[[0.0] * 8] * 8, scored_mask=[0] * 8,
+               n_samples=[1] * 8, avg_cost=[0.0] * 8, admitted_mask=0, selected_mask=0, global_loss=0.0,
+               model_digest=0, weight_by_score=0)
+    for key, short in (("n_samples", [1] * 3), ("avg_cost", [0.0]), ("scored_mask", []),
+                       ("score_rows", [[0.0] * 8] * 7 + [[0.0] * 2]), ("role_after", roles[:4])):
+        bad = dict(rec); bad[key] = short
+        assert "short" in led.AppendDeviceRound(bad), key
+    assert led.epoch() == 0                      # nothing was appended
+    rng = np.random.default_rng(3)
+    run_round(led, orc, rng)
+    blob = bytes(led.snapshot())
+    assert L.Ledger.restore(blob).state_hash() == led.state_hash()
+    ok = bad_n = 0
+    for _ in range(300):
+        b = bytearray(blob)
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(8, len(b)))] = int(rng.integers(0, 256))
+        try:
+            r = L.Ledger.restore(bytes(b))
+            assert all(0 <= c < 8 for c in range(len(r.roles())))
+            ok += 1
+        except (RuntimeError, ValueError, MemoryError):
+            bad_n += 1
+    assert ok + bad_n == 300 and bad_n > 0
+    with pytest.raises(RuntimeError):
+        L.Ledger.restore(blob[: len(blob) // 2])
