@@ -7,34 +7,43 @@
 //
 //   per step:  P1  h  = relu(x W1^T + b1)                       K = 784
 //              X   per 128 batch rows, 4 CTAs: fwd2 -> softmax-xent -> dh = (dlogits W2) relu'(h)
-//              B   dW1 = dh^T x  ||  dW2 = dlogits^T h, optimizer (SGD / Adam) applied to the fp32
-//                  master straight from the accumulator tile (E_OPT) + compute-copy refresh
+//              B   dW1 = dh^T x  ||  dW2 = dlogits^T h  as 64 x 64 tiles (UMMA M = 64) on 57 CTAs,
+//                  optimizer (SGD / Adam) applied to the fp32 master straight from the
+//                  accumulator tile (E_OPT) + compute-copy refresh
 //
 // Precision.  bf16 mode: every GEMM is tcgen05.mma.kind::f16 on bf16 shadows.  fp8 mode
 // (BASELINE.json config #2, "block-scaled fp8"): fwd1 and fwd2 are
 // tcgen05.mma.kind::mxf8f6f4.block_scale -- x arrives as e4m3 + UE8M0 scales from the input
-// kernel (elementwise_optim.cu), the E_OPT epilogue re-quantises every updated weight tile
-// (one scale per 32 K-elements, computed with three warp shuffles over the 8 lanes that own a
-// K-group) and the fwd1 epilogue quantises h; scale chunks reach TMEM through tcgen05.cp.
-// The hidden/weight gradients stay bf16, masters and Adam moments fp32.  In fp8 mode fwd1 runs
-// as 128 x 64 tiles (150 KB of TMA ingest per CTA instead of 300 KB).  Measured limits of the
-// block-scaled UMMA on sm_100a: M = 64 per CTA is an illegal instruction, and a scale-factor
-// TMEM address at an odd column (32-wide tiles) faults with `misaligned address`.
+// kernel (elementwise_optim.cu), the E_OPT epilogue re-quantises every updated weight tile (one
+// thread per 32-element K-group of the staged tile: amax, one scale byte, 32 e4m3 bytes) and
+// the fwd1 epilogue quantises h; scale chunks reach TMEM through tcgen05.cp.  The hidden/weight
+// gradients stay bf16, masters and Adam moments fp32.  Measured limits of the block-scaled
+// UMMA on sm_100a: M = 64 per CTA is an illegal instruction, and a scale-factor TMEM address
+// at an odd column (32-wide tiles) faults with `misaligned address` -- so fwd1 is 128 x 64.
 //
-// Each GEMM tile is the same tcgen05 / TMEM / TMA pipeline as gemm_sm100.cu (8-stage
-// 128B-swizzled ring, one elected MMA thread, staged coalesced epilogue); the smem ring, its
-// mbarriers and the TMEM allocation persist across tiles, phases and steps.
+// Warp roles (384 threads = three warpgroups): warpgroup 0 = warp 0 TMA producer, warp 1 TMEM
+// owner + single-thread MMA issuer (warps 2-3 idle); warpgroups 1-2 = eight epilogue warps.  A
+// warp may only touch the TMEM lane quarter (warp % 4); two warps share a quarter and split a
+// tile's 64 columns -- "half" h owns columns [32h, 32h+32).  Measured before the split (4
+// epilogue warps = one warp per SM sub-partition, every dependent instruction exposes its full
+// latency): epilogues were 9.8 of a 23 us step.  Registers follow the work: `setmaxnreg` shrinks
+// warpgroup 0 to 56 registers per thread and grows the epilogue warpgroups to 224.
+//
+// Each GEMM tile is the same tcgen05 / TMEM / TMA pipeline as gemm_sm100.cu (7-stage
+// 128B-swizzled ring, staged coalesced epilogue); the smem ring, its mbarriers and the TMEM
+// allocation persist across tiles, phases and steps.
 //
 // Why: at this problem size every stand-alone GEMM launch costs 6-12 us of which only a
 // fraction is math (launch, prologue, first-TMA latency, drain) -- six launches per step,
 // 48 per round.  Inside one kernel the fixed costs are paid once and a phase boundary is a
-// ~1-2 us grid barrier.  (Reference step: python-sdk/main.py:141-148, three sess.run calls;
+// ~2 us grid barrier.  (Reference step: python-sdk/main.py:141-148, three sess.run calls;
 // Adam: the commented alternative at python-sdk/main.py:126.)
 #include <cuda_bf16.h>
 
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "bflc_kernels.h"
 #include "epi_common.cuh"
@@ -46,7 +55,6 @@ namespace bflc {
 namespace {
 
 using epi::kStgLd;
-using epi::kStgBytes;
 using epi::kSfChunk;
 using epi::stage_put;
 using epi::stage_get;
@@ -54,33 +62,36 @@ using epi::col_sum32;
 using epi::st_sw128;
 __device__ __forceinline__ uint32_t pack2(float a, float b) { return epi::pack_bf16x2(a, b); }
 
-constexpr int kBM = 128, kBN = 64, kStages = 8;
+constexpr int kBM = 128, kBN = 64, kStages = 7;
 constexpr int kABytes = kBM * 128, kBBytes = kBN * 128, kStageBytes = kABytes + kBBytes;
 constexpr int kTileBytes = kStages * kStageBytes;
 constexpr int kSfStage = 2 * kSfChunk;              // per ring stage: [SFA chunk | SFB chunk]
 constexpr int kSfBytes = kStages * kSfStage;        // fp8 only; the chain uses the first 4 chunks
 constexpr int kBarBytes = 512;
+constexpr int kEpiWarps = 8;       // two per TMEM lane quarter: warp (q, half) owns 32 of a tile's 64 columns
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kStgAll = kEpiWarps * 32 * kStgLd * 4;
 constexpr int kBiasFloats = 320;   // chain: b1[256] | b2[64]; tile jobs use the first kBN
-constexpr int kSmemTotal = kTileBytes + kSfBytes + kBarBytes + kStgBytes + kBiasFloats * 4 + 1024;
+constexpr int kXchFloats = 4 * 2 * 128;   // chain E2: per-row partials exchanged by the two halves
+constexpr int kSmemTotal = kTileBytes + kSfBytes + kBarBytes + kStgAll + (kBiasFloats + kXchFloats) * 4 + 1024;
 static_assert(kSmemTotal <= 227 * 1024, "shared memory budget");
-constexpr int kThreads = 192;
+constexpr int kEpiT0 = 128;        // first epilogue thread (warpgroup 0 = producer / MMA / 2 idle warps)
+constexpr int kThreads = kEpiT0 + kEpiThreads;
+constexpr int kRegsLow = 56, kRegsHigh = 224;   // (168 - 56) * 128 == (224 - 168) * 256
 constexpr int kGrid = 32;
 
-// ---- fused chain (hidden == 256): the same 192 KB of ring memory, re-cut as
-//   3 stages x (x tile 16 KB + W1 tile 32 KB) for fwd1 (plan 1), then after fwd1 has retired
-//   [0, 64 KB) h as fwd2's A operand | [96, 128 KB) W2 MN-major (dh's B) | [128, 144 KB) dlogits
-//   (dh's A), and a dedicated [144, 176 KB) W2 K-major (fwd2's B) loaded up front.
-//   fp8: h is 2 x 16 KB of e4m3 at [0, 32 KB), W2 K-major 2 x 8 KB at [144, 160 KB).
-constexpr int kCStages = 3;
-constexpr int kCA = kBM * 128, kCB = 256 * 128, kCStage = kCA + kCB;
+// ---- fused chain (hidden == 256): the ring memory re-cut as
+//   [0, 64 KB) h tile = fwd2's A operand | [64, 96 KB) W2 K-major (fwd2's B) | [96, 104 KB) this
+//   CTA's 64-column slice of W2 MN-major (dh's B) | [104, 120 KB) dlogits (dh's A).
+//   fp8: h is 2 x 16 KB of e4m3 at [0, 32 KB), W2 K-major 2 x 8 KB at [64, 80 KB).
 constexpr int kOffH = 0;
-constexpr int kOffW2MN = 2 * kCStage;
-constexpr int kOffDL = kOffW2MN + 32768;
-constexpr int kOffW2K = kCStages * kCStage;
-static_assert(kOffDL + 16384 <= kOffW2K && kOffW2K + 32768 <= kTileBytes, "chain smem layout");
+constexpr int kOffW2K = 64 * 1024;
+constexpr int kOffW2MN = 96 * 1024;
+constexpr int kOffDL = 104 * 1024;
+static_assert(kOffDL + 16384 <= kTileBytes, "chain smem layout");
 constexpr int kChainH = 256;
-constexpr int kDefaultPlan = 3;    // phase plan when neither the caller nor BFLC_MLP_CHAIN picks one
-constexpr int kTmemCols = 512;     // chain: h / dh accumulator [0,256) + logits [256,320) + scales
+constexpr int kDefaultPlan = 3;    // phase plan when neither the caller nor BFLC_MLP_CHAIN picks one (0 | 3)
+constexpr int kTmemCols = 512;     // chain: dh accumulator [0,64) + logits [256,320) + scales
 constexpr uint32_t kTmemSfa = 320, kTmemSfb = 328;   // fp8: scale-factor columns (4 + up to 4)
 
 enum EpiMode : int { E_BIAS_RELU_BF16 = 0, E_XENT = 1, E_F32 = 2, E_MASK_COLSUM_BF16 = 3,
@@ -88,13 +99,12 @@ enum EpiMode : int { E_BIAS_RELU_BF16 = 0, E_XENT = 1, E_F32 = 2, E_MASK_COLSUM_
 
 struct Maps {  // TMA descriptors, SWIZZLE_128B
   CUtensorMap x_k, w1_k, h_k, w2_k, dl_mn, h_mn, dl_k, w2_mn, dh_mn, x_mn;   // bf16
-  CUtensorMap w1_k256;   // W1 with a 256-row box (plan 1: the whole hidden width in one tile)
-  CUtensorMap xq_k, w1q_k, hq_k, w2q_k;   // fp8 (e4m3 as u8): x 128-row box, W1 p1_bn rows, h 128, W2 64
+  CUtensorMap xq_k, w1q_k, hq_k, w2q_k;   // fp8 (e4m3 as u8): x 128-row box, W1 64, h 128, W2 64
 };
 
 struct Args {
   int B, steps, in_dim, hidden, n_classes, ncp;  // ncp = dlogits row stride (padded classes)
-  int chain;                     // 0: P1|P2|P3   1: fwd1->xent->dh chained   3: P1 | fwd2->xent->dh chained
+  int chain;                     // 0: P1|P2|P3 as separate phases   3: P1 | fwd2->xent->dh chained
   int epiopt;                    // optimizer applied in the weight-gradient epilogues (no P5)
   unsigned long long* dbg;       // optional %globaltimer stamps [steps][32] written by CTA 0
   const unsigned int* x_ready;   // optional input pipeline: step s may read x once x_ready[s] >= *round_seq
@@ -115,18 +125,19 @@ struct Args {
   // fp8 forward
   const uint8_t* x_sf; uint8_t* work_q; uint8_t* h_q; uint8_t* h_sf;
   Mx8MlpLayout ql;
-  int p1_bn;                     // fp8 fwd1 tile width: 64 (16 CTAs) or 32 (32 CTAs)
+  int bm_w;                      // weight-gradient tile height: 64 (default) or 128
   // fused upload
   int has_fed; FedArgs f; long long upq_off[2];
   int n_samples, n_loss_terms, byz_mode; float byz_scale;
 };
 
-struct Job {  // one output tile (128 or 64 rows x 64 columns)
+struct Job {  // one output tile (bm rows x 64 columns)
   const CUtensorMap* ta; const CUtensorMap* tb;
   int a_mn, b_mn;
   int a_c0, a_c1, b_c0, b_c1;   // TMA coordinates of K-block 0 (c0 = innermost)
   int n_kb;
   int m0, n0, M, N;             // output tile origin / logical extent
+  int bm;                       // tile height: 128, or 64 (UMMA M = 64, kind::f16 only)
   int mode;
   long long ldd;
   void* d;                      // output
@@ -136,10 +147,10 @@ struct Job {  // one output tile (128 or 64 rows x 64 columns)
   const int32_t* labels;        // E_XENT (already offset to this step's rows)
   float grad_scale;
   float bc1, bc2;               // E_OPT + Adam: bias corrections of this step
-  // ---- fp8 operands (K-major e4m3, K-blocks of 128 elements); bn = tile width (64, or 32)
-  int fp8, bn;
+  // ---- fp8 operands (K-major e4m3, K-blocks of 128 elements)
+  int fp8;
   const uint8_t* sfa; const uint8_t* sfb;   // scale chunk of K-block 0 of this tile's row block
-  uint32_t sfa_col, sfb_col;                // column of the tile's first row inside the 4-column chunk
+  uint32_t sfb_col;                         // column of the tile's first W row inside the 4-column chunk
   // ---- E_OPT in fp8 mode: where the re-quantised tile goes (byte offsets inside a model blob)
   int q_off, qsf_off, ldq, q_nkb;
   int last;                     // last step of the round: E_OPT also publishes the upload
@@ -152,13 +163,9 @@ struct Pipe {  // persistent pipeline state of one role
   uint32_t tile;  // tiles processed so far (accumulator barrier parity)
 };
 struct ChainBars {
-  uint64_t* full; uint64_t* empty;   // [kCStages] fwd1 ring
+  uint64_t* h;                       // h tile (+ scale chunks) landed
   uint64_t* w2k; uint64_t* w2mn;     // W2 operand tiles landed
-  uint64_t* acc_h; uint64_t* h_ready; uint64_t* acc_l; uint64_t* dl_ready; uint64_t* acc_dh;
-};
-struct CPipe {
-  uint32_t it;   // fwd1 K-blocks processed (ring slot / parity)
-  uint32_t n;    // chains processed (parity of the once-per-chain barriers)
+  uint64_t* acc_l; uint64_t* dl_ready; uint64_t* acc_dh;
 };
 
 template <typename T>
@@ -170,6 +177,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // Where the last step's optimizer epilogue publishes (resolved from the ledger page: the upload
 // buffers are double-buffered by epoch parity).
@@ -198,6 +206,7 @@ __device__ __forceinline__ UploadDst upload_dst(const Args& a) {
 template <bool FP8>
 __device__ __forceinline__ void produce_tile(const Job& j, uint8_t* smem, uint8_t* sf_smem,
                                              uint64_t* full_bar, uint64_t* empty_bar, Pipe& pp) {
+  const uint32_t a_bytes = static_cast<uint32_t>(j.bm) * 128u;
   for (int i = 0; i < j.n_kb; ++i, ++pp.it) {
     const int s = pp.it % kStages;
     const uint32_t ph = (pp.it / kStages) & 1;
@@ -207,19 +216,20 @@ __device__ __forceinline__ void produce_tile(const Job& j, uint8_t* smem, uint8_
     if (ptx::elect_one()) {
       if (FP8 && j.fp8) {
         // e4m3 tiles (K-block = 128 bytes) + the two 512-byte scale chunks of this K-block
-        ptx::mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(kABytes + j.bn * 128 + kSfStage));
+        ptx::mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(kABytes + kBBytes + kSfStage));
         ptx::tma_load_3d(sa, j.ta, &full_bar[s], j.a_c0 + i * 128, j.a_c1, 0);
         ptx::tma_load_3d(sb, j.tb, &full_bar[s], j.b_c0 + i * 128, j.b_c1, 0);
         epi::bulk_g2s(sf_smem + s * kSfStage, j.sfa + static_cast<long long>(i) * kSfChunk, kSfChunk, &full_bar[s]);
         epi::bulk_g2s(sf_smem + s * kSfStage + kSfChunk, j.sfb + static_cast<long long>(i) * kSfChunk, kSfChunk,
                       &full_bar[s]);
       } else {
-        ptx::mbar_expect_tx(&full_bar[s], kStageBytes);
+        ptx::mbar_expect_tx(&full_bar[s], a_bytes + kBBytes);
         if (!j.a_mn) {
           ptx::tma_load_3d(sa, j.ta, &full_bar[s], j.a_c0 + i * 64, j.a_c1, 0);
         } else {
+          // MN-major A: one 64-element (128-byte) chunk of M per box
           ptx::tma_load_3d(sa, j.ta, &full_bar[s], j.a_c0, j.a_c1 + i * 64, 0);
-          ptx::tma_load_3d(sa + 64 * 128, j.ta, &full_bar[s], j.a_c0 + 64, j.a_c1 + i * 64, 0);
+          if (j.bm == kBM) ptx::tma_load_3d(sa + 64 * 128, j.ta, &full_bar[s], j.a_c0 + 64, j.a_c1 + i * 64, 0);
         }
         if (!j.b_mn)
           ptx::tma_load_3d(sb, j.tb, &full_bar[s], j.b_c0 + i * 64, j.b_c1, 0);
@@ -238,7 +248,7 @@ __device__ __forceinline__ void mma_tile(const Job& j, uint8_t* smem, uint8_t* s
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024, v1, SWIZZLE_128B
   const uint32_t base_lo = ptx::smem_u32(smem) >> 4;
   if (FP8 && j.fp8) {
-    const uint32_t idesc0 = epi::make_idesc_mx8(kBM, static_cast<uint32_t>(j.bn));
+    const uint32_t idesc0 = epi::make_idesc_mx8(kBM, kBN);
     const uint32_t lo_a0 = base_lo | (1u << 16);
     const uint32_t lo_b0 = (base_lo + (kABytes >> 4)) | (1u << 16);
     const uint32_t tsfa = tmem_base + kTmemSfa, tsfb = tmem_base + kTmemSfb;
@@ -259,14 +269,15 @@ __device__ __forceinline__ void mma_tile(const Job& j, uint8_t* smem, uint8_t* s
           const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (lo_a0 + so + k * 2u);
           const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (lo_b0 + so + k * 2u);
           epi::umma_mx8(tmem_base, ad, bd, epi::idesc_mx8_k(idesc0, k), (i > 0 || k > 0) ? 1u : 0u,
-                        tsfa + j.sfa_col, tsfb + j.sfb_col);
+                        tsfa, tsfb + j.sfb_col);
         }
         ptx::umma_commit(&empty_bar[s]);
       }
       __syncwarp();
     }
   } else {
-    const uint32_t idesc = ptx::make_idesc(1u, j.a_mn ? 1u : 0u, j.b_mn ? 1u : 0u, kBM, kBN);
+    const uint32_t idesc = ptx::make_idesc(1u, j.a_mn ? 1u : 0u, j.b_mn ? 1u : 0u,
+                                           static_cast<uint32_t>(j.bm), kBN);
     const uint32_t lbo_a = j.a_mn ? (8192u >> 4) : 1u, lbo_b = j.b_mn ? (8192u >> 4) : 1u;
     const uint32_t lo_a0 = base_lo | (lbo_a << 16);
     const uint32_t lo_b0 = (base_lo + (kABytes >> 4)) | (lbo_b << 16);
@@ -343,34 +354,40 @@ __device__ __forceinline__ void opt_apply(const Args& a, long long pi, int n, co
   }
 }
 
+// Accumulator rows of lane quarter q: UMMA M = 128 -> rows 32q .. 32q+31 in lanes 0..31;
+// UMMA M = 64 -> row m lives in TMEM lane (m % 16) + 32 * (m / 16): rows 16q .. 16q+15 in the
+// quarter's first 16 lanes.
+__device__ __forceinline__ int rows_per_quarter(int bm) { return bm == 64 ? 16 : 32; }
+
 // E_OPT: the accumulator tile IS the weight gradient.  Per (row, 4 columns) thread: optimizer on
-// the fp32 master (+ moments), bf16 shadow refresh; fp8 mode: the updated 32-element K-group
-// (8 neighbouring lanes) is re-quantised -- group amax by three shuffles, one UE8M0 byte, four
-// e4m3 bytes per thread; on the last step the values (optionally Byzantine-transformed) also go
-// to the upload buffers the committee and the FedAvg kernel read.
+// the fp32 master (+ moments), bf16 shadow refresh -- master / moments of this thread's elements
+// are fetched BEFORE the accumulator wait, so the update pays no exposed load latency (Adam
+// without the prefetch: +4.3 us per step, measured).  fp8 mode: the updated tile is parked in
+// the staging buffer and re-quantised one K-group (32 columns of a row) per thread.  On the last
+// step the values (optionally Byzantine-transformed) also go to the upload buffers the committee
+// and the FedAvg kernel read.
 template <bool FP8>
-__device__ __forceinline__ void epilogue_opt(const Job& j, const Args& a, int warp, int lane,
-                                             uint64_t* accum_bar, uint32_t tmem_base, float* stage_base,
+__device__ __forceinline__ void epilogue_opt(const Job& j, const Args& a, int q, int half, int lane,
+                                             uint64_t* accum_bar, uint32_t tmem_base, float* stg,
                                              Pipe& pp) {
-  const int q = warp & 3;
-  float* stg = stage_base + (warp - 2) * (32 * kStgLd);
-  const int row_base = j.m0 + q * 32;
+  const int rpq = rows_per_quarter(j.bm);
+  const int n_it = rpq / 4;                      // staged store iterations: 4 rows each
+  const int row_base = j.m0 + q * rpq;
   const int cr = lane >> 3, cg = (lane & 7) * 4;
+  const int nc = j.n0 + half * 32;               // this warp's 32 columns
   const long long pbase = reinterpret_cast<float*>(j.d) - a.master;
-  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-  // SGD: this thread's share of the parameter tile is fetched while the MMAs are still running,
-  // so the update costs no exposed load latency
-  float4 wpre[kBN / 32][8];
-  if (!a.adam) {
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32;
+  float4 wpre[8], mpre[8], vpre[8];
 #pragma unroll
-    for (int c = 0; c < kBN / 32; ++c)
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rw = row_base + it * 4 + cr, col = j.n0 + c * 32 + cg;
-        wpre[c][it] = (rw < j.M && col + 3 < j.N)
-                          ? __ldcg(reinterpret_cast<const float4*>(a.master + pbase + static_cast<long long>(rw) * j.ldd + col))
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+  for (int it = 0; it < 8; ++it) {
+    const int rw = row_base + it * 4 + cr, col = nc + cg;
+    const bool ok = it < n_it && rw < j.M && col + 3 < j.N;
+    const long long pi = pbase + static_cast<long long>(rw) * j.ldd + col;
+    wpre[it] = ok ? __ldcg(reinterpret_cast<const float4*>(a.master + pi)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.adam) {
+      mpre[it] = ok ? __ldcg(reinterpret_cast<const float4*>(a.adam_m + pi)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      vpre[it] = ok ? __ldcg(reinterpret_cast<const float4*>(a.adam_v + pi)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   const bool up = j.last && a.has_fed;
   UploadDst ud{};
@@ -379,12 +396,11 @@ __device__ __forceinline__ void epilogue_opt(const Job& j, const Args& a, int wa
   ptx::mbar_wait(accum_bar, pp.tile & 1);
   ptx::tc_fence_after_sync();
   ++pp.tile;
-  if (j.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) j.dbg[j.dbg_slot] = globaltimer_ns();
-#pragma unroll
-  for (int c = 0; c < kBN / 32; ++c) {
-    const int nc = j.n0 + c * 32;
+  const bool stampit = j.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == kEpiT0;
+  if (stampit) j.dbg[j.dbg_slot] = globaltimer_ns();
+  {
     uint32_t r[32];
-    ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+    ptx::tmem_ld_32x32b_x32(taddr, r);
     ptx::tmem_ld_wait();
     float v[32];
 #pragma unroll
@@ -393,16 +409,16 @@ __device__ __forceinline__ void epilogue_opt(const Job& j, const Args& a, int wa
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
+      if (it >= n_it) break;
       const int rr = it * 4 + cr, rw = row_base + rr, col = nc + cg;
       const bool valid = rw < j.M && col + 3 < j.N;
       const long long pi = pbase + static_cast<long long>(rw) * j.ldd + col;
       float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
       if (valid) {
         const float4 g = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cg);
+        w = wpre[it];
         if (a.adam) {
-          w = __ldcg(reinterpret_cast<const float4*>(a.master + pi));
-          float4 m = __ldcg(reinterpret_cast<const float4*>(a.adam_m + pi));
-          float4 s = __ldcg(reinterpret_cast<const float4*>(a.adam_v + pi));
+          float4 m = mpre[it], s = vpre[it];
           const float b1 = a.beta1, b2 = a.beta2, c1 = 1.f - a.beta1, c2 = 1.f - a.beta2;
           m.x = b1 * m.x + c1 * g.x; m.y = b1 * m.y + c1 * g.y; m.z = b1 * m.z + c1 * g.z; m.w = b1 * m.w + c1 * g.w;
           s.x = b2 * s.x + c2 * g.x * g.x; s.y = b2 * s.y + c2 * g.y * g.y;
@@ -414,7 +430,6 @@ __device__ __forceinline__ void epilogue_opt(const Job& j, const Args& a, int wa
           *reinterpret_cast<float4*>(a.adam_m + pi) = m;
           *reinterpret_cast<float4*>(a.adam_v + pi) = s;
         } else {
-          w = wpre[c][it];
           w.x -= a.lr * g.x; w.y -= a.lr * g.y; w.z -= a.lr * g.z; w.w -= a.lr * g.w;
         }
         *reinterpret_cast<float4*>(a.master + pi) = w;
@@ -434,17 +449,17 @@ __device__ __forceinline__ void epilogue_opt(const Job& j, const Args& a, int wa
       if (FP8) *reinterpret_cast<float4*>(stg + rr * kStgLd + cg) = w;
     }
     if (FP8) {
-      // One thread per row of the staged 32 x 32 sub-tile: its 32 columns are exactly one K-group
-      // of the weight matrix -> amax, UE8M0 byte and 32 e4m3 bytes without any shuffle, two
-      // 16-byte stores (the shuffle-per-4-columns version cost 3.7 us per step, measured).
+      // One thread per row of the staged sub-tile: its 32 columns are exactly one K-group of the
+      // weight matrix -> amax, UE8M0 byte and 32 e4m3 bytes without any shuffle, two 16-byte
+      // stores (a shuffle-per-4-columns version cost 3.7 us per step, measured).
       __syncwarp();
       const int rw = row_base + lane;
       const int nv = j.N - nc < 32 ? j.N - nc : 32;          // valid columns of this group (multiple of 4)
-      if (rw < j.M && nv > 0) {
-        float v[32];
-        stage_get(stg, lane, v);
+      if (lane < rpq && rw < j.M && nv > 0) {
+        float x[32];
+        stage_get(stg, lane, x);
         uint32_t w8[8];
-        const int e = epi::mx8_quant32(v, w8);
+        const int e = epi::mx8_quant32(x, w8);
         uint4* qd = reinterpret_cast<uint4*>(qblob + j.q_off + static_cast<long long>(rw) * j.ldq + nc);
         qd[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
         if (nv > 16) qd[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
@@ -454,43 +469,40 @@ __device__ __forceinline__ void epilogue_opt(const Job& j, const Args& a, int wa
     __syncwarp();
   }
   ptx::tc_fence_before_sync();
-  if (j.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) j.dbg[j.dbg_slot + 1] = globaltimer_ns();
+  if (stampit) j.dbg[j.dbg_slot + 1] = globaltimer_ns();
 }
 
-// epilogue warps 2..5; `warp` is the hardware warp index
+// epilogue warps 4..11: q = TMEM lane quarter, half = which 32 of the tile's 64 columns
 template <bool FP8>
-__device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int warp, int lane,
+__device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int q, int half, int lane,
                                               uint64_t* accum_bar, uint32_t tmem_base,
-                                              float* stage_base, float* sbias, Pipe& pp) {
-  const int q = warp & 3;
-  float* stg = stage_base + (warp - 2) * (32 * kStgLd);
+                                              float* stg, float* sbias, Pipe& pp) {
   {
-    const int et = threadIdx.x - 64;
+    const int et = threadIdx.x - kEpiT0;
     // coherent (L2) loads: the biases are rewritten by the optimizer phase of this same kernel
-    for (int i = et; i < kBN; i += 128)
-      sbias[i] = (j.bias != nullptr && j.n0 + i < j.N) ? __ldcg(j.bias + j.n0 + i) : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (et < kBN) sbias[et] = (j.bias != nullptr && j.n0 + et < j.N) ? __ldcg(j.bias + j.n0 + et) : 0.f;
+    epi_bar();
   }
   if (j.mode == E_OPT) {
-    epilogue_opt<FP8>(j, a, warp, lane, accum_bar, tmem_base, stage_base, pp);
+    epilogue_opt<FP8>(j, a, q, half, lane, accum_bar, tmem_base, stg, pp);
     return;
   }
-  const int row_base = j.m0 + q * 32;
+  const int rpq = rows_per_quarter(j.bm);
+  const int row_base = j.m0 + q * rpq;
   const int row = row_base + lane;
-  const bool row_ok = row < j.M;
-  const int n_chunks = (FP8 && j.fp8) ? j.bn / 32 : kBN / 32;
+  const bool row_ok = lane < rpq && row < j.M;
   const int cr = lane >> 3, cg = (lane & 7) * 4;
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
   ptx::mbar_wait(accum_bar, pp.tile & 1);
   ptx::tc_fence_after_sync();
   ++pp.tile;
-  if (j.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) j.dbg[j.dbg_slot] = globaltimer_ns();
+  const bool stampit = j.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == kEpiT0;
+  if (stampit) j.dbg[j.dbg_slot] = globaltimer_ns();
 
   if (j.mode != E_XENT) {
-#pragma unroll 1
-    for (int c = 0; c < n_chunks; ++c) {
-      const int nc = j.n0 + c * 32;
-      if (nc >= j.N) break;
+    const int c = half;
+    const int nc = j.n0 + c * 32;
+    if (nc < j.N) {
       uint32_t r[32];
       ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
       ptx::tmem_ld_wait();
@@ -515,7 +527,7 @@ __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int w
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + cr, rw = row_base + rr, col = nc + cg;
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rw < j.M && col + 3 < j.N) {
+          if (rr < rpq && rw < j.M && col + 3 < j.N) {
             const uint2 u = __ldcg(reinterpret_cast<const uint2*>(j.aux + static_cast<long long>(rw) * j.ldd + col));
             const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
             const float2 hi2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
@@ -535,7 +547,7 @@ __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int w
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int rr = it * 4 + cr, rw = row_base + rr, col = nc + cg;
-        if (rw >= j.M || col >= j.N) continue;
+        if (rr >= rpq || rw >= j.M || col >= j.N) continue;
         const float4 x = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cg);
         const long long off = static_cast<long long>(rw) * j.ldd + col;
         if (j.mode == E_F32) {
@@ -551,13 +563,14 @@ __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int w
         }
       }
       if (j.colsum != nullptr) {
-        const float tot = col_sum32(stg, lane, min(32, j.M - row_base));
+        const float tot = col_sum32(stg, lane, min(rpq, j.M - row_base));
         if (nc + lane < j.N) atomicAdd(j.colsum + nc + lane, tot);
       }
       __syncwarp();
     }
-  } else {
-    // softmax cross-entropy over the N (<= 64) logits of each row
+  } else if (half == 0) {
+    // softmax cross-entropy over the N (<= 64) logits of each row (plan 0 only: general hidden
+    // sizes; one thread owns a whole row, the second half of the epilogue warps idles)
     const int32_t label = row_ok ? j.labels[row] : -1;
     float vmax = -INFINITY, zlab = 0.f;
     int amax = -1;
@@ -620,129 +633,64 @@ __device__ __forceinline__ void epilogue_tile(const Job& j, const Args& a, int w
     }
   }
   ptx::tc_fence_before_sync();
-  if (j.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) j.dbg[j.dbg_slot + 1] = globaltimer_ns();
+  if (stampit) j.dbg[j.dbg_slot + 1] = globaltimer_ns();
 }
 
 // ---------------------------------------------------------------- fused chain of one 128-row tile
-//   fwd1  acc[128 x 256] = x W1^T            (plan 1 only: TMA ring, 13 K-blocks)  TMEM cols [0,256)
-//   E1    h = relu(acc + b1) -> bf16 -> smem (128B-swizzled K-major = fwd2's A operand) + global
-//         (plan 3: h was produced by P1 and arrives by TMA -- bf16, or e4m3 + scale chunks)
+//   (h was produced by P1 and arrives by TMA -- bf16, or e4m3 + scale chunks)
 //   fwd2  logits[128 x 64] = h W2^T          (A, B from smem)                    TMEM cols [256,320)
-//   E2    softmax-xent per row (one thread owns a row) -> dlogits -> smem (dh's A operand) + global
+//   E2    softmax-xent per row -> dlogits -> smem (dh's A operand) + global
 //   dh    acc[128 x 64 slice] = dlogits W2   (B = W2 MN-major)                   TMEM cols [0,64)
 //   E3    dh = acc * relu'(h) -> bf16 global, db1
 // logits / dlogits never make the global -> TMA round trip; the three GEMMs cost one grid barrier.
+// Four CTAs per M-tile: all redo the cheap fwd2 + xent so that the dh GEMM and its epilogue run
+// 4-wide (64 hidden columns each); loss, db2 and the global dlogits copy are done by one of them.
 template <bool FP8>
 __device__ __forceinline__ void chain_produce(const Maps& maps, const Args& a, uint8_t* smem, uint8_t* sf_smem,
-                                              const ChainBars& cb, CPipe& cp, int r0, int m0, int mode,
-                                              int slice) {
-  const uint32_t par = cp.n & 1;
-  const int row0 = r0 + m0;
-  const bool f1 = mode == 1;
-  if (!f1) {
-    // h was produced by P1: TMA drops its 128 x 256 tile straight into the swizzled A-operand
-    // slots; both W2 forms can be fetched at once (no fwd1 stages to alias).  This CTA computes
-    // only hidden columns [64*slice, 64*slice+64) of dh: one 8 KB chunk of W2^T.
-    if (ptx::elect_one()) {
-      if (FP8) {
-        // e4m3: two K-blocks of 128 hidden units each, plus their scale chunks
-        ptx::mbar_expect_tx(cb.w2k, 2 * 8192 + 2 * kSfChunk);
-        ptx::mbar_expect_tx(&cb.full[0], 2 * 16384 + 2 * kSfChunk);
-        ptx::mbar_expect_tx(cb.w2mn, 8192);
+                                              const ChainBars& cb, int m0, int slice) {
+  if (ptx::elect_one()) {
+    if (FP8) {
+      // e4m3: two K-blocks of 128 hidden units each, plus their scale chunks
+      ptx::mbar_expect_tx(cb.w2k, 2 * 8192 + 2 * kSfChunk);
+      ptx::mbar_expect_tx(cb.h, 2 * 16384 + 2 * kSfChunk);
+      ptx::mbar_expect_tx(cb.w2mn, 8192);
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          ptx::tma_load_3d(smem + kOffH + kb * 16384, &maps.hq_k, &cb.full[0], kb * 128, m0, 0);
-          epi::bulk_g2s(sf_smem + kb * kSfChunk,
-                        a.h_sf + (static_cast<long long>(m0 >> 7) * a.ql.kb2 + kb) * kSfChunk, kSfChunk, &cb.full[0]);
-        }
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          ptx::tma_load_3d(smem + kOffW2K + kb * 8192, &maps.w2q_k, cb.w2k, kb * 128, 0, 0);
-          epi::bulk_g2s(sf_smem + (2 + kb) * kSfChunk, a.work_q + a.ql.w2sf + kb * kSfChunk, kSfChunk, cb.w2k);
-        }
-        ptx::tma_load_3d(smem + kOffW2MN, &maps.w2_mn, cb.w2mn, slice * 64, 0, 0);
-      } else {
-        ptx::mbar_expect_tx(cb.w2k, 32768);
-        ptx::mbar_expect_tx(&cb.full[0], 65536);
-        ptx::mbar_expect_tx(cb.w2mn, 8192);
-        // in the order the chain consumes them: h and W2 (fwd2) first, W2^T (dh) last
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb)
-          ptx::tma_load_3d(smem + kOffH + kb * 16384, &maps.h_k, &cb.full[0], kb * 64, m0, 0);
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb)
-          ptx::tma_load_3d(smem + kOffW2K + kb * 8192, &maps.w2_k, cb.w2k, kb * 64, 0, 0);
-        ptx::tma_load_3d(smem + kOffW2MN, &maps.w2_mn, cb.w2mn, slice * 64, 0, 0);
+      for (int kb = 0; kb < 2; ++kb) {
+        ptx::tma_load_3d(smem + kOffH + kb * 16384, &maps.hq_k, cb.h, kb * 128, m0, 0);
+        epi::bulk_g2s(sf_smem + kb * kSfChunk,
+                      a.h_sf + (static_cast<long long>(m0 >> 7) * a.ql.kb2 + kb) * kSfChunk, kSfChunk, cb.h);
       }
-    }
-    __syncwarp();
-    ++cp.n;
-    return;
-  }
-  if (ptx::elect_one()) {
-    ptx::mbar_expect_tx(cb.w2k, 32768);
 #pragma unroll
-    for (int kb = 0; kb < 4; ++kb)
-      ptx::tma_load_3d(smem + kOffW2K + kb * 8192, &maps.w2_k, cb.w2k, kb * 64, 0, 0);
+      for (int kb = 0; kb < 2; ++kb) {
+        ptx::tma_load_3d(smem + kOffW2K + kb * 8192, &maps.w2q_k, cb.w2k, kb * 128, 0, 0);
+        epi::bulk_g2s(sf_smem + (2 + kb) * kSfChunk, a.work_q + a.ql.w2sf + kb * kSfChunk, kSfChunk, cb.w2k);
+      }
+      ptx::tma_load_3d(smem + kOffW2MN, &maps.w2_mn, cb.w2mn, slice * 64, 0, 0);
+    } else {
+      ptx::mbar_expect_tx(cb.w2k, 32768);
+      ptx::mbar_expect_tx(cb.h, 65536);
+      ptx::mbar_expect_tx(cb.w2mn, 8192);
+      // in the order the chain consumes them: h and W2 (fwd2) first, W2^T (dh) last
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb)
+        ptx::tma_load_3d(smem + kOffH + kb * 16384, &maps.h_k, cb.h, kb * 64, m0, 0);
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb)
+        ptx::tma_load_3d(smem + kOffW2K + kb * 8192, &maps.w2_k, cb.w2k, kb * 64, 0, 0);
+      ptx::tma_load_3d(smem + kOffW2MN, &maps.w2_mn, cb.w2mn, slice * 64, 0, 0);
+    }
   }
   __syncwarp();
-  const int kb_d = (a.in_dim + 63) / 64;
-  for (int i = 0; i < kb_d; ++i, ++cp.it) {
-    const int s = cp.it % kCStages;
-    const uint32_t ph = (cp.it / kCStages) & 1;
-    ptx::mbar_wait(&cb.empty[s], ph ^ 1);
-    if (ptx::elect_one()) {
-      uint8_t* sa = smem + s * kCStage;
-      ptx::mbar_expect_tx(&cb.full[s], kCStage);
-      ptx::tma_load_3d(sa, &maps.x_k, &cb.full[s], i * 64, row0, 0);
-      ptx::tma_load_3d(sa + kCA, &maps.w1_k256, &cb.full[s], i * 64, 0, 0);
-    }
-    __syncwarp();
-  }
-  ptx::mbar_wait(cb.acc_h, par);   // every fwd1 MMA has retired: the stage memory is free
-  if (ptx::elect_one()) {
-    ptx::mbar_expect_tx(cb.w2mn, 32768);
-#pragma unroll
-    for (int jn = 0; jn < 4; ++jn)
-      ptx::tma_load_3d(smem + kOffW2MN + jn * 8192, &maps.w2_mn, cb.w2mn, jn * 64, 0, 0);
-  }
-  __syncwarp();
-  ++cp.n;
 }
 
 template <bool FP8>
-__device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, uint8_t* sf_smem, const ChainBars& cb,
-                                          uint32_t tmem_base, CPipe& cp, int mode) {
-  const bool f1 = mode == 1;
-  const uint32_t par = cp.n & 1;
+__device__ __forceinline__ void chain_mma(uint8_t* smem, uint8_t* sf_smem, const ChainBars& cb,
+                                          uint32_t tmem_base, uint32_t par) {
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   const uint32_t base_lo = ptx::smem_u32(smem) >> 4;
-  const int kb_d = (a.in_dim + 63) / 64;
-  // fwd1: 128 x 256 x in_dim
-  const uint32_t id1 = ptx::make_idesc(1u, 0u, 0u, kBM, 256);
-  for (int i = 0; f1 && i < kb_d; ++i, ++cp.it) {
-    const int s = cp.it % kCStages;
-    const uint32_t ph = (cp.it / kCStages) & 1;
-    ptx::mbar_wait(&cb.full[s], ph);
-    ptx::tc_fence_after_sync();
-    if (ptx::elect_one()) {
-      const uint32_t lo_a = (base_lo + static_cast<uint32_t>(s) * (kCStage >> 4)) | (1u << 16);
-      const uint32_t lo_b = lo_a + (kCA >> 4);
-#pragma unroll
-      for (uint32_t k = 0; k < 4; ++k)
-        ptx::umma_f16(tmem_base, (static_cast<uint64_t>(hi) << 32) | (lo_a + k * 2u),
-                      (static_cast<uint64_t>(hi) << 32) | (lo_b + k * 2u), id1, (i > 0 || k > 0) ? 1u : 0u);
-      ptx::umma_commit(&cb.empty[s]);
-    }
-    __syncwarp();
-  }
-  if (f1) {
-    if (ptx::elect_one()) ptx::umma_commit(cb.acc_h);
-    __syncwarp();
-  }
-  // fwd2: 128 x 64 x 256, A = h (smem: written by the epilogue warps, or by TMA), B = W2 K-major
+  // fwd2: 128 x 64 x 256, A = h (TMA), B = W2 K-major
   ptx::mbar_wait(cb.w2k, par);
-  ptx::mbar_wait(f1 ? cb.h_ready : &cb.full[0], par);
+  ptx::mbar_wait(cb.h, par);
   ptx::tc_fence_after_sync();
   if (ptx::elect_one()) {
     const uint32_t lo_a0 = (base_lo + (static_cast<uint32_t>(kOffH) >> 4)) | (1u << 16);
@@ -774,12 +722,12 @@ __device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, uint8_t*
     ptx::umma_commit(cb.acc_l);
   }
   __syncwarp();
-  // dh: 128 x 256 x 64, A = dlogits (smem), B = W2 MN-major (4 chunks of 64 hidden columns)
+  // dh: 128 x 64 x 64, A = dlogits (smem, written by the epilogue warps), B = W2 MN-major slice
   ptx::mbar_wait(cb.w2mn, par);
   ptx::mbar_wait(cb.dl_ready, par);
   ptx::tc_fence_after_sync();
   if (ptx::elect_one()) {
-    const uint32_t id3 = ptx::make_idesc(1u, 0u, 1u, kBM, f1 ? 256 : 64);   // !f1: one 64-column slice
+    const uint32_t id3 = ptx::make_idesc(1u, 0u, 1u, kBM, 64);
     const uint32_t lo_a0 = (base_lo + (static_cast<uint32_t>(kOffDL) >> 4)) | (1u << 16);
     const uint32_t lo_b0 = (base_lo + (static_cast<uint32_t>(kOffW2MN) >> 4)) | ((8192u >> 4) << 16);
 #pragma unroll
@@ -789,184 +737,147 @@ __device__ __forceinline__ void chain_mma(const Args& a, uint8_t* smem, uint8_t*
     ptx::umma_commit(cb.acc_dh);
   }
   __syncwarp();
-  ++cp.n;
 }
 
+// Epilogue of the chain.  Thread (q, half, lane) owns row rl = 32q + lane of the M-tile and the
+// column half `half`: logits [32 half, +32) in E2, hidden columns [32 half, +32) of this CTA's
+// 64-column dh slice in E3.  The two threads of a row combine their softmax partials through a
+// small smem exchange (xch) around two 256-thread named barriers.
 template <bool FP8>
 __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, const ChainBars& cb,
-                                               uint32_t tmem_base, int warp, int lane, float* stage_base,
-                                               float* sb, CPipe& cp, int m0, int r0, int mode, int slice,
+                                               uint32_t tmem_base, int q, int half, int lane, float* stg,
+                                               float* sb, float* xch, uint32_t par, int m0, int r0, int slice,
                                                unsigned long long* dbg) {
-  const bool f1 = mode == 1;
-  const uint32_t par = cp.n & 1;
   auto stampc = [&](int slot) {
-    if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) dbg[slot] = globaltimer_ns();
+    if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == kEpiT0) dbg[slot] = globaltimer_ns();
   };
-  const int q = warp & 3;
   const int rl = q * 32 + lane;        // row inside the tile == TMEM lane
   const int row = m0 + rl;             // row inside the mini-batch
   const bool row_ok = row < a.B;
   const int32_t label = row_ok ? __ldg(a.labels + r0 + row) : -1;   // issued early: needed by E2
   const int C = a.n_classes;
-  float* stg = stage_base + (warp - 2) * (32 * kStgLd);
   {
-    const int et = threadIdx.x - 64;   // coherent loads: the optimizer of this kernel rewrites the biases
-    for (int i = et; i < kChainH; i += 128) sb[i] = __ldcg(a.b1 + i);
+    const int et = threadIdx.x - kEpiT0;   // coherent loads: the optimizer of this kernel rewrites the biases
+    sb[et] = __ldcg(a.b1 + et);        // kEpiThreads == kChainH == 256
     if (et < 64) sb[kChainH + et] = et < C ? __ldcg(a.b2 + et) : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    epi_bar();
   }
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  float* xmax = xch + half * 128;            const float* omax = xch + (1 - half) * 128;
+  float* xidx = xch + 256 + half * 128;      const float* oidx = xch + 256 + (1 - half) * 128;
+  float* xzl = xch + 512 + half * 128;       const float* ozl = xch + 512 + (1 - half) * 128;
+  float* xsum = xch + 768 + half * 128;      const float* osum = xch + 768 + (1 - half) * 128;
 
-  // ---- E1: h
-  uint32_t mask[8];
-  uint32_t mk[2] = {0u, 0u};     // !f1: relu mask of this CTA's 64 hidden columns
-  if (!f1) {
-    // h tile came in by TMA: only the relu mask is needed (read back through the swizzle)
-    ptx::mbar_wait(&cb.full[0], par);
+  // ---- E1: relu mask of this thread's 32 hidden columns [64 slice + 32 half, +32), read back
+  //          through the swizzle from the h tile the TMA dropped into the A-operand slots
+  uint32_t mk = 0u;
+  ptx::mbar_wait(cb.h, par);
+  stampc(6);
+  {
     const uint8_t* hs = smem + kOffH;
     if (FP8) {
       // e4m3: K-block (slice / 2) holds hidden units [128 * (slice / 2), +128), one byte each
       const uint8_t* tile = hs + (slice >> 1) * 16384;
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const uint4 u = epi::ld_sw128(tile, rl, (slice & 1) * 4 + jj);
+      for (int jj = 0; jj < 2; ++jj) {
+        const uint4 u = epi::ld_sw128(tile, rl, (slice & 1) * 4 + half * 2 + jj);
         const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
-        uint32_t m = 0;
 #pragma unroll
         for (int e = 0; e < 4; ++e)
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             const uint32_t byte = (wds[e] >> (8 * b)) & 0xFFu;   // e4m3 > 0  <=>  sign clear, not zero
-            m |= ((byte != 0u && (byte & 0x80u) == 0u) ? 1u : 0u) << (e * 4 + b);
+            mk |= ((byte != 0u && (byte & 0x80u) == 0u) ? 1u : 0u) << (jj * 16 + e * 4 + b);
           }
-        mk[jj >> 1] |= m << ((jj & 1) * 16);
       }
     } else {
+      const int c = 2 * slice + half;       // 32-column chunk of the 256 hidden units
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = 2 * slice + cc;
-        uint32_t m = 0;
+      for (int jj = 0; jj < 4; ++jj) {
+        const uint4 u = epi::ld_sw128(hs + (c >> 1) * 16384, rl, (c & 1) * 4 + jj);
+        const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const uint4 u = epi::ld_sw128(hs + (c >> 1) * 16384, rl, (c & 1) * 4 + jj);
-          const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            // bf16 > 0  <=>  sign clear and not zero
-            m |= (((wds[e] & 0xFFFFu) != 0u && (wds[e] & 0x8000u) == 0u) ? 1u : 0u) << (jj * 8 + e * 2);
-            m |= (((wds[e] >> 16) != 0u && (wds[e] & 0x80000000u) == 0u) ? 1u : 0u) << (jj * 8 + e * 2 + 1);
-          }
-        }
-        mk[cc] = m;
-      }
-    }
-    stampc(6);
-  } else {
-    ptx::mbar_wait(cb.acc_h, par);
-    ptx::tc_fence_after_sync();
-    stampc(6);
-    {
-      uint8_t* hs = smem + kOffH;
-      __nv_bfloat16* hg = a.h + static_cast<long long>(row) * a.hidden;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
-        ptx::tmem_ld_wait();
-        uint32_t pk[16];
-        uint32_t m = 0;
-#pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          const float v0 = fmaxf(__uint_as_float(r[k]) + sb[c * 32 + k], 0.f);
-          const float v1 = fmaxf(__uint_as_float(r[k + 1]) + sb[c * 32 + k + 1], 0.f);
-          m |= (v0 > 0.f ? 1u : 0u) << k;
-          m |= (v1 > 0.f ? 1u : 0u) << (k + 1);
-          pk[k >> 1] = pack2(v0, v1);
-        }
-        mask[c] = m;
-        uint8_t* tile = hs + (c >> 1) * 16384;
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const uint4 v = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
-          st_sw128(tile, rl, (c & 1) * 4 + jj, v);
-          if (row_ok) reinterpret_cast<uint4*>(hg + c * 32)[jj] = v;
+        for (int e = 0; e < 4; ++e) {
+          // bf16 > 0  <=>  sign clear and not zero
+          mk |= (((wds[e] & 0xFFFFu) != 0u && (wds[e] & 0x8000u) == 0u) ? 1u : 0u) << (jj * 8 + e * 2);
+          mk |= (((wds[e] >> 16) != 0u && (wds[e] & 0x80000000u) == 0u) ? 1u : 0u) << (jj * 8 + e * 2 + 1);
         }
       }
     }
-    ptx::fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor core
-    ptx::tc_fence_before_sync();
-    ptx::mbar_arrive(cb.h_ready);
   }
   stampc(7);
 
-  // ---- E2: softmax cross-entropy of the row
+  // ---- E2: softmax cross-entropy of the row, 32 logits per thread
   ptx::mbar_wait(cb.acc_l, par);
   ptx::tc_fence_after_sync();
   stampc(8);
   {
-    // Latency matters more than instruction count here (one warp per SM sub-partition): both
-    // TMEM loads are in flight together, and max / argmax / sum use four independent chains.
-    float z[64];
+    float z[32];
     {
-      uint32_t ra[32], rb[32];
-      ptx::tmem_ld_32x32b_x32(taddr + 256, ra);
-      ptx::tmem_ld_32x32b_x32(taddr + 288, rb);
+      uint32_t ra[32];
+      ptx::tmem_ld_32x32b_x32(taddr + 256 + half * 32, ra);
       ptx::tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        z[k] = __uint_as_float(ra[k]) + sb[kChainH + k];
-        z[32 + k] = __uint_as_float(rb[k]) + sb[kChainH + 32 + k];
-      }
+      for (int k = 0; k < 32; ++k) z[k] = __uint_as_float(ra[k]) + sb[kChainH + half * 32 + k];
     }
+    const int nb = half * 32;
     float pm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     int pi[4] = {-1, -1, -1, -1};
     float zlab = 0.f;
 #pragma unroll
-    for (int n = 0; n < 64; ++n) {
-      if (n < C) {
-        if (z[n] > pm[n & 3]) { pm[n & 3] = z[n]; pi[n & 3] = n; }
-        if (n == label) zlab = z[n];
+    for (int k = 0; k < 32; ++k) {
+      if (nb + k < C) {
+        if (z[k] > pm[k & 3]) { pm[k & 3] = z[k]; pi[k & 3] = nb + k; }
+        if (nb + k == label) zlab = z[k];
       }
     }
     float vmax = pm[0];
     int amax = pi[0];
 #pragma unroll
-    for (int jq = 1; jq < 4; ++jq)   // first maximum wins, as in the serial scan
+    for (int jq = 1; jq < 4; ++jq)   // first maximum wins, as in a serial scan
       if (pm[jq] > vmax || (pm[jq] == vmax && pi[jq] >= 0 && pi[jq] < amax)) { vmax = pm[jq]; amax = pi[jq]; }
+    xmax[rl] = vmax; xidx[rl] = __int_as_float(amax); xzl[rl] = zlab;
+    epi_bar();
+    {
+      const float ov = omax[rl];
+      const int oi = __float_as_int(oidx[rl]);
+      // the lower half holds the lower class indices: it wins ties
+      const bool take = half == 0 ? (ov > vmax) : (ov >= vmax && oi >= 0);
+      if (take) { vmax = ov; amax = oi; }
+      zlab += ozl[rl];
+    }
     stampc(12);
     float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int n = 0; n < 64; ++n) {   // z <- exp(z - max): each exponential is evaluated once
-      z[n] = n < C ? __expf(z[n] - vmax) : 0.f;
-      ps[n & 3] += z[n];
+    for (int k = 0; k < 32; ++k) {   // z <- exp(z - max): each exponential is evaluated once
+      z[k] = nb + k < C ? __expf(z[k] - vmax) : 0.f;
+      ps[k & 3] += z[k];
     }
-    const float sum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+    const float psum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+    xsum[rl] = psum;
+    epi_bar();
+    const float sum = psum + osum[rl];
     const float inv = 1.f / sum;
-    float loss = row_ok ? (__logf(sum) + vmax - zlab) : 0.f;
-    const bool hit = row_ok && (amax == label);
     const float gs = 1.f / static_cast<float>(a.B);
     // the 4 slice-CTAs of an M-tile all need dlogits in smem, but the bookkeeping is done once:
-    const bool do_colsum = f1 || slice == 1, do_global = f1 || slice == 2, do_loss = f1 || slice == 3;
+    const bool do_colsum = slice == 1, do_global = slice == 2, do_loss = slice == 3 && half == 0;
     uint8_t* dls = smem + kOffDL;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       float v[32];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const int n = c * 32 + k;
-        v[k] = (n < C && row_ok) ? (z[n] * inv - (n == label ? 1.f : 0.f)) * gs : 0.f;
-      }
+      for (int k = 0; k < 32; ++k)
+        v[k] = (nb + k < C && row_ok) ? (z[k] * inv - (nb + k == label ? 1.f : 0.f)) * gs : 0.f;
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const uint4 u = make_uint4(pack2(v[8 * jj], v[8 * jj + 1]), pack2(v[8 * jj + 2], v[8 * jj + 3]),
                                    pack2(v[8 * jj + 4], v[8 * jj + 5]), pack2(v[8 * jj + 6], v[8 * jj + 7]));
-        st_sw128(dls, rl, c * 4 + jj, u);
+        st_sw128(dls, rl, half * 4 + jj, u);
       }
       if (do_colsum) {
         stage_put(stg, lane, v);
         __syncwarp();
         const float tot = col_sum32(stg, lane, 32);
-        if (c * 32 + lane < C) atomicAdd(a.gb2 + c * 32 + lane, tot);
+        if (nb + lane < C) atomicAdd(a.gb2 + nb + lane, tot);
         __syncwarp();
       }
     }
@@ -976,97 +887,67 @@ __device__ __forceinline__ void chain_epilogue(const Args& a, uint8_t* smem, con
     ptx::tc_fence_before_sync();
     ptx::mbar_arrive(cb.dl_ready);
     stampc(14);
-    // dlogits -> global for dW2, read back out of the swizzled tile so that one store
-    // instruction covers 4 whole rows (a row-per-thread store touches 32 lines per instruction)
+    // dlogits -> global for dW2, read back out of the swizzled tile: one store instruction covers
+    // 8 rows x this half's 64 bytes (a row-per-thread store touches 32 lines per instruction)
     __syncwarp();
     if (do_global) {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rt = q * 32 + it * 4 + (lane >> 3), ch = lane & 7;
+      for (int it = 0; it < 4; ++it) {
+        const int rt = q * 32 + it * 8 + (lane >> 2), ch = half * 4 + (lane & 3);
         const uint4 u = epi::ld_sw128(dls, rt, ch);
         if (m0 + rt < a.B && ch * 8 < a.ncp)
           *reinterpret_cast<uint4*>(a.dlogits + static_cast<long long>(m0 + rt) * a.ncp + ch * 8) = u;
       }
     }
+    if (do_loss) {
+      float loss = row_ok ? (__logf(sum) + vmax - zlab) : 0.f;
+      const bool hit = row_ok && (amax == label);
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, off);
-    const unsigned cnt = __popc(__ballot_sync(0xffffffffu, hit));
-    if (lane == 0 && do_loss) {
-      atomicAdd(a.loss_sum, loss);
-      if (cnt) atomicAdd(a.correct, cnt);
+      for (int off = 16; off >= 1; off >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, off);
+      const unsigned cnt = __popc(__ballot_sync(0xffffffffu, hit));
+      if (lane == 0) {
+        atomicAdd(a.loss_sum, loss);
+        if (cnt) atomicAdd(a.correct, cnt);
+      }
     }
   }
   stampc(9);
 
-  // ---- E3: dh = (dlogits W2) * relu'(h), db1
+  // ---- E3: dh = (dlogits W2) * relu'(h), db1 -- 32 hidden columns per thread
   ptx::mbar_wait(cb.acc_dh, par);
   ptx::tc_fence_after_sync();
   stampc(10);
   {
-    // The h tile at kOffH is dead (fwd2 retired before acc_l, the mask is in registers): it
-    // becomes a bf16 staging tile so that dh leaves the SM in whole rows per store instruction
-    // instead of 32 scattered 16-byte pieces.
+    // The h tile at kOffH is dead (fwd2 retired before acc_l, the mask is in registers): its first
+    // 16 KB become a bf16 staging tile (128 rows x 128 bytes) so that dh leaves the SM 8 rows x 64
+    // bytes per store instruction instead of 32 scattered 16-byte pieces.
     uint8_t* ds = smem + kOffH;
-    if (!f1) {
-      // 64-column slice: 128-byte staging rows, 4 whole rows per store instruction
+    uint32_t r[32];
+    ptx::tmem_ld_32x32b_x32(taddr + half * 32, r);
+    ptx::tmem_ld_wait();
+    float v[32];
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(taddr + cc * 32, r);
-        ptx::tmem_ld_wait();
-        float v[32];
+    for (int k = 0; k < 32; ++k) v[k] = ((mk >> k) & 1u) ? __uint_as_float(r[k]) : 0.f;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = ((mk[cc] >> k) & 1u) ? __uint_as_float(r[k]) : 0.f;
+    for (int jj = 0; jj < 4; ++jj)
+      st_sw128(ds, rl, half * 4 + jj,
+               make_uint4(pack2(v[8 * jj], v[8 * jj + 1]), pack2(v[8 * jj + 2], v[8 * jj + 3]),
+                          pack2(v[8 * jj + 4], v[8 * jj + 5]), pack2(v[8 * jj + 6], v[8 * jj + 7])));
+    stage_put(stg, lane, v);
+    __syncwarp();
+    const float tot = col_sum32(stg, lane, 32);
+    atomicAdd(a.gb1 + (2 * slice + half) * 32 + lane, tot);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-          st_sw128(ds, rl, cc * 4 + jj,
-                   make_uint4(pack2(v[8 * jj], v[8 * jj + 1]), pack2(v[8 * jj + 2], v[8 * jj + 3]),
-                              pack2(v[8 * jj + 4], v[8 * jj + 5]), pack2(v[8 * jj + 6], v[8 * jj + 7])));
-        stage_put(stg, lane, v);
-        __syncwarp();
-        const float tot = col_sum32(stg, lane, 32);
-        atomicAdd(a.gb1 + (2 * slice + cc) * 32 + lane, tot);
-        __syncwarp();
-      }
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rt = q * 32 + it * 4 + (lane >> 3), ch = lane & 7;
-        const uint4 u = epi::ld_sw128(ds, rt, ch);
-        if (m0 + rt < a.B)
-          *reinterpret_cast<uint4*>(a.dh + static_cast<long long>(m0 + rt) * a.hidden + slice * 64 + ch * 8) = u;
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
-        ptx::tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = ((mask[c] >> k) & 1u) ? __uint_as_float(r[k]) : 0.f;
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-          *reinterpret_cast<uint4*>(ds + rl * 512 + (((c * 4 + jj) ^ (rl & 7)) << 4)) =
-              make_uint4(pack2(v[8 * jj], v[8 * jj + 1]), pack2(v[8 * jj + 2], v[8 * jj + 3]),
-                         pack2(v[8 * jj + 4], v[8 * jj + 5]), pack2(v[8 * jj + 6], v[8 * jj + 7]));
-        stage_put(stg, lane, v);
-        __syncwarp();
-        const float tot = col_sum32(stg, lane, 32);
-        atomicAdd(a.gb1 + c * 32 + lane, tot);
-        __syncwarp();
-      }
-#pragma unroll 8
-      for (int rr = 0; rr < 32; ++rr) {
-        const int rt = q * 32 + rr;
-        if (m0 + rt >= a.B) break;
-        const uint4 u = *reinterpret_cast<const uint4*>(ds + rt * 512 + ((lane ^ (rt & 7)) << 4));
-        *reinterpret_cast<uint4*>(a.dh + static_cast<long long>(m0 + rt) * a.hidden + lane * 8) = u;
-      }
+    for (int it = 0; it < 4; ++it) {
+      const int rt = q * 32 + it * 8 + (lane >> 2), ch = half * 4 + (lane & 3);
+      const uint4 u = epi::ld_sw128(ds, rt, ch);
+      if (m0 + rt < a.B)
+        *reinterpret_cast<uint4*>(a.dh + static_cast<long long>(m0 + rt) * a.hidden + slice * 64 + ch * 8) = u;
     }
+    __syncwarp();
   }
   ptx::tc_fence_before_sync();
   stampc(11);
-  ++cp.n;
 }
 
 // Device-wide barrier between phases.  All CTAs are co-resident (one per SM), the counter
@@ -1107,11 +988,12 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kTileBytes + kSfBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* accum_bar = empty_bar + kStages;
-  uint64_t* cbar = accum_bar + 1;      // chain barriers: full[3] empty[3] + 7 single-use
-  ChainBars cb{cbar, cbar + kCStages, cbar + 6, cbar + 7, cbar + 8, cbar + 9, cbar + 10, cbar + 11, cbar + 12};
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cbar + 13);
+  uint64_t* cbar = accum_bar + 1;      // chain barriers
+  ChainBars cb{cbar, cbar + 1, cbar + 2, cbar + 3, cbar + 4, cbar + 5};
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cbar + 6);
   float* stage_base = reinterpret_cast<float*>(smem + kTileBytes + kSfBytes + kBarBytes);
-  float* sbias = stage_base + 4 * 32 * kStgLd;
+  float* sbias = stage_base + kEpiWarps * 32 * kStgLd;
+  float* xch = sbias + kBiasFloats;
 
   ptx::pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1121,13 +1003,9 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
       ptx::mbar_init(&empty_bar[s], 1);
     }
     ptx::mbar_init(accum_bar, 1);
-    for (int s = 0; s < kCStages; ++s) {
-      ptx::mbar_init(&cb.full[s], 1);
-      ptx::mbar_init(&cb.empty[s], 1);
-    }
-    ptx::mbar_init(cb.w2k, 1); ptx::mbar_init(cb.w2mn, 1);
-    ptx::mbar_init(cb.acc_h, 1); ptx::mbar_init(cb.acc_l, 1); ptx::mbar_init(cb.acc_dh, 1);
-    ptx::mbar_init(cb.h_ready, 128); ptx::mbar_init(cb.dl_ready, 128);
+    ptx::mbar_init(cb.h, 1); ptx::mbar_init(cb.w2k, 1); ptx::mbar_init(cb.w2mn, 1);
+    ptx::mbar_init(cb.acc_l, 1); ptx::mbar_init(cb.acc_dh, 1);
+    ptx::mbar_init(cb.dl_ready, kEpiThreads);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, kTmemCols);
@@ -1142,33 +1020,42 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
   }
 
   Pipe pp{0u, 0u};
-  CPipe cp{0u, 0u};
+  uint32_t chains = 0;        // chains processed by this CTA (parity of the once-per-chain barriers)
   bool x_all_ready = false;   // input pipeline: every chunk of this round has been converted
   unsigned int bar_epoch = 0;
   const int t = blockIdx.x;
+  const int q = warp & 3, half = (warp - 4) >> 2;       // epilogue warps 4..11
+  float* stg = stage_base + (warp >= 4 ? warp - 4 : 0) * (32 * kStgLd);
   const int B = a.B, H = a.hidden, C = a.n_classes, D = a.in_dim;
   const int mt_b = (B + kBM - 1) / kBM;                 // M-tiles over the batch
   const int nt_h = (H + kBN - 1) / kBN;                 // N-tiles over hidden
   const int nt_d = (D + kBN - 1) / kBN;                 // N-tiles over in_dim
-  const int mt_h = (H + kBM - 1) / kBM;                 // M-tiles over hidden (dW1)
+  const int bm_w = a.bm_w;                              // weight-gradient tile height (64 | 128)
+  const int mt_hw = (H + bm_w - 1) / bm_w;              // M-tiles over hidden (dW1)
   const int kb_d = (D + 63) / 64, kb_h = (H + 63) / 64, kb_b = (B + 63) / 64, kb_c = (C + 63) / 64;
-  const int p1_bn = FP8 ? a.p1_bn : kBN;                // fwd1 tile width
-  const int p1_nt = (H + p1_bn - 1) / p1_bn;
-  const int p1_tiles = mt_b * p1_nt;
+  const int p1_tiles = mt_b * nt_h;
 
+  // The step loop exists twice, specialised per role group, so that each side of the
+  // `setmaxnreg` split is compiled against its own register budget: EPI = false is warpgroup 0
+  // (TMA producer, MMA issuer, two idle warps), EPI = true the eight epilogue warps.  Both copies
+  // execute the same sequence of CTA-wide barriers.
+  auto round_loop = [&](auto epi_tag) {
+  constexpr bool EPI = decltype(epi_tag)::value;
   auto run = [&](const Job& j) {
-    if (warp == 0) produce_tile<FP8>(j, smem, sf_smem, full_bar, empty_bar, pp);
-    else if (warp == 1) mma_tile<FP8>(j, smem, sf_smem, full_bar, empty_bar, accum_bar, tmem_base, pp);
-    else epilogue_tile<FP8>(j, a, warp, lane, accum_bar, tmem_base, stage_base, sbias, pp);
+    if constexpr (EPI) {
+      epilogue_tile<FP8>(j, a, q, half, lane, accum_bar, tmem_base, stg, sbias, pp);
+    } else {
+      if (warp == 0) produce_tile<FP8>(j, smem, sf_smem, full_bar, empty_bar, pp);
+      else if (warp == 1) mma_tile<FP8>(j, smem, sf_smem, full_bar, empty_bar, accum_bar, tmem_base, pp);
+    }
   };
 
   // Phase plan of one step (a.chain, a.epiopt pick the variant; all are numerically equivalent):
-  //   chain 1:  [fwd1 -> xent -> dh chained per M-tile]                       | B
   //   chain 3:  P1 fwd1 | [fwd2 -> xent -> dh chained per M-tile]             | B
-  //   chain 0:  P1 | P2 xent | P3 dh                                          | B
+  //   chain 0:  P1 | P2 xent | P3 dh                                          | B   (any hidden size)
   //   B = dW1 || dW2 (+ SGD/Adam in the epilogue and a bias CTA when epiopt, else a flat P5)
   auto stamp = [&](int step, int slot) {
-    if (a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64) a.dbg[step * 32 + slot] = globaltimer_ns();
+    if (a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == kEpiT0) a.dbg[step * 32 + slot] = globaltimer_ns();
   };
   for (int step = 0; step < a.steps; ++step) {
     const int r0 = step * B;
@@ -1180,67 +1067,67 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
       bc2 = 1.f - powf(a.beta2, static_cast<float>(tt));
     }
     const bool eo = a.epiopt != 0;
+    unsigned long long* sdbg = a.dbg != nullptr ? a.dbg + step * 32 : nullptr;
     stamp(step, 0);
-    if (a.chain != 1) {
-      // ---- P1: h = relu(x W1^T + b1)
-      if (t < p1_tiles) {
-        if (a.x_ready != nullptr && warp == 0 && !x_all_ready) {
-          // input pipeline: this step's rows are converted by the side-branch kernel as soon as
-          // their H2D copy lands; only the TMA producer has to wait (phase B reads them later).
-          // Once the LAST chunk is seen ready nothing is checked any more.
-          int all = 0;
-          if (lane == 0) {
-            const unsigned int want = __ldcg(a.round_seq);
-            unsigned int v;
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.x_ready + a.steps - 1) : "memory");
-            all = static_cast<int>(v - want) >= 0 ? 1 : 0;
-            unsigned long long spins = 0;
-            while (!all) {
-              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.x_ready + step) : "memory");
-              if (static_cast<int>(v - want) >= 0) break;
-              if (++spins > (1ull << 28)) __trap();   // the input kernel gives up (error word) long before this
-              __nanosleep(32);
-            }
+    // ---- P1: h = relu(x W1^T + b1)
+    if (t < p1_tiles) {
+      if (!EPI && a.x_ready != nullptr && warp == 0 && !x_all_ready) {
+        // input pipeline: this step's rows are converted by the side-branch kernel as soon as
+        // their H2D copy lands; only the TMA producer has to wait (phase B reads them later).
+        // Once the LAST chunk is seen ready nothing is checked any more.
+        int all = 0;
+        if (lane == 0) {
+          const unsigned int want = __ldcg(a.round_seq);
+          unsigned int v;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.x_ready + a.steps - 1) : "memory");
+          all = static_cast<int>(v - want) >= 0 ? 1 : 0;
+          unsigned long long spins = 0;
+          while (!all) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.x_ready + step) : "memory");
+            if (static_cast<int>(v - want) >= 0) break;
+            if (++spins > (1ull << 28)) __trap();   // the input kernel gives up (error word) long before this
+            __nanosleep(32);
           }
-          x_all_ready = __shfl_sync(0xffffffffu, all, 0) != 0;
-          ptx::fence_proxy_async_all();   // their generic stores -> this warp's TMA (async proxy) loads
         }
-        Job j{};
-        j.mode = E_BIAS_RELU_BF16; j.d = a.h; j.ldd = H; j.bias = a.b1; j.M = B; j.N = H;
-        j.dbg = a.dbg != nullptr ? a.dbg + step * 32 : nullptr; j.dbg_slot = 16;
-        j.m0 = (t / p1_nt) * kBM; j.n0 = (t % p1_nt) * p1_bn; j.bn = p1_bn;
-        if (FP8) {
-          // e4m3 x tile against a p1_bn-row tile of e4m3 W1; scale chunks are per 128-row block,
-          // the W1 tile's rows start at TMEM column (row % 128) / 32 of the 4-column chunk
-          const int kbq = a.ql.kb1;
-          const int xr = r0 + j.m0;
-          j.fp8 = 1; j.n_kb = kbq;
-          j.ta = &maps.xq_k; j.tb = &maps.w1q_k;
-          j.a_c0 = 0; j.a_c1 = xr; j.b_c0 = 0; j.b_c1 = j.n0;
-          j.sfa = a.x_sf + static_cast<long long>(xr >> 7) * kbq * kSfChunk;
-          j.sfa_col = 0;
-          j.sfb = a.work_q + a.ql.w1sf + static_cast<long long>(j.n0 >> 7) * kbq * kSfChunk;
-          j.sfb_col = static_cast<uint32_t>((j.n0 & 127) >> 5);
-        } else {
-          j.ta = &maps.x_k; j.tb = &maps.w1_k; j.a_mn = 0; j.b_mn = 0;
-          j.a_c0 = 0; j.a_c1 = r0 + j.m0; j.b_c0 = 0; j.b_c1 = j.n0; j.n_kb = kb_d;
-        }
-        run(j);
+        x_all_ready = __shfl_sync(0xffffffffu, all, 0) != 0;
+        ptx::fence_proxy_async_all();   // their generic stores -> this warp's TMA (async proxy) loads
       }
-      grid_barrier(a.barrier, bar_epoch);
-      stamp(step, 1);
+      Job j{};
+      j.mode = E_BIAS_RELU_BF16; j.d = a.h; j.ldd = H; j.bias = a.b1; j.M = B; j.N = H; j.bm = kBM;
+      j.dbg = sdbg; j.dbg_slot = 16;
+      j.m0 = (t / nt_h) * kBM; j.n0 = (t % nt_h) * kBN;
+      if (FP8) {
+        // e4m3 x tile against a 64-row tile of e4m3 W1; scale chunks are per 128-row block, the
+        // W1 tile's rows start at TMEM column (row % 128) / 32 of the 4-column chunk (0 or 2)
+        const int kbq = a.ql.kb1;
+        const int xr = r0 + j.m0;
+        j.fp8 = 1; j.n_kb = kbq;
+        j.ta = &maps.xq_k; j.tb = &maps.w1q_k;
+        j.a_c0 = 0; j.a_c1 = xr; j.b_c0 = 0; j.b_c1 = j.n0;
+        j.sfa = a.x_sf + static_cast<long long>(xr >> 7) * kbq * kSfChunk;
+        j.sfb = a.work_q + a.ql.w1sf + static_cast<long long>(j.n0 >> 7) * kbq * kSfChunk;
+        j.sfb_col = static_cast<uint32_t>((j.n0 & 127) >> 5);
+      } else {
+        j.ta = &maps.x_k; j.tb = &maps.w1_k; j.a_mn = 0; j.b_mn = 0;
+        j.a_c0 = 0; j.a_c1 = r0 + j.m0; j.b_c0 = 0; j.b_c1 = j.n0; j.n_kb = kb_d;
+      }
+      run(j);
     }
+    grid_barrier(a.barrier, bar_epoch);
+    stamp(step, 1);
     if (a.chain != 0) {
-      // ---- chained tail (or whole) of the forward/backward pass per 128-row tile
-      // chain 1: one CTA per M-tile; chain 3: four CTAs per M-tile, each redoes fwd2 + xent
-      // (cheap) and owns a 64-column slice of dh, so the long dh epilogue runs 4-wide
-      const int xs = a.chain == 1 ? 1 : 4;
-      if (t < mt_b * xs) {
-        const int m0 = (t / xs) * kBM, slice = t % xs;
-        if (warp == 0) chain_produce<FP8>(maps, a, smem, sf_smem, cb, cp, r0, m0, a.chain, slice);
-        else if (warp == 1) chain_mma<FP8>(a, smem, sf_smem, cb, tmem_base, cp, a.chain);
-        else chain_epilogue<FP8>(a, smem, cb, tmem_base, warp, lane, stage_base, sbias, cp, m0, r0, a.chain,
-                                 slice, a.dbg != nullptr ? a.dbg + step * 32 : nullptr);
+      // ---- chained tail of the forward/backward pass per 128-row tile: four CTAs per M-tile, each
+      // redoes fwd2 + xent (cheap) and owns a 64-column slice of dh
+      if (t < mt_b * 4) {
+        const int m0 = (t / 4) * kBM, slice = t % 4;
+        const uint32_t par = chains & 1;
+        if constexpr (EPI) {
+          chain_epilogue<FP8>(a, smem, cb, tmem_base, q, half, lane, stg, sbias, xch, par, m0, r0, slice, sdbg);
+        } else {
+          if (warp == 0) chain_produce<FP8>(maps, a, smem, sf_smem, cb, m0, slice);
+          else if (warp == 1) chain_mma<FP8>(smem, sf_smem, cb, tmem_base, par);
+        }
+        ++chains;
       }
       grid_barrier(a.barrier, bar_epoch);
       stamp(step, 2);
@@ -1248,7 +1135,7 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
       // ---- P2: logits -> dlogits / loss / db2
       if (t < mt_b) {
         Job j{};
-        j.ta = &maps.h_k; j.tb = &maps.w2_k; j.a_mn = 0; j.b_mn = 0;
+        j.ta = &maps.h_k; j.tb = &maps.w2_k; j.a_mn = 0; j.b_mn = 0; j.bm = kBM;
         j.m0 = t * kBM; j.n0 = 0; j.M = B; j.N = C;
         j.a_c0 = 0; j.a_c1 = j.m0; j.b_c0 = 0; j.b_c1 = 0; j.n_kb = kb_h;
         j.mode = E_XENT; j.d = a.dlogits; j.ldd = a.ncp; j.bias = a.b2; j.colsum = a.gb2;
@@ -1259,7 +1146,7 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
       // ---- P3: dh = (dlogits W2) * relu'(h), db1
       if (t < mt_b * nt_h) {
         Job j{};
-        j.ta = &maps.dl_k; j.tb = &maps.w2_mn; j.a_mn = 0; j.b_mn = 1;
+        j.ta = &maps.dl_k; j.tb = &maps.w2_mn; j.a_mn = 0; j.b_mn = 1; j.bm = kBM;
         j.m0 = (t / nt_h) * kBM; j.n0 = (t % nt_h) * kBN; j.M = B; j.N = H;
         j.a_c0 = 0; j.a_c1 = j.m0; j.b_c0 = j.n0; j.b_c1 = 0; j.n_kb = kb_c;
         j.mode = E_MASK_COLSUM_BF16; j.d = a.dh; j.ldd = H; j.aux = a.h; j.colsum = a.gb1;
@@ -1268,28 +1155,28 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
       grid_barrier(a.barrier, bar_epoch);
       stamp(step, 2);
     }
-    // ---- B: dW1 = dh^T x (tiles [0, mt_h*nt_d))  ||  dW2 = dlogits^T h (next nt_h tiles)  || biases
-    if (t < mt_h * nt_d) {
+    // ---- B: dW1 = dh^T x (tiles [0, mt_hw*nt_d))  ||  dW2 = dlogits^T h (next nt_h tiles)  || biases
+    if (t < mt_hw * nt_d) {
       Job j{};
-      j.ta = &maps.dh_mn; j.tb = &maps.x_mn; j.a_mn = 1; j.b_mn = 1;
-      j.m0 = (t / nt_d) * kBM; j.n0 = (t % nt_d) * kBN; j.M = H; j.N = D;
+      j.ta = &maps.dh_mn; j.tb = &maps.x_mn; j.a_mn = 1; j.b_mn = 1; j.bm = bm_w;
+      j.m0 = (t / nt_d) * bm_w; j.n0 = (t % nt_d) * kBN; j.M = H; j.N = D;
       j.a_c0 = j.m0; j.a_c1 = 0; j.b_c0 = j.n0; j.b_c1 = r0; j.n_kb = kb_b;
       j.mode = eo ? E_OPT : E_F32; j.d = eo ? a.master + (a.gw1 - a.grad) : a.gw1; j.ldd = D;
       j.bc1 = bc1; j.bc2 = bc2; j.last = last ? 1 : 0;
-      j.dbg = a.dbg != nullptr ? a.dbg + step * 32 : nullptr; j.dbg_slot = 18;
+      j.dbg = sdbg; j.dbg_slot = 18;
       j.q_off = a.ql.w1q; j.qsf_off = a.ql.w1sf; j.ldq = D; j.q_nkb = a.ql.kb1;
       run(j);
-    } else if (t < mt_h * nt_d + nt_h) {
-      const int u = t - mt_h * nt_d;
+    } else if (t < mt_hw * nt_d + nt_h) {
+      const int u = t - mt_hw * nt_d;
       Job j{};
-      j.ta = &maps.dl_mn; j.tb = &maps.h_mn; j.a_mn = 1; j.b_mn = 1;
+      j.ta = &maps.dl_mn; j.tb = &maps.h_mn; j.a_mn = 1; j.b_mn = 1; j.bm = bm_w;
       j.m0 = 0; j.n0 = u * kBN; j.M = C; j.N = H;
       j.a_c0 = 0; j.a_c1 = 0; j.b_c0 = j.n0; j.b_c1 = 0; j.n_kb = kb_b;
       j.mode = eo ? E_OPT : E_F32; j.d = eo ? a.master + (a.gw2 - a.grad) : a.gw2; j.ldd = H;
       j.bc1 = bc1; j.bc2 = bc2; j.last = last ? 1 : 0;
       j.q_off = a.ql.w2q; j.qsf_off = a.ql.w2sf; j.ldq = H; j.q_nkb = a.ql.kb2;
       run(j);
-    } else if (eo && t == mt_h * nt_d + nt_h) {
+    } else if (eo && t == mt_hw * nt_d + nt_h) {
       // biases: their gradients were accumulated by column sums earlier in the step; consume + re-zero
       const bool up = last && a.has_fed;
       UploadDst ud{};
@@ -1328,6 +1215,15 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
     }
     grid_barrier(a.barrier, bar_epoch);
     stamp(step, 5);
+  }
+
+  };   // round_loop
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLow));
+    round_loop(std::false_type{});
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsHigh));
+    round_loop(std::true_type{});
   }
 
   // ---- UploadLocalUpdate, second half: every CTA's upload stores were fenced at system scope
@@ -1386,26 +1282,27 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
   if (r.hidden % 8 || r.in_dim % 8 || r.n_params % 4 || r.batch % 8 || r.ncp % 8 || r.n_classes > 64)
     return cudaErrorInvalidValue;
   const int mt_b = (r.batch + kBM - 1) / kBM, nt_h = (r.hidden + kBN - 1) / kBN;
-  const int nt_d = (r.in_dim + kBN - 1) / kBN, mt_h = (r.hidden + kBM - 1) / kBM;
-  // phase plan: r.plan / r.epiopt when >= 0, else BFLC_MLP_CHAIN = 0 | 1 | 3 and
-  // BFLC_MLP_EPIOPT = 0 | 1 (see the kernel), else the defaults
+  const int nt_d = (r.in_dim + kBN - 1) / kBN;
+  // phase plan: r.plan / r.epiopt when >= 0, else BFLC_MLP_CHAIN = 0 | 3 and BFLC_MLP_EPIOPT = 0 | 1
+  // (see the kernel), else the defaults
   static const int chain_env0 = [] { const char* e = std::getenv("BFLC_MLP_CHAIN"); return e ? std::atoi(e) : kDefaultPlan; }();
   static const bool epiopt_env0 = [] { const char* e = std::getenv("BFLC_MLP_EPIOPT"); return !(e && e[0] == '0'); }();
   const int chain_env = r.plan >= 0 ? r.plan : chain_env0;
   const bool epiopt = r.epiopt >= 0 ? r.epiopt != 0 : epiopt_env0;
   const bool chain_ok = r.hidden == kChainH && r.ncp == 64 && r.n_classes <= 64;
-  const int chain = !chain_ok ? 0 : chain_env == 0 ? 0 : chain_env == 1 ? 1 : 3;
+  const int chain = (!chain_ok || chain_env == 0) ? 0 : 3;
   const bool fp8 = r.fp8;
   if (fp8 && (chain != 3 || !epiopt || r.batch % 128 || r.in_dim % 16 || !r.x_q || !r.x_sf || !r.work_q ||
               !r.h_q || !r.h_sf))
     return cudaErrorNotSupported;
   if (r.fed != nullptr && !epiopt) return cudaErrorNotSupported;
-  // fp8 fwd1 tile width.  64: a tile's W1 rows start at column 0 or 2 of the 4-column scale chunk
-  // in TMEM.  (32-wide tiles would start at odd columns: `misaligned address` on sm_100a, measured.)
-  const int p1_bn = kBN;
-  const int p1_tiles = mt_b * ((r.hidden + p1_bn - 1) / p1_bn);
-  const int need = std::max(std::max(p1_tiles, mt_h * nt_d + nt_h + 1), chain == 3 ? mt_b * 4 : 0);
-  if (need > kGrid * 4) return cudaErrorInvalidValue;
+  // weight-gradient tiles: 64 rows (UMMA M = 64) spread the optimizer epilogue over twice the CTAs;
+  // BFLC_MLP_BMW=128 keeps the 128-row tiles
+  static const int bmw_env = [] { const char* e = std::getenv("BFLC_MLP_BMW"); return e && std::atoi(e) == 128 ? 128 : 64; }();
+  int bm_w = bmw_env;
+  int mt_hw = (r.hidden + bm_w - 1) / bm_w;
+  if (mt_hw * nt_d + nt_h + 1 > 148) { bm_w = 128; mt_hw = (r.hidden + 127) / 128; }
+  const int need = std::max(std::max(mt_b * nt_h, mt_hw * nt_d + nt_h + 1), chain == 3 ? mt_b * 4 : 0);
   const int grid = need > kGrid ? need : kGrid;
   if (grid > 148) return cudaErrorInvalidValue;
 
@@ -1429,12 +1326,11 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
   if ((e = mk(&m.w2_mn, r.w2_shadow, r.hidden, true, r.hidden, r.n_classes, kBN)) != cudaSuccess) return e;
   if ((e = mk(&m.dh_mn, r.dh, r.hidden, true, r.hidden, r.batch, kBM)) != cudaSuccess) return e;
   if ((e = mk(&m.x_mn, r.x, r.in_dim, true, r.in_dim, (int)rows_x, kBN)) != cudaSuccess) return e;
-  if ((e = mk(&m.w1_k256, r.w1_shadow, r.in_dim, false, r.hidden, r.in_dim, chain == 1 ? 256 : kBN)) != cudaSuccess) return e;
   const Mx8MlpLayout ql = mx8_mlp_layout(r.in_dim, r.hidden);
   if (fp8) {
     const DType q = DType::FP8_E4M3;
     if ((e = mk(&m.xq_k, r.x_q, r.in_dim, false, (int)rows_x, r.in_dim, kBM, q)) != cudaSuccess) return e;
-    if ((e = mk(&m.w1q_k, r.work_q + ql.w1q, r.in_dim, false, r.hidden, r.in_dim, p1_bn, q)) != cudaSuccess) return e;
+    if ((e = mk(&m.w1q_k, r.work_q + ql.w1q, r.in_dim, false, r.hidden, r.in_dim, kBN, q)) != cudaSuccess) return e;
     if ((e = mk(&m.hq_k, r.h_q, r.hidden, false, r.batch, r.hidden, kBM, q)) != cudaSuccess) return e;
     if ((e = mk(&m.w2q_k, r.work_q + ql.w2q, r.hidden, false, 64, r.hidden, 64, q)) != cudaSuccess) return e;
   }
@@ -1443,8 +1339,7 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
   a.B = r.batch; a.steps = r.steps; a.in_dim = r.in_dim; a.hidden = r.hidden;
   a.n_classes = r.n_classes; a.ncp = r.ncp; a.n_params = r.n_params;
   a.chain = chain; a.epiopt = epiopt ? 1 : 0; a.dbg = r.dbg;
-  a.x_ready = chain != 1 ? r.x_ready : nullptr; a.round_seq = r.round_seq;
-  if (r.x_ready != nullptr && chain == 1) return cudaErrorNotSupported;
+  a.x_ready = r.x_ready; a.round_seq = r.round_seq;
   a.pred = r.pred ? r.pred : current_predicate();
   a.barrier = r.barrier;
   a.master = r.master; a.b1 = r.b1; a.b2 = r.b2;
@@ -1456,7 +1351,7 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
   a.dlogits = reinterpret_cast<__nv_bfloat16*>(r.dlogits);
   a.dh = reinterpret_cast<__nv_bfloat16*>(r.dh);
   a.labels = r.labels; a.loss_sum = r.loss_sum; a.correct = r.correct;
-  a.x_sf = r.x_sf; a.work_q = r.work_q; a.h_q = r.h_q; a.h_sf = r.h_sf; a.ql = ql; a.p1_bn = p1_bn;
+  a.x_sf = r.x_sf; a.work_q = r.work_q; a.h_q = r.h_q; a.h_sf = r.h_sf; a.ql = ql; a.bm_w = bm_w;
   a.has_fed = r.fed != nullptr ? 1 : 0;
   if (r.fed != nullptr) a.f = *r.fed;
   a.upq_off[0] = r.upq_off[0]; a.upq_off[1] = r.upq_off[1];

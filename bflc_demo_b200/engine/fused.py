@@ -241,6 +241,7 @@ class FusedEngine:
         self.graph_pipe: Optional[torch.cuda.CUDAGraph] = None
         self.stream = torch.cuda.Stream(device=self.dev)
         self._side = torch.cuda.Stream(device=self.dev)
+        self._side2 = torch.cuda.Stream(device=self.dev)
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         # host -> device input pipeline (run_round_e2e): needs the one-launch trainer (its producer
         # waits per step) and a shard that is exactly steps x batch rows
@@ -278,12 +279,14 @@ class FusedEngine:
         self._ev_fork.record(main)
         self._side.wait_event(self._ev_fork)
         B = cfg.batch_size
-        with torch.cuda.stream(self._side):
-            if self.fp8:
-                # the consensus kernel of the previous round rewrote the training weights: refresh
-                # this trainer's MXFP8 copy (e4m3 + scale chunks) before step 0
+        if self.fp8:
+            # the consensus kernel of the previous round rewrote the training weights: refresh this
+            # trainer's MXFP8 copy (e4m3 + scale chunks) before step 0 -- a third parallel branch
+            self._side2.wait_event(self._ev_fork)
+            with torch.cuda.stream(self._side2):
                 self.trainer.quantize_weights()
-                self._ev_wq.record(self._side)
+                self._ev_wq.record(self._side2)
+        with torch.cuda.stream(self._side):
             if pipe:
                 m.prep_inputs_chunks(self.x_u8, self.x_bf, self.x_q, self.x_sf, B, self.steps,
                                      1.0 / 255.0, self.in_flags, self.in_seq, self.cast_cnt,
@@ -298,7 +301,7 @@ class FusedEngine:
             m.fed_plan_round(self.fed, self.plan_layers, self.steps, self.staged)
         if not pipe:
             main.wait_event(self._ev_join)
-        elif self.fp8:
+        if self.fp8:
             main.wait_event(self._ev_wq)
         # local training, predicated on the trainer role bit
         m.set_predicate(self.is_trainer_ptr)

@@ -91,6 +91,12 @@ class NcclBaselineEngine:
         self.out_host = torch.zeros(world + 1, dtype=torch.float32).pin_memory()
         self.out_dev = torch.zeros(world + 1, device=self.dev)
         self.byz = rank in cfg.byzantine_ranks
+        try:    # cuBLAS writes fp32 straight out of a bf16 GEMM when torch exposes out_dtype
+            a = torch.zeros(8, 8, device=self.dev, dtype=torch.bfloat16)
+            torch.mm(a, a, out_dtype=torch.float32)
+            self._mm32 = lambda a, b: torch.mm(a, b, out_dtype=torch.float32)
+        except Exception:  # noqa: BLE001
+            self._mm32 = lambda a, b: (a @ b).float()
 
     # ---------------------------------------------------------------- local work
     def _train_pass(self):
@@ -105,18 +111,18 @@ class NcclBaselineEngine:
             y = self.y[i * B:(i + 1) * B]
             # cuBLASLt: bias + ReLU in the GEMM epilogue
             h = torch._addmm_activation(s["b1"], x, s["w1"].t(), use_gelu=False)
-            logits = torch.addmm(s["b2"], h, s["w2"].t()).float()
-            logp = torch.log_softmax(logits, 1)
-            self.loss_acc -= logp.gather(1, y[:, None]).sum()
+            logits = torch.addmm(s["b2"], h, s["w2"].t())
+            logp = torch.log_softmax(logits, 1, dtype=torch.float32)       # cast fused into the softmax
+            self.loss_acc += torch.nn.functional.nll_loss(logp, y, reduction="sum")
             p = torch.exp(logp)
             p.scatter_add_(1, y[:, None], self.minus_one)
             dlf = p * (1.0 / B)
             dl = dlf.to(torch.bfloat16)
-            gw2 = (dl.t() @ h).float()
+            gw2 = self._mm32(dl.t(), h)                                    # bf16 x bf16 -> fp32 out
             gb2 = dlf.sum(0)
-            dh = (dl @ s["w2"]) * (h > 0)
-            gw1 = (dh.t() @ x).float()
-            gb1 = dh.float().sum(0)
+            dh = torch.ops.aten.threshold_backward(dl @ s["w2"], h, 0)     # fused relu'
+            gw1 = self._mm32(dh.t(), x)
+            gb1 = dh.sum(0, dtype=torch.float32)
             grads = [gw1, gb1, gw2, gb2]
             if self.adam:
                 torch._foreach_add_(self.t, 1.0)

@@ -166,7 +166,7 @@ def test_mlp_training_step_matches_torch():
     assert bool((grad == 0).all())
 
 
-@pytest.mark.parametrize("plan,epiopt", [(-1, -1), (0, 0), (0, 1), (1, 1), (3, 0), (3, 1)])
+@pytest.mark.parametrize("plan,epiopt", [(-1, -1), (0, 0), (0, 1), (3, 0), (3, 1)])
 @pytest.mark.parametrize("B,steps,opt", [(256, 3, "sgd"), (512, 4, "adam"), (200, 2, "sgd")])
 def test_persistent_round_kernel_matches_six_kernel_path(B, steps, opt, plan, epiopt):
     """mlp_round_sm100.cu (one launch, grid barriers) vs the per-GEMM launches (models/mlp.py),

@@ -185,15 +185,15 @@ def test_fp8_ranking_matches_bf16():
         eng = FusedEngine(cfg, femnist_like(1, 2048, seed=7, only=0)[0])
         test = femnist_like(2, 2048, seed=7, only=1)[0]      # same class prototypes, unseen samples
         a = [eng.evaluate(test)]
-        for _ in range(4):
+        for _ in range(10):
             eng.run_round()
             a.append(eng.evaluate(test))
         assert not eng.drain_blocks()
         accs[dt] = a
         del eng
-    # accuracy after k rounds is (weakly) increasing in both, and the two curves stay close
+    # both learn (held-out accuracy far above the 1/62 prior), and the two curves stay close
     for dt in accs:
-        assert accs[dt][-1] > accs[dt][0] + 0.2, accs
+        assert accs[dt][-1] > accs[dt][0] + 0.3, accs
     assert all(abs(a - b) < 0.05 for a, b in zip(accs["bf16"], accs["fp8"])), accs
 
 
