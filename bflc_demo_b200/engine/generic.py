@@ -1,8 +1,14 @@
 """Model-agnostic federated engine: any ``FlatNet`` (LeNet-5, ResNet-18, BERT-base, MLP) on the
 same device-resident protocol as ``FusedEngine`` -- symmetric-heap upload buffers, epoch-tagged
-P2P flags, the consensus/aggregation kernel, the host ledger re-executing every election --
-with the round driven from Python instead of a captured graph (rounds of these models take
-milliseconds, so one device->host read of the role table per round is noise).
+P2P flags, the consensus/aggregation kernel, the host ledger re-executing every election.
+
+A round is five launches: ``fed_plan_round``, the whole local-training pass as ONE captured
+CUDA graph (forward, backward and optimizer of every mini-batch step -- all our kernels, no
+host sync), ``fed_upload``, the committee's pull + validation of every candidate as a second
+graph, ``fed_consensus_aggregate``.  Which graphs a rank replays is decided from the role
+table it read back (104 bytes, pinned, non-blocking) at the end of the previous round -- no
+device->host read inside a round.  (``capture()`` is optional: without it the same round runs
+eagerly, kernel by kernel.)
 
 Committee validation runs the model *directly on the trainers' HBM*: a candidate's ``Bound`` is a
 set of tensor views over the peer-mapped upload buffers, so every GEMM of the forward pass
@@ -29,6 +35,7 @@ from .fused import ROLE_COMM, ROLE_TRAINER, FusedEngine, initial_roles
 class GenericFedEngine:
     read_state = FusedEngine.read_state
     drain_blocks = FusedEngine.drain_blocks
+    read_stamps = FusedEngine.read_stamps
 
     def __init__(self, cfg: FLConfig, net: FlatNet, shard: Shard, *, rank: int = 0, world: int = 1,
                  device: int = 0, group=None):
@@ -59,6 +66,7 @@ class GenericFedEngine:
         self.global_shadow = hv(o["global_shadow"], [P], torch.bfloat16)
         self.state_bytes = hv(o["state"], [sz["RoundState"]], torch.uint8)
         self.ring_bytes = hv(o["ring"], [cfg.ring_slots * sz["BlockRecord"]], torch.uint8)
+        self.plan_bytes = hv(o["plan"], [sz["RoundPlan"]], torch.uint8)
         self.loss_sum = hv(o["plan"] + sz["plan_loss_sum_off"], [1], torch.float32)
         self.val_correct = hv(o["plan"] + sz["plan_correct_off"], [sz["kMaxRanks"]], torch.int32)
         self.opt_step_ptr = self.heap.local_ptr + o["plan"] + sz["plan_opt_step_off"]
@@ -87,6 +95,17 @@ class GenericFedEngine:
         self.byz = 1 if rank in cfg.byzantine_ranks else 0
         self._peer_bounds = {}
         self._stage = None
+        self._rounds = 0
+        self.n_cand = world if cfg.solo else cfg.n_trainers      # candidates per round (fixed count)
+        self.staged = bool(cfg.stage_candidates) and world > 1
+        self.graph_train: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_val: Optional[torch.cuda.CUDAGraph] = None
+        self.capture_error = ""
+        self.stream = torch.cuda.Stream(device=self.dev)
+        # role table cache: refreshed from the ledger page at the end of every round
+        self._st_host = torch.empty(sz["RoundState"], dtype=torch.uint8).pin_memory()
+        self._st_event = torch.cuda.Event()
+        self._st = None
         if world > 1:
             dist.barrier(group=group)
         torch.cuda.synchronize()
@@ -112,19 +131,32 @@ class GenericFedEngine:
                                 self.work_shadow, self.m, self.v, cfg.learning_rate, 0.0, 0.9,
                                 0.999, 1e-8, i + 1, self.opt_step_ptr, 0, True)
 
+    def _ensure_stage(self):
+        if self._stage is None:
+            P = self.n_params
+            self._stage = (torch.empty(self.world, P, device=self.dev, dtype=torch.bfloat16),
+                           torch.empty(self.world, P, device=self.dev, dtype=torch.float32))
+            self._stage_bounds = [self.net.bind(self._stage[1][z], self._stage[0][z], None)
+                                  for z in range(self.world)]
+
+    def validate_staged(self):
+        """Committee: one P2P pass per candidate (bf16 weights + fp32 master) into local staging,
+        started per candidate as soon as its trainer's flag is up (the kernel resolves the
+        candidate -> trainer mapping from the ledger page), then the forward pass of every
+        candidate slot out of local HBM.  No host-side knowledge of who the trainers are: the
+        sequence is identical every round and therefore capturable."""
+        xv, yv = self.x[: self.n_val], self.y[: self.n_val]
+        self._ensure_stage()
+        self.mod.fed_pull_candidates(self.fed, self._stage[0], self._stage[1])
+        for z in range(self.n_cand):
+            cnt = self.net.correct(self._stage_bounds[z], xv, yv)
+            self.val_correct[z:z + 1].copy_(cnt)
+
     def validate(self, trainers: List[int], parity: int):
         xv, yv = self.x[: self.n_val], self.y[: self.n_val]
-        if self.cfg.stage_candidates and self.world > 1:
-            # one P2P pass per candidate (weights + fp32 master) into local staging, started per
-            # candidate as soon as its trainer's flag is up; the forward passes then read local HBM
-            if self._stage is None:
-                P = self.n_params
-                self._stage = (torch.empty(self.world, P, device=self.dev, dtype=torch.bfloat16),
-                               torch.empty(self.world, P, device=self.dev, dtype=torch.float32))
-                self._stage_bounds = [self.net.bind(self._stage[1][z], self._stage[0][z], None)
-                                      for z in range(self.world)]
-            self.mod.fed_pull_candidates(self.fed, self._stage[0], self._stage[1])
-            bounds = [self._stage_bounds[z] for z in range(len(trainers))]
+        if self.staged:
+            self.validate_staged()
+            return
         else:
             # direct: every GEMM of the forward pass TMA-loads its weight tiles from the peer
             self.mod.fed_wait_trained(self.fed)
@@ -133,26 +165,73 @@ class GenericFedEngine:
             cnt = self.net.correct(b, xv, yv)
             self.val_correct[z:z + 1].copy_(cnt)
 
+    # ------------------------------------------------------------------ graphs
+    def capture(self):
+        """Warm up with one real (eager) round -- lazy kernel attribute setup, autograd graph
+        buffers -- then capture the local-training pass and the staged validation pass.  Collective:
+        every rank calls it.  Falls back to eager rounds if a capture fails (``capture_error``)."""
+        self.run_round()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        if not self.cfg.cuda_graph:
+            return
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream):
+                self.local_training()
+            self.graph_train = g
+            if self.staged:      # (direct validation reads parity/trainer-dependent peer views: eager)
+                gv = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gv, stream=self.stream):
+                    self.validate_staged()
+                self.graph_val = gv
+        except Exception as e:  # noqa: BLE001
+            self.graph_train = self.graph_val = None
+            self.capture_error = repr(e)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def _roles(self) -> dict:
+        """Role table of the round about to start: read back at the end of the previous round."""
+        if self._st is None:
+            return self.read_state()
+        self._st_event.synchronize()
+        return self.read_state(self._st_host)
+
     # ------------------------------------------------------------------ one round
     def run_round(self) -> dict:
         m, cfg = self.mod, self.cfg
         # ring backpressure: drain the device BlockRecord ring before slots can be overwritten
-        self._rounds = getattr(self, "_rounds", 0) + 1
+        self._rounds += 1
         if self._rounds - self.drained >= max(cfg.ring_slots // 2, 1):
             errs = self.drain_blocks()
             if errs:
                 raise RuntimeError(f"host/device ledgers disagree: {errs[:2]}")
-        m.fed_plan_round(self.fed, [], self.steps, False)
-        st = self.read_state()  # host learns roles/epoch (D2H of the 104-byte ledger page)
+        st = self._roles()
         role = st["roles"][self.rank]
         trainers = [r for r in range(self.world) if st["roles"][r] & ROLE_TRAINER]
-        if role & ROLE_TRAINER:
-            self.local_training()
-        m.fed_upload(self.fed, self.S, self.steps * cfg.batch_size, self.byz, cfg.byzantine_scale)
-        if role & ROLE_COMM:
-            self.validate(trainers, st["epoch"] & 1)
-        m.fed_consensus_aggregate(self.fed, self.n_val, cfg.weight_by_score, self.two_shot,
-                                  cfg.use_multicast and self.heap.has_multicast)
+        with torch.cuda.stream(self.stream):
+            m.fed_plan_round(self.fed, [], self.steps, False)
+            if role & ROLE_TRAINER:
+                if self.graph_train is not None:
+                    self.graph_train.replay()
+                else:
+                    self.local_training()
+            m.fed_upload(self.fed, self.S, self.steps * cfg.batch_size, self.byz, cfg.byzantine_scale)
+            if role & ROLE_COMM:
+                if self.graph_val is not None:
+                    self.graph_val.replay()
+                else:
+                    self.validate(trainers, st["epoch"] & 1)
+            m.fed_consensus_aggregate(self.fed, self.n_val, cfg.weight_by_score, self.two_shot,
+                                      cfg.use_multicast and self.heap.has_multicast)
+            # next round's role table: non-blocking readback of the ledger page
+            self._st_host.copy_(self.state_bytes, non_blocking=True)
+            self._st_event.record(self.stream)
+            self._st = True
+        torch.cuda.current_stream().wait_stream(self.stream)
         return st
 
     def evaluate(self, shard: Shard) -> float:
