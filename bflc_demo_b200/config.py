@@ -41,6 +41,8 @@ class FLConfig:
     # ---- faults ----
     byzantine_ranks: List[int] = field(default_factory=list)
     byzantine_scale: float = 5.0
+    straggler_ranks: List[int] = field(default_factory=list)   # these clients publish late ...
+    straggler_delay_us: int = 0                                # ... by this much (first-K-wins test)
     # ---- engine ----
     backend: str = "auto"             # auto | fused (P2P kernels) | nccl (baseline) | gloo
     two_shot: Optional[bool] = None   # None = by model size
@@ -163,7 +165,7 @@ class FLConfig:
                 kw[f.name] = float(v)
             elif f.type in ("bool", bool):
                 kw[f.name] = v.lower() in ("1", "true", "yes")
-            elif f.name == "byzantine_ranks":
+            elif f.name in ("byzantine_ranks", "straggler_ranks"):
                 kw[f.name] = [int(x) for x in v.split(",") if x]
             else:
                 kw[f.name] = v

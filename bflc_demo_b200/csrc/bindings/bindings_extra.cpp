@@ -49,6 +49,7 @@ bflc::FedArgs make_fed(const py::dict& d) {
   l.global_shadow_off = d["global_shadow_off"].cast<int64_t>();
   l.ring_off = d["ring_off"].cast<int64_t>();
   l.n_params = d["n_params"].cast<int64_t>();
+  l.admit_off = d["admit_off"].cast<int64_t>();
   l.ring_slots = d["ring_slots"].cast<int>();
   return f;
 }
@@ -112,6 +113,7 @@ void bind_extra(py::module_& m) {
     d["RoundPlan"] = sizeof(bflc::RoundPlan);
     d["BlockRecord"] = sizeof(bflc::BlockRecord);
     d["UploadMeta"] = sizeof(bflc::UploadMeta);
+    d["AdmitPage"] = sizeof(bflc::AdmitPage);
     d["GemmDynamic"] = sizeof(bflc::GemmDynamic);
     d["FLAG_COUNT"] = (int)bflc::FLAG_COUNT;
     d["kMaxRanks"] = bflc::kMaxRanks;
@@ -136,13 +138,14 @@ void bind_extra(py::module_& m) {
   });
 
   // host-side init of the replicated ledger page
-  m.def("state_init_bytes", [](int n_ranks, int n_comm, int n_aggregate, std::vector<int> roles) {
+  m.def("state_init_bytes", [](int n_ranks, int n_comm, int n_aggregate, std::vector<int> roles, int n_needed) {
     bflc::RoundState st;
     std::memset(&st, 0, sizeof(st));
     st.epoch = 0; st.n_ranks = n_ranks; st.n_comm = n_comm; st.n_aggregate = n_aggregate;
+    st.n_needed = (uint32_t)n_needed;
     for (int r = 0; r < n_ranks && r < bflc::kMaxRanks; ++r) st.role[r] = (uint32_t)roles.at(r);
     return py::bytes(reinterpret_cast<const char*>(&st), sizeof(st));
-  });
+  }, py::arg("n_ranks"), py::arg("n_comm"), py::arg("n_aggregate"), py::arg("roles"), py::arg("n_needed") = 0);
 
   // ------------------------------------------------------------ fed kernels
   m.def("fed_plan_round", [](const py::dict& fd, std::vector<std::pair<int64_t, bool>> layers,
@@ -171,11 +174,12 @@ void bind_extra(py::module_& m) {
     check(bflc::fed_pull_blobs(make_fed(fd), off0, off1, nbytes, stage.data_ptr(), cur_stream()), "fed_pull_blobs");
   });
   m.def("fed_upload", [](const py::dict& fd, int n_samples, int n_loss_terms, int byz_mode,
-                         double byz_scale) {
-    check(bflc::fed_upload(make_fed(fd), n_samples, n_loss_terms, byz_mode, (float)byz_scale,
-                           cur_stream()),
+                         double byz_scale, int straggle_us) {
+    check(bflc::fed_upload(make_fed(fd), n_samples, n_loss_terms, byz_mode, (float)byz_scale, cur_stream(),
+                           straggle_us),
           "fed_upload");
-  });
+  }, py::arg("fed"), py::arg("n_samples"), py::arg("n_loss_terms"), py::arg("byz_mode"), py::arg("byz_scale"),
+     py::arg("straggle_us") = 0);
   m.def("fed_consensus_aggregate", [](const py::dict& fd, int n_val, bool weight_by_score,
                                       bool two_shot, bool use_mc) {
     check(bflc::fed_consensus_aggregate(make_fed(fd), n_val, weight_by_score ? 1 : 0,
@@ -223,7 +227,7 @@ void bind_extra(py::module_& m) {
                         int64_t round_seq_ptr, const OptT& x_q, const OptT& x_sf, const OptT& work_q,
                         const OptT& h_q, const OptT& h_sf, const std::optional<py::dict>& fed,
                         std::vector<int64_t> upq_off, int n_samples, int n_loss_terms, int byz_mode,
-                        double byz_scale) {
+                        double byz_scale, int straggle_us) {
     TORCH_CHECK(offs.size() == 4, "offs = element offsets of w1, b1, w2, b2 in the flat buffer");
     bflc::MlpRoundArgs r;
     r.batch = batch; r.steps = steps; r.in_dim = in_dim; r.hidden = hidden; r.n_classes = n_classes;
@@ -265,6 +269,7 @@ void bind_extra(py::module_& m) {
       r.fed = &f;
       if (upq_off.size() == 2) { r.upq_off[0] = upq_off[0]; r.upq_off[1] = upq_off[1]; }
       r.n_samples = n_samples; r.n_loss_terms = n_loss_terms; r.byz_mode = byz_mode; r.byz_scale = (float)byz_scale;
+      r.straggle_us = straggle_us;
     }
     check(bflc::mlp_round_sm100(r, cur_stream()), "mlp_round_sm100");
   }, py::arg("x"), py::arg("labels"), py::arg("master"), py::arg("shadow"), py::arg("grad"), py::arg("offs"),
@@ -275,7 +280,8 @@ void bind_extra(py::module_& m) {
      py::arg("round_seq_ptr") = 0, py::arg("x_q") = py::none(), py::arg("x_sf") = py::none(),
      py::arg("work_q") = py::none(), py::arg("h_q") = py::none(), py::arg("h_sf") = py::none(),
      py::arg("fed") = py::none(), py::arg("upq_off") = std::vector<int64_t>{}, py::arg("n_samples") = 0,
-     py::arg("n_loss_terms") = 0, py::arg("byz_mode") = 0, py::arg("byz_scale") = 0.0);
+     py::arg("n_loss_terms") = 0, py::arg("byz_mode") = 0, py::arg("byz_scale") = 0.0,
+     py::arg("straggle_us") = 0);
   // committee validation of every candidate in one launch (fwd1 -> relu -> fwd2 -> argmax)
   m.def("mlp_val", [](at::Tensor x, at::Tensor labels, at::Tensor correct, at::Tensor maps,
                       int64_t dyn1_ptr, int64_t dyn2_ptr, int n_val, int in_dim, int hidden,

@@ -162,6 +162,7 @@ struct MlpRoundArgs {
   long long upq_off[2] = {0, 0};
   int n_samples = 0, n_loss_terms = 0, byz_mode = 0;
   float byz_scale = 0.f;
+  int straggle_us = 0;   // fault injection: publish this late (first-K-wins admission test)
 };
 cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream);
 
@@ -303,7 +304,8 @@ struct RoundState {
   float global_loss;
   unsigned long long model_digest;
   uint32_t blocks_appended;
-  uint32_t pad;
+  uint32_t n_needed;              // NEEDED_UPDATE_COUNT: updates admitted per round.  == #trainers:
+                                  // every trainer is awaited; < #trainers: first-K-wins (C:239-244)
 };
 
 struct UploadMeta {
@@ -365,8 +367,22 @@ struct HeapLayout {
   long long global_shadow_off; // bf16
   long long ring_off;          // BlockRecord [ring_slots]
   long long n_params;          // elements (multiple of 8)
+  long long admit_off;         // AdmitPage [2 parity]: first-K-wins admission (ticket + slots)
   int ring_slots;
   int pad;
+};
+
+// First-K-wins admission (reference: UploadLocalUpdate drops an update once update_count reached
+// NEEDED_UPDATE_COUNT, C:239-244 -- there the order is the chain's transaction order; here it is
+// the order of an atomic ticket counter on rank 0's page).  A trainer that finished its local
+// pass takes a ticket; tickets 0..K-1 are admitted: the trainer writes (epoch+1)<<8 | rank into
+// slot[ticket] of EVERY replica with a release store issued after its upload is visible, so a
+// reader that acquires a slot may read that trainer's upload.  Later tickets are rejected: the
+// trainer publishes nothing and its update is ignored, exactly like a dropped transaction.
+struct AdmitPage {
+  uint32_t ticket;                 // (epoch+1)<<8 | tickets handed out; only rank 0's copy is used
+  uint32_t slot[kMaxRanks];        // candidate slot z -> (epoch+1)<<8 | trainer rank
+  uint32_t pad[7];
 };
 
 // One record per finished round, written by the consensus kernel and drained by the host
@@ -425,9 +441,10 @@ cudaError_t fed_plan_round(const FedArgs& f, const PlanLayer* layers, int n_laye
 // trainer ("UploadLocalUpdate", CommitteePrecompiled.cpp:215-258): copy the trained weights
 // into the peer-readable upload buffers, push {n_samples, avg_cost} to every replica and
 // release FLAG_TRAINED on every peer.  byz_mode 1 = sign-flipped, scaled delta (fault
-// injection).
+// injection).  straggle_us > 0: sleep that long before publishing (a slow
+// client; fault injection for first-K-wins admission).
 cudaError_t fed_upload(const FedArgs& f, int n_samples, int n_loss_terms, int byz_mode,
-                       float byz_scale, cudaStream_t s);
+                       float byz_scale, cudaStream_t s, int straggle_us = 0);
 // everyone ("UploadScores" + "Aggregate", CommitteePrecompiled.cpp:259-298, 349-456):
 // committee ranks push their score row to every replica; all ranks wait for the rows, run
 // the consensus math, reduce the selected uploads over P2P loads in a fixed order, write

@@ -18,6 +18,7 @@
 
 #include "bflc_kernels.h"
 #include "consensus_math.hpp"
+#include "fed_admit.cuh"
 #include "launch.cuh"
 #include "sm100_ptx.cuh"
 
@@ -80,13 +81,19 @@ __global__ void k_plan(FedArgs f, PlanLayers layers) {
   int n_cand = 0;
   for (int r = 0; r < f.n_ranks; ++r)
     if (st->role[r] & ROLE_TRAINER) plan->cand_rank[n_cand++] = r;
+  if (admit::first_k(st)) {
+    // first-K-wins: candidate slot z is whoever takes ticket z this round -- resolved by the
+    // consumers of the slot (k_pull*, k_consensus), not here
+    n_cand = static_cast<int>(st->n_needed);
+    for (int z = 0; z < kMaxRanks; ++z) plan->cand_rank[z] = -1;
+  }
   plan->n_cand = n_cand;
   for (int l = 0; l < layers.n; ++l) {
     GemmDynamic& d = plan->dyn[l];
     d.active_batches = plan->is_comm ? n_cand : 0;
     d.wait_value = epoch + 1;
     for (int z = 0; z < kMaxRanks; ++z) {
-      const int t = z < n_cand ? plan->cand_rank[z] : 0;
+      const int t = (z < n_cand && plan->cand_rank[z] >= 0) ? plan->cand_rank[z] : 0;
       // tensor-map table: staged -> [layer][slot] over local staging; direct -> [layer][parity]
       // [rank] over the trainers' upload buffers (TMA pulls across NVLink)
       d.map_index[z] = layers.staged ? (l * kMaxRanks + z)
@@ -100,7 +107,7 @@ __global__ void k_plan(FedArgs f, PlanLayers layers) {
   }
   for (int z = 0; z < kMaxRanks; ++z) {
     plan->correct[z] = 0;
-    const int t = z < n_cand ? plan->cand_rank[z] : f.rank;
+    const int t = (z < n_cand && plan->cand_rank[z] >= 0) ? plan->cand_rank[z] : f.rank;
     plan->cand_blob[z] = !layers.use_blob ? nullptr
                          : layers.staged  ? layers.stage_blob + z * layers.blob_bytes
                                           : reinterpret_cast<const uint8_t*>(f.peers.base[t]) + layers.upq_off[par];
@@ -118,7 +125,7 @@ __global__ void k_plan(FedArgs f, PlanLayers layers) {
 
 // ------------------------------------------------------------------ upload
 __global__ void __launch_bounds__(kFedThreads)
-k_upload(FedArgs f, int n_samples, int n_loss_terms, int byz_mode, float byz_scale) {
+k_upload(FedArgs f, int n_samples, int n_loss_terms, int byz_mode, float byz_scale, int straggle_us) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   char* me = f.peers.base[f.rank];
@@ -160,7 +167,15 @@ k_upload(FedArgs f, int n_samples, int n_loss_terms, int byz_mode, float byz_sca
   __syncthreads();
   if (!last) return;
   __threadfence_system();
-  if (threadIdx.x < f.n_ranks) {
+  // first-K-wins admission: one ticket per trainer and round; late tickets publish nothing
+  __shared__ int ticket;
+  if (threadIdx.x == 0) {
+    admit::straggle(straggle_us);
+    ticket = admit::first_k(st) ? admit::take_ticket(&admit::page(f.peers.base[0], f.lay, par)->ticket, epoch) : 0;
+    if (ticket >= static_cast<int>(st->n_needed) && admit::first_k(st)) ticket = -1;
+  }
+  __syncthreads();
+  if (ticket >= 0 && threadIdx.x < f.n_ranks) {
     const int r = threadIdx.x;
     UploadMeta* meta = at<UploadMeta>(f.peers.base[r], f.lay.meta_off) + par * kMaxRanks + f.rank;
     UploadMeta m;
@@ -168,6 +183,9 @@ k_upload(FedArgs f, int n_samples, int n_loss_terms, int byz_mode, float byz_sca
     m.avg_cost = plan->loss_sum / static_cast<float>(n_loss_terms > 0 ? n_loss_terms : 1);
     *meta = m;
     __threadfence_system();
+    if (admit::first_k(st))
+      ptx::st_release_sys(&admit::page(f.peers.base[r], f.lay, par)->slot[ticket],
+                          ((epoch + 1u) << 8) | static_cast<uint32_t>(f.rank));
     ptx::st_release_sys(at<uint32_t>(f.peers.base[r], f.lay.flags_off) + FLAG_TRAINED + f.rank,
                         epoch + 1);
   }
@@ -207,6 +225,21 @@ k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc)
   const bool i_am_comm = (st->role[f.rank] & ROLE_COMM) != 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) stamp(plan, STAMP_CONS_BEGIN);
 
+  // first-K-wins: candidate slot z -> admitted trainer (every block resolves all K slots; the
+  // acquire also makes those trainers' uploads readable)
+  const bool fk = admit::first_k(st);
+  __shared__ int cand_of[kMaxRanks];
+  __shared__ uint32_t adm_mask;
+  if (threadIdx.x == 0) {
+    uint32_t m = 0;
+    for (int z = 0; z < plan->n_cand; ++z) {
+      cand_of[z] = fk ? admit::wait_slot(admit::page(me, f.lay, par), z, epoch) : plan->cand_rank[z];
+      m |= 1u << cand_of[z];
+    }
+    adm_mask = m;
+  }
+  __syncthreads();
+
   // (a) committee: push my score row into every replica's ledger page, then release.
   if (blockIdx.x == 0 && i_am_comm) {
     if (threadIdx.x < n) {
@@ -214,7 +247,7 @@ k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc)
       float* row = at<float>(f.peers.base[r], f.lay.scores_off) +
                    (par * kMaxRanks + f.rank) * kMaxRanks;
       for (int z = 0; z < plan->n_cand; ++z)
-        row[plan->cand_rank[z]] =
+        row[cand_of[z]] =
             static_cast<float>(plan->correct[z]) / static_cast<float>(n_val > 0 ? n_val : 1);
       __threadfence_system();
       ptx::st_release_sys(at<uint32_t>(f.peers.base[r], f.lay.flags_off) + FLAG_SCORED + f.rank,
@@ -226,7 +259,9 @@ k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc)
   if (threadIdx.x < n) {
     const int r = threadIdx.x;
     if (st->role[r] & ROLE_COMM) ptx::wait_flag_ge(flags + FLAG_SCORED + r, epoch + 1);
-    if (st->role[r] & ROLE_TRAINER) ptx::wait_flag_ge(flags + FLAG_TRAINED + r, epoch + 1);
+    // every admitted trainer's upload (first-K-wins: only the K ticket holders -- a straggler or
+    // a dead trainer beyond them is not waited for)
+    if ((st->role[r] & ROLE_TRAINER) && ((adm_mask >> r) & 1u)) ptx::wait_flag_ge(flags + FLAG_TRAINED + r, epoch + 1);
   }
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x == 0) stamp(plan, STAMP_CONS_SCORED);
@@ -242,14 +277,15 @@ k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc)
     const int i = threadIdx.x;
     if (i < kMaxRanks * kMaxRanks) {
       const int r = i / kMaxRanks, t = i % kMaxRanks;
-      const bool ok = r < n && t < n && (st->role[r] & ROLE_COMM) && (st->role[t] & ROLE_TRAINER);
+      const bool ok = r < n && t < n && (st->role[r] & ROLE_COMM) && (st->role[t] & ROLE_TRAINER) &&
+                      ((adm_mask >> t) & 1u);
       in.scored[r][t] = ok ? 1 : 0;
       in.score[r][t] =
           ok ? __uint_as_float(ptx::ld_relaxed_sys(reinterpret_cast<const uint32_t*>(rows + r * kMaxRanks + t))) : 0.f;
     } else if (i < kMaxRanks * kMaxRanks + kMaxRanks) {
       const int r = i - kMaxRanks * kMaxRanks;
       in.role[r] = r < n ? st->role[r] : 0u;
-      in.admitted[r] = (r < n && (st->role[r] & ROLE_TRAINER)) ? 1 : 0;
+      in.admitted[r] = (r < n && (st->role[r] & ROLE_TRAINER) && ((adm_mask >> r) & 1u)) ? 1 : 0;
       in.n_samples[r] = r < n ? ptx::ld_relaxed_sys(&meta[r].n_samples) : 0u;
       in.avg_cost[r] =
           r < n ? __uint_as_float(ptx::ld_relaxed_sys(reinterpret_cast<const uint32_t*>(&meta[r].avg_cost))) : 0.f;
@@ -487,12 +523,16 @@ k_pull(FedArgs f, uint4* stage_shadow, float4* stage_master) {
   const int z = blockIdx.y;
   if (z >= plan->n_cand) return;
   if (blockIdx.x == 0 && z == 0 && threadIdx.x == 0) stamp(plan, STAMP_PULL_BEGIN);
-  const int t = plan->cand_rank[z];
   const uint32_t epoch = st->epoch;
   const uint32_t par = epoch & 1u;
-  if (threadIdx.x == 0)
-    ptx::wait_flag_ge(at<uint32_t>(me, f.lay.flags_off) + FLAG_TRAINED + t, epoch + 1);
+  __shared__ int t_sh;
+  if (threadIdx.x == 0) {
+    const int tt = admit::first_k(st) ? admit::wait_slot(admit::page(me, f.lay, par), z, epoch) : plan->cand_rank[z];
+    ptx::wait_flag_ge(at<uint32_t>(me, f.lay.flags_off) + FLAG_TRAINED + tt, epoch + 1);
+    t_sh = tt;
+  }
   __syncthreads();
+  const int t = t_sh;
   const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   {
@@ -527,11 +567,16 @@ k_pull_blob(FedArgs f, long long off0, long long off1, long long nbytes, uint8_t
   const int z = blockIdx.y;
   if (z >= plan->n_cand) return;
   if (blockIdx.x == 0 && z == 0 && threadIdx.x == 0) stamp(plan, STAMP_PULL_BEGIN);
-  const int t = plan->cand_rank[z];
   const uint32_t epoch = st->epoch;
-  if (threadIdx.x == 0)
-    ptx::wait_flag_ge(at<uint32_t>(me, f.lay.flags_off) + FLAG_TRAINED + t, epoch + 1);
+  __shared__ int t_sh;
+  if (threadIdx.x == 0) {
+    const int tt = admit::first_k(st) ? admit::wait_slot(admit::page(me, f.lay, epoch & 1u), z, epoch)
+                                      : plan->cand_rank[z];
+    ptx::wait_flag_ge(at<uint32_t>(me, f.lay.flags_off) + FLAG_TRAINED + tt, epoch + 1);
+    t_sh = tt;
+  }
   __syncthreads();
+  const int t = t_sh;
   const long long nv = nbytes / 16;
   const float4* src = at<const float4>(f.peers.base[t], (epoch & 1u) ? off1 : off0);
   float4* dst = reinterpret_cast<float4*>(stage + static_cast<long long>(z) * nbytes);
@@ -577,10 +622,10 @@ cudaError_t fed_plan_round(const FedArgs& f, const PlanLayer* layers, int n_laye
 }
 
 cudaError_t fed_upload(const FedArgs& f, int n_samples, int n_loss_terms, int byz_mode,
-                       float byz_scale, cudaStream_t s) {
+                       float byz_scale, cudaStream_t s, int straggle_us) {
   note_launch();
   return launch_pdl(k_upload, dim3(fed_grid(f.lay.n_params)), dim3(kFedThreads), 0, s, f, n_samples,
-                    n_loss_terms, byz_mode, byz_scale);
+                    n_loss_terms, byz_mode, byz_scale, straggle_us);
 }
 
 cudaError_t fed_consensus_aggregate(const FedArgs& f, int n_val, int weight_by_score,

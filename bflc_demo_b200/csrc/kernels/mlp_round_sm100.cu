@@ -47,6 +47,7 @@
 
 #include "bflc_kernels.h"
 #include "epi_common.cuh"
+#include "fed_admit.cuh"
 #include "launch.cuh"
 #include "sm100_ptx.cuh"
 
@@ -128,7 +129,7 @@ struct Args {
   int bm_w;                      // weight-gradient tile height: 64 (default) or 128
   // fused upload
   int has_fed; FedArgs f; long long upq_off[2];
-  int n_samples, n_loss_terms, byz_mode; float byz_scale;
+  int n_samples, n_loss_terms, byz_mode; float byz_scale; int straggle_us;
 };
 
 struct Job {  // one output tile (bm rows x 64 columns)
@@ -1236,7 +1237,18 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
     const uint32_t epoch = st->epoch;
     const uint32_t par = epoch & 1u;
     if (threadIdx.x == 0) atomicMax(&plan->t_stamp[STAMP_UPLOAD_BEGIN], globaltimer_ns());
-    if (threadIdx.x < a.f.n_ranks) {
+    // first-K-wins admission (C:239-244): one ticket per trainer and round from the counter on
+    // rank 0's page; a ticket beyond NEEDED_UPDATE_COUNT publishes nothing (update dropped)
+    __shared__ int ticket;
+    const bool fk = admit::first_k(st);
+    if (threadIdx.x == 0) {
+      admit::straggle(a.straggle_us);
+      int tk = fk ? admit::take_ticket(&admit::page(a.f.peers.base[0], a.f.lay, par)->ticket, epoch) : 0;
+      if (fk && tk >= static_cast<int>(st->n_needed)) tk = -1;
+      ticket = tk;
+    }
+    __syncthreads();
+    if (ticket >= 0 && threadIdx.x < a.f.n_ranks) {
       const int r = threadIdx.x;
       UploadMeta* meta = heap_at<UploadMeta>(a.f.peers.base[r], a.f.lay.meta_off) + par * kMaxRanks + a.f.rank;
       UploadMeta m;
@@ -1244,6 +1256,9 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
       m.avg_cost = __ldcg(a.loss_sum) / static_cast<float>(a.n_loss_terms > 0 ? a.n_loss_terms : 1);
       *meta = m;
       __threadfence_system();
+      if (fk)
+        ptx::st_release_sys(&admit::page(a.f.peers.base[r], a.f.lay, par)->slot[ticket],
+                            ((epoch + 1u) << 8) | static_cast<uint32_t>(a.f.rank));
       ptx::st_release_sys(heap_at<uint32_t>(a.f.peers.base[r], a.f.lay.flags_off) + FLAG_TRAINED + a.f.rank,
                           epoch + 1);
     }
@@ -1356,6 +1371,7 @@ cudaError_t mlp_round_sm100(const MlpRoundArgs& r, cudaStream_t stream) {
   if (r.fed != nullptr) a.f = *r.fed;
   a.upq_off[0] = r.upq_off[0]; a.upq_off[1] = r.upq_off[1];
   a.n_samples = r.n_samples; a.n_loss_terms = r.n_loss_terms; a.byz_mode = r.byz_mode; a.byz_scale = r.byz_scale;
+  a.straggle_us = r.straggle_us;
 
   static bool configured[2] = {false, false};
   if (!configured[fp8 ? 1 : 0]) {

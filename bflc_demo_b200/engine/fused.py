@@ -129,7 +129,8 @@ class FusedEngine:
 
         # ledger page + host chain
         roles = initial_roles(cfg)
-        st = self.mod.state_init_bytes(world, cfg.committee_size, cfg.aggregate_count, roles)
+        st = self.mod.state_init_bytes(world, cfg.committee_size, cfg.aggregate_count, roles,
+                                       cfg.needed_updates)
         self.state_bytes.copy_(torch.frombuffer(bytearray(st), dtype=torch.uint8))
         self.host_ledger = _ledger().Ledger(cfg.to_ledger_config(P))
         self.host_ledger.Bootstrap(roles)
@@ -231,6 +232,12 @@ class FusedEngine:
         self.two_shot = (cfg.two_shot if cfg.two_shot is not None
                          else world > 1 and (P * 4 > (64 << 20) or world >= 8))
         self.byz = 1 if rank in cfg.byzantine_ranks else 0
+        self.straggle_us = cfg.straggler_delay_us if rank in cfg.straggler_ranks else 0
+        # first-K-wins admission (needed_updates < trainers): candidate slots are resolved on the
+        # device from the admission tickets, which needs the staged (pull) validation path
+        self.first_k = (not cfg.solo) and cfg.needed_updates < cfg.n_trainers
+        if self.first_k and not self.staged:
+            raise ValueError("needed_updates < trainers (first-K-wins admission) needs stage_candidates=True")
         self.fused_step = bool(cfg.fused_step) and self.trainer.fused_ok(self.steps)
         # UploadLocalUpdate inside the trainer's last optimizer epilogue (needs E_OPT)
         self.fused_upload = self.fused_step and os.environ.get("BFLC_MLP_EPIOPT", "1") != "0"
@@ -311,7 +318,7 @@ class FusedEngine:
             # fused_upload its last optimizer epilogue publishes the update (UploadLocalUpdate).
             up = dict(fed=self.fed, upq_off=self.upq_off, n_samples=self.S,
                       n_loss_terms=self.steps * B, byz_mode=self.byz,
-                      byz_scale=cfg.byzantine_scale) if self.fused_upload else {}
+                      byz_scale=cfg.byzantine_scale, straggle_us=self.straggle_us) if self.fused_upload else {}
             self.trainer.train_epoch_fused(
                 self.x_bf, self.y, self.steps, self.plan_ptr + self.sz["plan_step_barrier_off"],
                 None, -1, -1,
@@ -323,7 +330,7 @@ class FusedEngine:
         if pipe:
             main.wait_event(self._ev_join)      # validation reads every converted row
         if not (self.fused_step and self.fused_upload):
-            m.fed_upload(self.fed, self.S, self.steps * B, self.byz, cfg.byzantine_scale)
+            m.fed_upload(self.fed, self.S, self.steps * B, self.byz, cfg.byzantine_scale, self.straggle_us)
         # committee validation: grouped GEMMs whose B operands are the trainers' uploads
         if self.staged:
             if self.fp8:

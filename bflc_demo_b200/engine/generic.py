@@ -83,7 +83,8 @@ class GenericFedEngine:
         self.bound = net.bind(self.work_master, self.work_shadow, self.grad)
 
         roles = initial_roles(cfg)
-        st = self.mod.state_init_bytes(world, cfg.committee_size, cfg.aggregate_count, roles)
+        st = self.mod.state_init_bytes(world, cfg.committee_size, cfg.aggregate_count, roles,
+                                       cfg.needed_updates)
         self.state_bytes.copy_(torch.frombuffer(bytearray(st), dtype=torch.uint8))
         self.host_ledger = _ledger().Ledger(cfg.to_ledger_config(P))
         self.host_ledger.Bootstrap(roles)
@@ -93,6 +94,7 @@ class GenericFedEngine:
         self.y = shard.y.to(self.dev, torch.int32)
         self.two_shot = cfg.two_shot if cfg.two_shot is not None else (P * 4 > (64 << 20) and world > 1)
         self.byz = 1 if rank in cfg.byzantine_ranks else 0
+        self.straggle_us = cfg.straggler_delay_us if rank in cfg.straggler_ranks else 0
         self._peer_bounds = {}
         self._stage = None
         self._rounds = 0
@@ -219,7 +221,8 @@ class GenericFedEngine:
                     self.graph_train.replay()
                 else:
                     self.local_training()
-            m.fed_upload(self.fed, self.S, self.steps * cfg.batch_size, self.byz, cfg.byzantine_scale)
+            m.fed_upload(self.fed, self.S, self.steps * cfg.batch_size, self.byz, cfg.byzantine_scale,
+                         self.straggle_us)
             if role & ROLE_COMM:
                 if self.graph_val is not None:
                     self.graph_val.replay()

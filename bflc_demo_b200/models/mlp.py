@@ -149,7 +149,8 @@ class FlatMLP:
                           epiopt: int = -1, x_ready_ptr: int = 0, round_seq_ptr: int = 0,
                           x_q: Optional[torch.Tensor] = None, x_sf: Optional[torch.Tensor] = None,
                           fed: Optional[dict] = None, upq_off=(), n_samples: int = 0,
-                          n_loss_terms: int = 0, byz_mode: int = 0, byz_scale: float = 0.0) -> None:
+                          n_loss_terms: int = 0, byz_mode: int = 0, byz_scale: float = 0.0,
+                          straggle_us: int = 0) -> None:
         """All ``steps`` mini-batch steps in ONE persistent kernel launch; ``barrier_ptr`` is a
         device uint32 that is zero on entry (the phase barrier).  ``dbg``: optional int64
         [steps, 32] buffer that receives %globaltimer phase stamps of CTA 0.  ``plan`` /
@@ -170,7 +171,7 @@ class FlatMLP:
                       x_q if self.fp8 else None, x_sf if self.fp8 else None,
                       self.work_q if self.fp8 else None, self.h_q if self.fp8 else None,
                       self.h_sf if self.fp8 else None, fed, list(upq_off), n_samples, n_loss_terms,
-                      byz_mode, byz_scale)
+                      byz_mode, byz_scale, straggle_us)
 
     # ------------------------------------------------------------ evaluation
     def accuracy_counts(self, X: torch.Tensor, Y: torch.Tensor, shadow: Optional[torch.Tensor] = None,

@@ -42,6 +42,7 @@ class HeapLayout:
         take("plan", sz["RoundPlan"])
         take("scores", 2 * K * K * 4 + 2 * K * 8)   # score rows by parity + two-shot slice digests
         take("meta", 2 * K * sz["UploadMeta"])
+        take("admit", 2 * sz["AdmitPage"])              # first-K-wins admission: ticket + slots, by parity
         take("ring", self.ring_slots * sz["BlockRecord"])
         f32, b16 = self.n_params * 4, self.n_params * 2
         take("work_master", f32, 4096)
@@ -64,4 +65,5 @@ class HeapLayout:
                     upload_master_off=[o["upload_master0"], o["upload_master1"]],
                     upload_shadow_off=[o["upload_shadow0"], o["upload_shadow1"]],
                     global_off=o["global"], global_shadow_off=o["global_shadow"],
-                    ring_off=o["ring"], n_params=self.n_params, ring_slots=self.ring_slots)
+                    ring_off=o["ring"], n_params=self.n_params, ring_slots=self.ring_slots,
+                    admit_off=o["admit"])

@@ -8,6 +8,9 @@ Checks:
   two_shot    two-shot (slice-reduce + publish) aggregation gives the same digest as one-shot
   multicast   the same through NVLS multimem stores when the heap has a multicast mapping
   generic     LeNet-5 through the model-agnostic engine (validation on peers' HBM)
+  firstk      device-side first-K-wins admission (C:239-244): needed_updates = trainers - 1 and one
+              artificially slow trainer -- every round completes with exactly K admitted, the
+              straggler's update is dropped, the host ledger re-executes from the admitted mask
   fedavg      the aggregated global model is RIGHT, not just identical: after every round each rank
               recomputes sum_k w_k * upload_k (selected set + weights from the host ledger's block,
               uploads read out of the trainers' HBM, ascending rank order, fp32 fma) in PyTorch and
@@ -91,6 +94,34 @@ def main():
                              loss=r["loss"], multicast=r["symm"]["multicast"],
                              multicast_error=r["symm"]["multicast_error"], notes=r["symm"]["notes"])
         out["two_shot"] = res
+    if "firstk" in which and world >= 4:
+        res = {}
+        slow = world - 1
+        for dt in ("bf16", "fp8"):
+            base = FLConfig.for_world(world)
+            k = base.n_trainers - 1
+            cfg = FLConfig.for_world(world, needed_updates=k, hidden=256, batch_size=128,
+                                     samples_per_client=512, learning_rate=0.05, dtype=dt,
+                                     straggler_ranks=[slow], straggler_delay_us=400)
+            shard = femnist_like(world, 512, seed=3, only=rank)[0]
+            eng = FusedEngine(cfg, shard, rank=rank, world=world, device=lr)
+            eng.capture()
+            for _ in range(6):
+                eng.run_round()
+            errs = eng.drain_blocks()
+            st = eng.read_state()
+            blocks = eng.host_ledger.blocks()
+            g = gather(dict(digest=st["model_digest"], errs=errs, epoch=st["epoch"]))
+            res[dt] = dict(k=k, trainers=cfg.n_trainers, epoch=st["epoch"],
+                           admitted_per_round=[len(b["admitted"]) for b in blocks],
+                           slow_rank=slow, slow_was_trainer=sum(b["role_before"][slow] == 1 for b in blocks),
+                           slow_admitted=sum(slow in b["admitted"] for b in blocks),
+                           identical=len({i["digest"] for i in g}) == 1,
+                           errs=sum((i["errs"] for i in g), []), chain_ok=eng.host_ledger.verify_chain())
+            torch.cuda.synchronize(); dist.barrier()
+            del eng
+            torch.cuda.synchronize(); dist.barrier()
+        out["firstk"] = res
     if "fedavg" in which:
         res = {}
         for dt in ("bf16", "fp8"):

@@ -52,6 +52,21 @@ def test_fedavg_result_equals_weighted_mean_of_uploads():
                                                  #  double-round a rare element by one ulp)
 
 
+def test_first_k_admission_drops_the_straggler():
+    """NEEDED_UPDATE_COUNT < trainers on the device path (C:239-244): with one slow trainer every
+    round still completes, exactly K updates are admitted, the slow one is dropped while it is a
+    trainer, all replicas agree and the host ledger re-executes every election from the
+    admitted mask."""
+    n, res = _run(["firstk"])
+    if n < 4:
+        pytest.skip("first-K admission needs >= 2 trainers: >= 4 GPUs")
+    for dt in ("bf16", "fp8"):
+        r = res["firstk"][dt]
+        assert r["errs"] == [] and r["identical"] and r["chain_ok"] and r["epoch"] == 7
+        assert all(a == r["k"] for a in r["admitted_per_round"]), r
+        assert r["slow_was_trainer"] >= 5 and r["slow_admitted"] == 0, r
+
+
 def test_generic_engine_and_byzantine_multi_gpu():
     n, res = _run(["generic", "byzantine"])
     g = res["generic_lenet5"]
