@@ -135,6 +135,28 @@ void bind_nn(py::module_& m) {
     p.act = static_cast<bflc::Act>(act);
     check(bflc::gemm_mx8_sm100(p, st()), "gemm_mx8_sm100");
   });
+  // fused attention (seq 128, head dim 64): q, k, v, o, gradients are [B*S, H*64] bf16
+  m.def("attention_fwd", [](at::Tensor q, at::Tensor k, at::Tensor v, at::Tensor o, at::Tensor lse, int B,
+                            int S, int H, double scale) {
+    const int D = (int)q.size(1) / H;
+    TORCH_CHECK(q.stride(1) == 1 && k.stride(1) == 1 && v.stride(1) == 1 && o.stride(1) == 1 &&
+                q.stride(0) == k.stride(0) && q.stride(0) == v.stride(0) && q.stride(0) == o.stride(0),
+                "attention: q, k, v, o must share one row pitch");
+    check(bflc::attention_fwd_sm100(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr<float>(),
+                                    B, S, H, D, q.stride(0), (float)scale, st()),
+          "attention_fwd_sm100");
+  });
+  m.def("attention_bwd", [](at::Tensor q, at::Tensor k, at::Tensor v, at::Tensor o, at::Tensor dout, at::Tensor lse,
+                            at::Tensor dq, at::Tensor dk, at::Tensor dv, int B, int S, int H, double scale) {
+    const int D = (int)q.size(1) / H;
+    const int64_t ld = q.stride(0);
+    for (const at::Tensor* t : {&k, &v, &o, &dout, &dq, &dk, &dv})
+      TORCH_CHECK(t->stride(1) == 1 && t->stride(0) == ld, "attention: all operands must share one row pitch");
+    check(bflc::attention_bwd_sm100(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), dout.data_ptr(),
+                                    lse.data_ptr<float>(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, S, H, D,
+                                    ld, (float)scale, st()),
+          "attention_bwd_sm100");
+  });
   m.def("transpose_0213", [](at::Tensor x, at::Tensor y, int d0, int d1, int d2, int d3) {
     check(bflc::transpose_0213_bf16(x.data_ptr(), y.data_ptr(), d0, d1, d2, d3, st()),
           "transpose_0213");

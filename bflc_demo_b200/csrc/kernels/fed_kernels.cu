@@ -324,7 +324,8 @@ k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc)
   const long long nv = f.lay.n_params / 4;
   long long lo = 0, hi = nv;
   if (two_shot) {  // each rank reduces only its own slice, then publishes it to every peer
-    const long long per = (nv + n - 1) / n;
+    long long per = (nv + n - 1) / n;
+    per += per & 1;   // even slices: two neighbouring lanes pair their bf16 halves into one 16-byte store
     lo = per * f.rank;
     hi = lo + per < nv ? lo + per : nv;
     if (lo > nv) lo = nv;
@@ -364,10 +365,16 @@ k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc)
       // one NVLS store per destination buffer lands in all replicas
       ptx::multimem_st_f4(at<float4>(f.peers.mc_base, f.lay.global_off) + i, acc);
       ptx::multimem_st_f4(at<float4>(f.peers.mc_base, f.lay.work_master_off) + i, acc);
-      // bf16 copies: two uint2 make one 16-byte multimem store only when paired; keep P2P
-      for (int r = 0; r < n; ++r) {
-        at<uint2>(f.peers.base[r], f.lay.global_shadow_off)[i] = b;
-        at<uint2>(f.peers.base[r], f.lay.work_shadow_off)[i] = b;
+      // bf16 copies: the even lane of each lane pair takes its neighbour's 8 bytes and issues ONE
+      // 16-byte multimem store per buffer (slices are even, so pairs are never split); before,
+      // these were 2 x n_ranks 8-byte P2P stores per thread -- 80 % of the publish traffic
+      const unsigned am = __activemask();
+      const uint32_t ox = __shfl_down_sync(am, b.x, 1), oy = __shfl_down_sync(am, b.y, 1);
+      if ((i & 1) == 0) {
+        const float4 pk = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(ox),
+                                      __uint_as_float(oy));
+        ptx::multimem_st_f4(at<float4>(f.peers.mc_base, f.lay.global_shadow_off) + (i >> 1), pk);
+        ptx::multimem_st_f4(at<float4>(f.peers.mc_base, f.lay.work_shadow_off) + (i >> 1), pk);
       }
     } else {
       for (int r = 0; r < n; ++r) {

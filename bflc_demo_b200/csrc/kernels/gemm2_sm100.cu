@@ -1,4 +1,14 @@
-// 2-CTA tcgen05 GEMM (cta_group::2) for large K-major problems.
+// 2-CTA tcgen05 GEMM (cta_group::2) for large K-major problems -- persistent, with the TMEM
+// accumulator double-buffered so the epilogue of tile i drains under the mainloop of tile i+1.
+//
+// 74 CTA pairs (one per TPC, 148 SMs) walk the tile list with a static stride; the TMA ring, its
+// mbarriers and the 512-column TMEM allocation (2 x 256 accumulator columns) live for the whole
+// kernel.  Hand-offs: `tmem_full[b]` (MMA commit, multicast to both CTAs) tells the epilogue warps
+// that accumulator b is complete; `tmem_empty[b]` on the LEADER collects one arrive per epilogue
+// warp of BOTH CTAs (the peer's warps arrive remotely through the cluster address) before the
+// leader's MMA thread may overwrite buffer b.  Before this change every tile paid a launch slot,
+// a TMEM allocation, barrier init and an exposed epilogue: 577 TFLOP/s at 16384 x 1024 x 1024
+// against cuBLAS' 1078 (16 K-blocks per tile cannot hide any of it).
 //
 // A CTA pair (cluster 2x1, both SMs of one TPC) computes one 256 x 256 output tile:
 // each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N-rows) per
@@ -33,12 +43,14 @@ constexpr int kTileBytes = kStages * kStageBytes;
 constexpr int kBarBytes = 256;
 using epi::kStgLd;
 using epi::kStgBytes;
-constexpr int kSmemTotal = kTileBytes + kBarBytes + kStgBytes + kBN * 4 + 1024;
+constexpr int kSmemTotal = kTileBytes + kBarBytes + kStgBytes + 2 * kBN * 4 + 1024;
+constexpr int kAccBufs = 2;
 constexpr int kThreads = 192;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
 
 struct P2 {
   int M, N, K, k_blocks;
+  int m_pairs, n_tiles;      // tile grid: 256-row pair tiles x 256-column tiles (M fastest)
   void* d; int d_dtype; long long ldd; float alpha;
   const float* bias; int act;
 };
@@ -94,17 +106,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kTileBytes);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* accum_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tmem_full = empty_bar + kStages;           // [kAccBufs] accumulator b complete (both CTAs)
+  uint64_t* tmem_empty = tmem_full + kAccBufs;         // [kAccBufs] leader only: accumulator b drained by all 8 warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccBufs);
   float* stage_base = reinterpret_cast<float*>(smem + kTileBytes + kBarBytes);
-  float* sbias = stage_base + 4 * 32 * kStgLd;
+  float* sbias = stage_base + 4 * 32 * kStgLd;         // [2][kBN]: double-buffered with the accumulator
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1;                 // cluster index along x
-  const int n0 = blockIdx.y * kBN;
-  const int m0 = pair * (2 * kBM) + static_cast<int>(rank) * kBM;
+  const int n_clusters = gridDim.x >> 1;
+  const int cluster = blockIdx.x >> 1;
+  const int n_tiles_total = p.m_pairs * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmA);
@@ -113,12 +126,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       ptx::mbar_init(&full_bar[s], 2);   // leader's expect_tx arrive + the peer's remote arrive
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(accum_bar, 1);
+    for (int b = 0; b < kAccBufs; ++b) {
+      ptx::mbar_init(&tmem_full[b], 1);
+      ptx::mbar_init(&tmem_empty[b], 8);   // 4 epilogue warps x 2 CTAs
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     ptx::smem_u32(tmem_slot)), "r"(kBN) : "memory");
+                     ptx::smem_u32(tmem_slot)), "r"(kAccBufs * kBN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   ptx::tc_fence_before_sync();
@@ -128,20 +144,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int n_kb = p.k_blocks;
 
   if (warp == 0) {
-    for (int i = 0; i < n_kb; ++i) {
-      const int s = i % kStages;
-      const uint32_t ph = (i / kStages) & 1;
-      ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-      uint8_t* sa = smem + s * kStageBytes;
-      uint8_t* sb = sa + kABytes;
-      const uint32_t full_leader = ptx::smem_u32(&full_bar[s]) & kPeerMask;
-      if (ptx::elect_one()) {
-        if (leader) ptx::mbar_expect_tx(&full_bar[s], 2 * kStageBytes);
-        else mbar_arrive_cluster(full_leader);
-        tma_load_3d_2sm(sa, &tmA, full_leader, i * 64, m0, 0);
-        tma_load_3d_2sm(sb, &tmB, full_leader, i * 64, n0 + static_cast<int>(rank) * (kBN / 2), 0);
+    uint32_t it = 0;
+    for (int t = cluster; t < n_tiles_total; t += n_clusters) {
+      const int m0 = (t % p.m_pairs) * (2 * kBM) + static_cast<int>(rank) * kBM;
+      const int n0 = (t / p.m_pairs) * kBN;
+      for (int i = 0; i < n_kb; ++i, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * kStageBytes;
+        uint8_t* sb = sa + kABytes;
+        const uint32_t full_leader = ptx::smem_u32(&full_bar[s]) & kPeerMask;
+        if (ptx::elect_one()) {
+          if (leader) ptx::mbar_expect_tx(&full_bar[s], 2 * kStageBytes);
+          else mbar_arrive_cluster(full_leader);
+          tma_load_3d_2sm(sa, &tmA, full_leader, i * 64, m0, 0);
+          tma_load_3d_2sm(sb, &tmB, full_leader, i * 64, n0 + static_cast<int>(rank) * (kBN / 2), 0);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
     if (leader) {
@@ -151,94 +172,116 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t base_lo = ptx::smem_u32(smem) >> 4;
       const uint32_t lo_a0 = base_lo | (1u << 16);
       const uint32_t lo_b0 = (base_lo + (kABytes >> 4)) | (1u << 16);
-      for (int i = 0; i < n_kb; ++i) {
-        const int s = i % kStages;
-        const uint32_t ph = (i / kStages) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tile = 0;
+      for (int t = cluster; t < n_tiles_total; t += n_clusters, ++tile) {
+        const uint32_t b = tile & 1u, use = tile >> 1;
+        // buffer b was drained by the epilogue of tile - 2 (first two tiles: free)
+        ptx::mbar_wait(&tmem_empty[b], (use & 1u) ^ 1u);
         ptx::tc_fence_after_sync();
-        const uint32_t so = static_cast<uint32_t>(s) * (kStageBytes >> 4);
-        if (ptx::elect_one()) {
+        const uint32_t tacc = tmem_base + b * kBN;
+        for (int i = 0; i < n_kb; ++i, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after_sync();
+          const uint32_t so = static_cast<uint32_t>(s) * (kStageBytes >> 4);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (lo_a0 + so + k * 2u);
-            const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (lo_b0 + so + k * 2u);
-            umma2_f16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (lo_a0 + so + k * 2u);
+              const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (lo_b0 + so + k * 2u);
+              umma2_f16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            }
+            umma2_commit_mc(&empty_bar[s]);
           }
-          umma2_commit_mc(&empty_bar[s]);
+          __syncwarp();
         }
+        if (ptx::elect_one()) umma2_commit_mc(&tmem_full[b]);
         __syncwarp();
       }
-      if (ptx::elect_one()) umma2_commit_mc(accum_bar);
-      __syncwarp();
     }
   } else {
     const int q = warp & 3;
     float* stg = stage_base + (warp - 2) * (32 * kStgLd);
-    const int row_base = m0 + q * 32;
     const int cr = lane >> 3, cg = (lane & 7) * 4;
-    {
-      const int et = threadIdx.x - 64;
-      for (int i = et; i < kBN; i += 128)
-        sbias[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-    ptx::mbar_wait(accum_bar, 0);
-    ptx::tc_fence_after_sync();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t empty_leader = ptx::smem_u32(&tmem_empty[0]) & kPeerMask;
+    uint32_t tile = 0;
+    for (int t = cluster; t < n_tiles_total; t += n_clusters, ++tile) {
+      const uint32_t b = tile & 1u, use = tile >> 1;
+      const int m0 = (t % p.m_pairs) * (2 * kBM) + static_cast<int>(rank) * kBM;
+      const int n0 = (t / p.m_pairs) * kBN;
+      const int row_base = m0 + q * 32;
+      float* sb = sbias + b * kBN;
+      {
+        // bias of this tile's columns (buffer b of sbias was last read two tiles ago: every
+        // epilogue warp has since passed a bar.sync of tile - 1)
+        const int et = threadIdx.x - 64;
+        for (int i = et; i < kBN; i += 128)
+          sb[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      ptx::mbar_wait(&tmem_full[b], use & 1u);
+      ptx::tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + b * kBN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < kBN / 32; ++c) {
-      const int nc = n0 + c * 32;
-      if (nc >= p.N) break;
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
-      ptx::tmem_ld_wait();
-      float4* rowp = reinterpret_cast<float4*>(stg + lane * kStgLd);
+      for (int c = 0; c < kBN / 32; ++c) {
+        const int nc = n0 + c * 32;
+        if (nc >= p.N) break;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        float4* rowp = reinterpret_cast<float4*>(stg + lane * kStgLd);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v[4];
+        for (int j = 0; j < 8; ++j) {
+          float v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float x = __uint_as_float(r[4 * j + k]) * p.alpha + sbias[c * 32 + 4 * j + k];
-          if (p.act == 1) x = fmaxf(x, 0.f);
-          else if (p.act == 2) x = gelu_f(x);
-          v[k] = x;
-        }
-        rowp[j] = make_float4(v[0], v[1], v[2], v[3]);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + cr, rw = row_base + rr, col = nc + cg;
-        if (rw >= p.M || col >= p.N) continue;
-        const float4 x = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cg);
-        const long long off = static_cast<long long>(rw) * p.ldd + col;
-        const bool vec = col + 3 < p.N;
-        if (p.d_dtype == 0) {
-          float* d = reinterpret_cast<float*>(p.d) + off;
-          if (vec) *reinterpret_cast<float4*>(d) = x;
-          else {
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-            for (int k = 0; k < 4; ++k) if (col + k < p.N) d[k] = xs[k];
+          for (int k = 0; k < 4; ++k) {
+            float x = __uint_as_float(r[4 * j + k]) * p.alpha + sb[c * 32 + 4 * j + k];
+            if (p.act == 1) x = fmaxf(x, 0.f);
+            else if (p.act == 2) x = gelu_f(x);
+            v[k] = x;
           }
-        } else {
-          __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.d) + off;
-          if (vec) *reinterpret_cast<uint2*>(d) = make_uint2(pack2(x.x, x.y), pack2(x.z, x.w));
-          else {
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-            for (int k = 0; k < 4; ++k) if (col + k < p.N) d[k] = __float2bfloat16(xs[k]);
+          rowp[j] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + cr, rw = row_base + rr, col = nc + cg;
+          if (rw >= p.M || col >= p.N) continue;
+          const float4 x = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cg);
+          const long long off = static_cast<long long>(rw) * p.ldd + col;
+          const bool vec = col + 3 < p.N;
+          if (p.d_dtype == 0) {
+            float* d = reinterpret_cast<float*>(p.d) + off;
+            if (vec) *reinterpret_cast<float4*>(d) = x;
+            else {
+              const float xs[4] = {x.x, x.y, x.z, x.w};
+              for (int k = 0; k < 4; ++k) if (col + k < p.N) d[k] = xs[k];
+            }
+          } else {
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.d) + off;
+            if (vec) *reinterpret_cast<uint2*>(d) = make_uint2(pack2(x.x, x.y), pack2(x.z, x.w));
+            else {
+              const float xs[4] = {x.x, x.y, x.z, x.w};
+              for (int k = 0; k < 4; ++k) if (col + k < p.N) d[k] = __float2bfloat16(xs[k]);
+            }
           }
         }
+        __syncwarp();
       }
+      // this warp's quarter of accumulator b is in registers / memory: hand the buffer back to
+      // the leader's MMA thread (one arrive per warp, remote for the peer CTA)
+      ptx::tc_fence_before_sync();
       __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(empty_leader + b * 8u);
     }
-    ptx::tc_fence_before_sync();
   }
   // both CTAs must be done with the pair's TMEM / smem before either tears down
   ptx::tc_fence_before_sync();
   cluster_sync_all();
   if (warp == 1) {
     ptx::tc_fence_after_sync();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kBN)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAccBufs * kBN)
                  : "memory");
   }
 }
@@ -259,6 +302,7 @@ cudaError_t gemm2_sm100(const GemmProblem& p, cudaStream_t stream) {
   if (e != cudaSuccess) return e;
   P2 kp{};
   kp.M = p.M; kp.N = p.N; kp.K = p.K; kp.k_blocks = (p.K + 63) / 64;
+  kp.m_pairs = (p.M + 2 * kBM - 1) / (2 * kBM); kp.n_tiles = (p.N + kBN - 1) / kBN;
   kp.d = p.epi.d; kp.d_dtype = static_cast<int>(p.epi.d_dtype); kp.ldd = p.epi.ldd;
   kp.alpha = p.epi.alpha; kp.bias = p.epi.bias; kp.act = static_cast<int>(p.epi.act);
   static bool configured = false;
@@ -267,8 +311,11 @@ cudaError_t gemm2_sm100(const GemmProblem& p, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  // pairs along x (M fastest so concurrently running clusters share B tiles in L2)
-  dim3 grid(2 * ((p.M + 2 * kBM - 1) / (2 * kBM)), (p.N + kBN - 1) / kBN, 1);
+  // persistent: one CTA pair per TPC (74 on a B200), M fastest so that pairs running at the same
+  // time share B tiles in L2
+  const int tiles = kp.m_pairs * kp.n_tiles;
+  const int pairs = tiles < 74 ? tiles : 74;
+  dim3 grid(2 * pairs, 1, 1);
   gemm2_kernel<<<grid, kThreads, kSmemTotal, stream>>>(ta, tb, kp);
   note_launch();
   return cudaGetLastError();

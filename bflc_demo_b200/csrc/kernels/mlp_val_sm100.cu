@@ -33,7 +33,8 @@ using epi::st_sw128;
 __device__ __forceinline__ uint32_t pack2(float a, float b) { return epi::pack_bf16x2(a, b); }
 
 constexpr int kBM = 128;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;        // two per TMEM lane quarter: each owns 4 of the 8 hidden-column chunks
+constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kCStages = 3;
 constexpr int kCA = kBM * 128, kCB = 256 * 128, kCStage = kCA + kCB;   // x tile 16 KB + W1 tile 32 KB
 constexpr int kOffH = 0;                        // h tile (fwd2's A) aliases stage memory once fwd1 retired
@@ -87,7 +88,7 @@ mlp_val_kernel(const __grid_constant__ CUtensorMap tmX, const ValArgs v) {
       ptx::mbar_init(&empty[s], 1);
     }
     ptx::mbar_init(w2k, 1); ptx::mbar_init(acc_h, 1); ptx::mbar_init(acc_l, 1);
-    ptx::mbar_init(h_ready, 128);
+    ptx::mbar_init(h_ready, kEpiWarps * 32);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, kTmemCols);
@@ -218,22 +219,23 @@ mlp_val_kernel(const __grid_constant__ CUtensorMap tmX, const ValArgs v) {
     }
     __syncwarp();
   } else {
-    const int q = warp & 3, rl = q * 32 + lane, row = m0 + rl;
+    // warps 2..9: q = TMEM lane quarter, half = which four 32-column chunks of h this warp converts
+    const int q = warp & 3, half = (warp - 2) >> 2, rl = q * 32 + lane, row = m0 + rl;
     const bool row_ok = row < v.n_val;
     const int C = v.n_classes;
     {
       const int et = threadIdx.x - 64;
       const float* b1 = FP8 ? reinterpret_cast<const float*>(blob + v.ql.b1) : v.dyn1->bias[z];
       const float* b2 = FP8 ? reinterpret_cast<const float*>(blob + v.ql.b2) : v.dyn2->bias[z];
-      for (int i = et; i < kChainH; i += 128) sb[i] = b1 != nullptr ? b1[i] : 0.f;
+      sb[et] = b1 != nullptr ? b1[et] : 0.f;            // kEpiWarps * 32 == kChainH
       if (et < 64) sb[kChainH + et] = (b2 != nullptr && et < C) ? b2[et] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     ptx::mbar_wait(acc_h, 0);
     ptx::tc_fence_after_sync();
 #pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
+    for (int c = half * 4; c < half * 4 + 4; ++c) {
       uint32_t r[32];
       ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
       ptx::tmem_ld_wait();
@@ -264,6 +266,7 @@ mlp_val_kernel(const __grid_constant__ CUtensorMap tmX, const ValArgs v) {
     ptx::fence_proxy_async_smem();
     ptx::tc_fence_before_sync();
     ptx::mbar_arrive(h_ready);
+    if (half == 0) {     // the 64 logits of a row: one thread
     ptx::mbar_wait(acc_l, 0);
     ptx::tc_fence_after_sync();
     const int32_t label = row_ok ? v.labels[row] : -1;
@@ -283,6 +286,7 @@ mlp_val_kernel(const __grid_constant__ CUtensorMap tmX, const ValArgs v) {
     }
     const unsigned cnt = __popc(__ballot_sync(0xffffffffu, row_ok && amax == label));
     if (lane == 0 && cnt) atomicAdd(v.correct + z, cnt);
+    }
     ptx::tc_fence_before_sync();
   }
   __syncthreads();

@@ -359,9 +359,36 @@ def embedding(ids, table, pos, gtable, gpos, seq):
     return EmbeddingFn.apply(anchor, ids, table, pos, gtable, gpos, seq)
 
 
+class FusedAttentionFn(Function):
+    """Multi-head self-attention core on q, k, v of shape [B*S, H*64], seq_len 128: ONE kernel per
+    direction, one CTA per (batch, head) -- QK^T, softmax, PV (and in backward the five GEMMs of
+    dQ / dK / dV) on tcgen05 with the S x S matrix held in TMEM / smem only, heads addressed as TMA
+    boxes of the projection outputs so no transpose exists (csrc/kernels/attn_sm100.cu)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, B, S, H):
+        D = q.shape[1] // H
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        out = torch.empty_like(q)
+        lse = torch.empty(B * H * S, device=q.device, dtype=torch.float32)
+        C().attention_fwd(q, k, v, out, lse, B, S, H, 1.0 / (D ** 0.5))
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.dims = (B, S, H, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse = ctx.saved_tensors
+        B, S, H, D = ctx.dims
+        dout = dout.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+        C().attention_bwd(q, k, v, out, dout, lse, dq, dk, dv, B, S, H, 1.0 / (D ** 0.5))
+        return dq, dk, dv, None, None, None
+
+
 class AttentionFn(Function):
-    """Multi-head self-attention core on q, k, v of shape [B*S, H*D] (seq 128: the score tile
-    of one head is a single 128-row UMMA tile).  Batched tcgen05 GEMMs + row-softmax kernel."""
+    """Unfused fallback for shapes the fused kernel does not cover (seq != 128 or head dim != 64):
+    batched tcgen05 GEMMs + row-softmax kernel + head transposes."""
 
     @staticmethod
     def forward(ctx, q, k, v, B, S, H):
@@ -406,5 +433,7 @@ class AttentionFn(Function):
         return unheads(dq), unheads(dk), unheads(dv), None, None, None
 
 
-def attention(q, k, v, B, S, H):
+def attention(q, k, v, B, S, H, fused: bool = True):
+    if fused and S == 128 and q.shape[1] // H == 64 and q.shape[1] % 8 == 0:
+        return FusedAttentionFn.apply(q, k, v, B, S, H)
     return AttentionFn.apply(q, k, v, B, S, H)

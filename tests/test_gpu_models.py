@@ -148,11 +148,14 @@ def test_layernorm_softmax_embedding_pool(F):
     assert rel(xa.grad, torch.full_like(xa, 1 / 16).float()) < 1e-2
 
 
-def test_attention_fwd_bwd(F):
+@pytest.mark.parametrize("fused,B,H", [(True, 2, 4), (True, 3, 12), (False, 2, 4)])
+def test_attention_fwd_bwd(F, fused, B, H):
+    """Fused one-kernel attention (attn_sm100.cu: QK^T -> softmax -> PV in TMEM / smem; backward
+    with five tcgen05 GEMMs) and the unfused fallback, against fp32 PyTorch SDPA + autograd."""
     torch.manual_seed(4)
-    B, S, H, D = 2, 128, 4, 64
-    q, k, v = (_leaf(B * S, H * D, scale=0.3) for _ in range(3))
-    o = F.attention(q, k, v, B, S, H)
+    S, D = 128, 64
+    q, k, v = (_leaf(B * S, H * D, scale=0.7) for _ in range(3))
+    o = F.attention(q, k, v, B, S, H, fused=fused)
     do = torch.randn_like(o)
     o.backward(do)
 
