@@ -136,6 +136,42 @@ void bind_nn(py::module_& m) {
     check(bflc::gemm_mx8_sm100(p, st()), "gemm_mx8_sm100");
   });
   // fused attention (seq 128, head dim 64): q, k, v, o, gradients are [B*S, H*64] bf16
+  // Implicit-GEMM convolution (ConvView in bflc_kernels.h).  `x` is the NHWC activation the
+  // shifted boxes are read from, `other` the dense operand (weights, or dy for mode 2).
+  m.def("conv_gemm", [](int mode, int flip, at::Tensor x, at::Tensor other, at::Tensor d, int N, int H,
+                        int W, int Cc, int OH, int OW, int KH, int KW, int stride, int pad, int n_out,
+                        const OptT& bias, int act, const OptT& aux_out, const OptT& aux_in, int act_bwd,
+                        const OptT& colsum, int split_k, bool accumulate) {
+    bflc::GemmProblem p;
+    auto& cv = p.conv;
+    cv.mode = mode; cv.flip = flip; cv.x = x.data_ptr();
+    cv.N = N; cv.H = H; cv.W = W; cv.C = Cc; cv.OH = OH; cv.OW = OW;
+    cv.KH = KH; cv.KW = KW; cv.stride = stride; cv.pad = pad;
+    const int taps = KH * KW;
+    const int64_t pixels = (int64_t)N * OH * OW;
+    if (mode == 1) {
+      p.M = (int)pixels; p.N = n_out; p.K = taps * Cc;
+      p.a = {x.data_ptr(), Cc, 0, false};
+      p.b = {other.data_ptr(), other.stride(0), 0, flip != 0};
+    } else {
+      p.M = n_out; p.N = taps * Cc; p.K = (int)pixels;
+      p.a = {other.data_ptr(), other.stride(0), 0, true};   // dy [pixels][Cout]
+      p.b = {x.data_ptr(), Cc, 0, true};
+    }
+    auto& e = p.epi;
+    e.d = d.data_ptr();
+    e.d_dtype = d.scalar_type() == at::kFloat ? bflc::DType::F32 : bflc::DType::BF16;
+    e.ldd = d.stride(0);
+    e.bias = optp<const float>(bias);
+    e.act = static_cast<bflc::Act>(act);
+    e.aux_out = aux_out.has_value() ? aux_out->data_ptr() : nullptr;
+    e.aux_in = aux_in.has_value() ? aux_in->data_ptr() : nullptr;
+    e.act_bwd = act_bwd;
+    e.colsum = optp<float>(colsum);
+    e.split_k = split_k;
+    e.accumulate = accumulate ? 1 : 0;
+    check(bflc::gemm_sm100(p, st()), "conv_gemm (implicit-GEMM convolution)");
+  });
   m.def("attention_fwd", [](at::Tensor q, at::Tensor k, at::Tensor v, at::Tensor o, at::Tensor lse, int B,
                             int S, int H, double scale) {
     const int D = (int)q.size(1) / H;

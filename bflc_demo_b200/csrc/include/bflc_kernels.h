@@ -54,6 +54,24 @@ struct GemmEpilogue {
   unsigned int* correct = nullptr;  // [batch] += #(argmax == label)
 };
 
+// Implicit-GEMM convolution: one operand is an NHWC bf16 activation read through a 4-D tensor
+// map, so the im2col matrix is never written.  Each K block (mode 1) or N tile (mode 2) is one
+// filter tap (r, s) x 64 channels, fetched as a TMA box shifted by the tap offset; boxes that
+// hang over the image border are zero-filled by the TMA unit (= the padding).
+//   mode 1, flip 0  forward        : A = x  [N,H,W,C]    rows = output pixels, B = w [Cout][KH*KW*C]
+//   mode 1, flip 1  input gradient : A = dy [N,OH,OW,C]  rows = input pixels (stride 1 only),
+//                                    B = w read MN-major, tap-mirrored
+//   mode 2          weight gradient: B = x shifted per tap, reduction over output pixels,
+//                                    A = dy [pixels][Cout] MN-major, D = dW [Cout][KH*KW*C]
+struct ConvView {
+  int mode = 0;
+  int flip = 0;
+  const void* x = nullptr;  // the NHWC activation
+  int N = 0, H = 0, W = 0, C = 0;   // its dims
+  int OH = 0, OW = 0;               // pixel grid the GEMM rows / reduction enumerate
+  int KH = 1, KW = 1, stride = 1, pad = 0;
+};
+
 struct GemmDynamic;  // device-resident per-launch arguments, defined below
 
 struct GemmProblem {
@@ -69,6 +87,7 @@ struct GemmProblem {
   // debug overrides for descriptor bring-up (0 = use built-in)
   uint32_t dbg_lbo_a = 0, dbg_sbo_a = 0, dbg_lbo_b = 0, dbg_sbo_b = 0;
   int force_bn = 0;  // 0 = heuristic; 64/128/256 pins the N-tile (must match pre-built b maps)
+  ConvView conv;     // mode != 0: the A (mode 1) or B (mode 2) operand is an implicit im2col view
 };
 
 // cuTensorMapEncodeTiled is a driver call and needs a context current on the calling thread;

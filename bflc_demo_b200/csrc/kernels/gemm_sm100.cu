@@ -68,6 +68,12 @@ struct KParams {
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b;
   uint32_t kstep_a, kstep_b;  // descriptor start-address advance per UMMA_K step (bytes)
   int vec_ok;                 // d / aux rows are 16-byte aligned -> vectorised global access
+  // implicit-GEMM convolution (ConvView): which operand is the shifted NHWC view and its taps
+  int cv_mode, cv_flip;
+  int cv_cb;                  // 64-channel blocks per filter tap
+  int cv_kw, cv_pad, cv_stride;
+  int cv_oh, cv_ow;           // pixel grid enumerated by the rows (mode 1) / the reduction (mode 2)
+  int cv_c;                   // channels of the viewed activation
 };
 
 template <int BN>
@@ -179,7 +185,7 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const KParams p) {
+            const __grid_constant__ CUtensorMap tmC, const KParams p) {
   using L = SmemLayout<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -213,6 +219,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmA);
     if (p.b_maps_dev == nullptr) ptx::tma_prefetch_desc(&tmB);
+    if (p.cv_mode != 0) ptx::tma_prefetch_desc(&tmC);
     for (int s = 0; s < L::kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -259,6 +266,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint8_t* sa = smem + s * L::kStageBytes;
       uint8_t* sb = sa + kABytes;
       const int k0 = (kb_begin + i) * block_k;
+      if (p.cv_mode != 0) {
+        // ---- implicit-GEMM convolution: one operand is a tap-shifted NHWC box (tmC)
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&full_bar[s], L::kStageBytes);
+          const int kb = kb_begin + i;
+          const int per_img = p.cv_oh * p.cv_ow;
+          if (p.cv_mode == 1) {
+            // rows m0.. = 128 consecutive output pixels (whole image rows); K block = (tap, 64 ch)
+            const int tap = kb / p.cv_cb, cblk = kb - tap * p.cv_cb;
+            const int r = tap / p.cv_kw, t = tap - r * p.cv_kw;
+            const int img0 = m0 / per_img, oh0 = (m0 - img0 * per_img) / p.cv_ow;
+            const int dh = p.cv_flip ? p.cv_pad - r : r - p.cv_pad;
+            const int dw = p.cv_flip ? p.cv_pad - t : t - p.cv_pad;
+            ptx::tma_load_4d(sa, &tmC, &full_bar[s], cblk * 64, dw, oh0 * p.cv_stride + dh, img0);
+            if (!p.cv_flip) {
+              ptx::tma_load_3d(sb, mapB, &full_bar[s], k0, n0, 0);
+            } else {  // w[Cout][taps*Cin] read MN-major: N offset selects the tap, K = out channels
+              for (int b = 0; b < BN / 64; ++b)
+                ptx::tma_load_3d(sb + b * (64 * 128), mapB, &full_bar[s],
+                                 tap * p.N + n0 + b * 64, cblk * 64, 0);
+            }
+          } else {
+            // weight gradient: K block = 64 output pixels; N tile = (tap, BN channels)
+            for (int b = 0; b < 2; ++b)  // A = dy^T, MN-major: two 64-wide boxes of out channels
+              ptx::tma_load_3d(sa + b * (64 * 128), &tmA, &full_bar[s], m0 + b * 64, k0, 0);
+            const int tap = n0 / p.cv_c, c0 = n0 - tap * p.cv_c;
+            const int r = tap / p.cv_kw, t = tap - r * p.cv_kw;
+            const int pix0 = kb * 64;
+            const int img0 = pix0 / per_img, oh0 = (pix0 - img0 * per_img) / p.cv_ow;
+            for (int b = 0; b < BN / 64; ++b)
+              ptx::tma_load_4d(sb + b * (64 * 128), &tmC, &full_bar[s], c0 + b * 64, t - p.cv_pad,
+                               oh0 * p.cv_stride + r - p.cv_pad, img0);
+          }
+        }
+        __syncwarp();
+        continue;
+      }
       if (ptx::elect_one()) {
         ptx::mbar_expect_tx(&full_bar[s], L::kStageBytes);
         if (!p.a_mn) {
@@ -572,9 +616,52 @@ cudaError_t make_map(CUtensorMap* out, const GemmOperand& op, DType dt, int rows
   return cudaSuccess;
 }
 
+// Pixel tile of `pix` output pixels as whole image rows: (pw, ph, pn) with pw*ph*pn == pix.
+bool conv_pixel_tile(int pix, int OH, int OW, int* pw, int* ph, int* pn) {
+  if (OW <= 0 || OH <= 0 || OW > pix || pix % OW != 0) return false;
+  const int rows = pix / OW;
+  if (rows <= OH) {
+    if (OH % rows != 0) return false;
+    *pw = OW; *ph = rows; *pn = 1;
+  } else {
+    if (rows % OH != 0) return false;
+    *pw = OW; *ph = OH; *pn = rows / OH;
+  }
+  return true;
+}
+
+// 4-D map over an NHWC bf16 activation whose box is `pix` pixels x 64 channels, traversed with
+// the convolution stride (elementStrides) so consecutive box rows are consecutive output pixels.
+cudaError_t make_conv_map(CUtensorMap* out, const ConvView& cv, int pix) {
+  EncodeFn enc = get_encode();
+  if (!enc) return cudaErrorNotSupported;
+  int pw, ph, pn;
+  if (!conv_pixel_tile(pix, cv.OH, cv.OW, &pw, &ph, &pn)) return cudaErrorInvalidValue;
+  if (cv.C % 64 != 0 || cv.stride < 1 || pw * cv.stride > 256 || ph * cv.stride > 256)
+    return cudaErrorInvalidValue;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(cv.C), static_cast<cuuint64_t>(cv.W),
+                        static_cast<cuuint64_t>(cv.H), static_cast<cuuint64_t>(cv.N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(cv.C) * 2,
+                           static_cast<cuuint64_t>(cv.W) * cv.C * 2,
+                           static_cast<cuuint64_t>(cv.H) * cv.W * cv.C * 2};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(pw * cv.stride),
+                       static_cast<cuuint32_t>(ph * cv.stride), static_cast<cuuint32_t>(pn)};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(cv.stride), static_cast<cuuint32_t>(cv.stride), 1};
+  if (reinterpret_cast<uintptr_t>(cv.x) & 15) return cudaErrorMisalignedAddress;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(cv.x), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::fprintf(stderr, "[bflc] conv tensor map failed (CUresult %d): NHWC=%d,%d,%d,%d box=%u,%u,%u,%u stride=%d\n",
+                 static_cast<int>(r), cv.N, cv.H, cv.W, cv.C, box[0], box[1], box[2], box[3], cv.stride);
+    return cudaErrorInvalidValue;
+  }
+  return cudaSuccess;
+}
+
 template <int BN, int EPI>
-cudaError_t launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& kp, dim3 grid,
-                   cudaStream_t stream) {
+cudaError_t launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                   const KParams& kp, dim3 grid, cudaStream_t stream) {
   using L = SmemLayout<BN>;
   static bool configured = false;
   if (!configured) {
@@ -584,7 +671,7 @@ cudaError_t launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& 
     configured = true;
   }
   note_launch();
-  return launch_pdl(gemm_kernel<BN, EPI>, grid, dim3(kThreads), L::kTotal, stream, ta, tb, kp);
+  return launch_pdl(gemm_kernel<BN, EPI>, grid, dim3(kThreads), L::kTotal, stream, ta, tb, tc, kp);
 }
 
 }  // namespace
@@ -643,14 +730,46 @@ cudaError_t gemm_sm100(const GemmProblem& p, cudaStream_t stream) {
   if (fp8 && p.b.mn_major && BN < 128) BN = 128;
   const int block_k = fp8 ? 128 : 64;
 
-  CUtensorMap ta, tb;
-  cudaError_t e = make_map(&ta, p.a, p.ab_dtype, p.M, p.K, p.batch, kBM);
-  if (e != cudaSuccess) return e;
-  if (p.b_maps_dev == nullptr) {
-    e = make_map(&tb, p.b, p.ab_dtype, p.N, p.K, p.batch, BN);
-    if (e != cudaSuccess) return e;
+  CUtensorMap ta, tb, tc;
+  std::memset(&tc, 0, sizeof(tc));
+  cudaError_t e = cudaSuccess;
+  const ConvView& cv = p.conv;
+  const int taps = cv.KH * cv.KW;
+  if (cv.mode != 0) {
+    if (fp8 || p.batch != 1 || p.b_maps_dev || p.dyn || p.epi.kind != EpiKind::GENERIC)
+      return cudaErrorInvalidValue;
+    if (cv.mode == 1) {
+      // rows = pixels of the (OH, OW) grid; K = taps x C
+      if (p.a.mn_major || p.K != taps * cv.C || p.M != cv.N * cv.OH * cv.OW) return cudaErrorInvalidValue;
+      if (cv.flip && (cv.stride != 1 || !p.b.mn_major || p.N % 64 != 0)) return cudaErrorInvalidValue;
+      if (!cv.flip && p.b.mn_major) return cudaErrorInvalidValue;
+      if (cv.flip && BN > p.N) BN = (p.N % 128 == 0) ? 128 : 64;
+      if (cv.flip && p.N % BN != 0) BN = 64;
+      e = make_conv_map(&tc, cv, kBM);
+      if (e != cudaSuccess) return e;
+      std::memset(&ta, 0, sizeof(ta));
+      e = cv.flip ? make_map(&tb, p.b, p.ab_dtype, taps * p.N, cv.C, 1, BN)
+                  : make_map(&tb, p.b, p.ab_dtype, p.N, p.K, 1, BN);
+      if (e != cudaSuccess) return e;
+    } else {
+      // D = dW [Cout][taps x C]; reduction over the pixels
+      if (!p.a.mn_major || p.N != taps * cv.C || p.K != cv.N * cv.OH * cv.OW) return cudaErrorInvalidValue;
+      BN = (cv.C % 256 == 0 && BN == 256) ? 256 : ((cv.C % 128 == 0 && BN >= 128) ? 128 : 64);
+      e = make_conv_map(&tc, cv, 64);
+      if (e != cudaSuccess) return e;
+      e = make_map(&ta, p.a, p.ab_dtype, p.M, p.K, 1, kBM);
+      if (e != cudaSuccess) return e;
+      std::memset(&tb, 0, sizeof(tb));
+    }
   } else {
-    std::memset(&tb, 0, sizeof(tb));
+    e = make_map(&ta, p.a, p.ab_dtype, p.M, p.K, p.batch, kBM);
+    if (e != cudaSuccess) return e;
+    if (p.b_maps_dev == nullptr) {
+      e = make_map(&tb, p.b, p.ab_dtype, p.N, p.K, p.batch, BN);
+      if (e != cudaSuccess) return e;
+    } else {
+      std::memset(&tb, 0, sizeof(tb));
+    }
   }
 
   KParams kp{};
@@ -707,9 +826,14 @@ cudaError_t gemm_sm100(const GemmProblem& p, cudaStream_t stream) {
   kp.sbo_b = p.dbg_sbo_b ? p.dbg_sbo_b : 1024u;
   kp.kstep_a = p.a.mn_major ? mn_kstep : 32u;
   kp.kstep_b = p.b.mn_major ? mn_kstep : 32u;
+  kp.cv_mode = cv.mode; kp.cv_flip = cv.flip;
+  kp.cv_cb = cv.C / 64; kp.cv_kw = cv.KW; kp.cv_pad = cv.pad; kp.cv_stride = cv.stride;
+  kp.cv_oh = cv.OH; kp.cv_ow = cv.OW; kp.cv_c = cv.C;
+  if (cv.mode == 2) kp.b_mn = 1;  // shifted activation boxes are [pixels][channels]: MN-major B
+  if (cv.mode == 2) { kp.lbo_b = 64u * 128u; kp.kstep_b = mn_kstep; }
 
   dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, p.batch * kp.split_k);
-#define BFLC_LAUNCH(BN_, EPI_) return launch<BN_, EPI_>(ta, tb, kp, grid, stream)
+#define BFLC_LAUNCH(BN_, EPI_) return launch<BN_, EPI_>(ta, tb, tc, kp, grid, stream)
   const int epi = static_cast<int>(p.epi.kind);
   if (epi == 0) {
     if (BN == 64) BFLC_LAUNCH(64, 0);

@@ -12,6 +12,7 @@ softmax-xent, K3 backward; the rest exists for the LeNet/ResNet
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -150,6 +151,77 @@ def linear_xent(h, w, b, gw, gb, labels, correct=None):
     return LinearXentFn.apply(h, w, b, gw, gb, labels, correct)
 
 
+_IMPLICIT = os.environ.get("BFLC_CONV_IMPLICIT", "1") != "0"
+
+
+def _pix_tile(pix: int, OH: int, OW: int) -> bool:
+    """Can `pix` consecutive output pixels be fetched as one TMA box of whole image rows?"""
+    if OW > pix or pix % OW:
+        return False
+    rows = pix // OW
+    return OH % rows == 0 if rows <= OH else rows % OH == 0
+
+
+def conv_is_implicit(H, W, Cin, kh, kw, stride, pad, Kp) -> bool:
+    """Implicit-GEMM eligibility (csrc/kernels/gemm_sm100.cu, ConvView): 64-channel K blocks and
+    pixel tiles made of whole image rows; everything else takes the im2col path."""
+    OH, OW = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    return (_IMPLICIT and _PRECISION == "bf16" and Cin % 64 == 0 and Kp == kh * kw * Cin
+            and _pix_tile(128, OH, OW) and _pix_tile(64, OH, OW) and OW * stride <= 256)
+
+
+class ConvImplicitFn(Function):
+    """NHWC convolution as an implicit GEMM: the tcgen05 GEMM's TMA producer fetches each
+    (filter tap, 64 channels) K block as a tap-shifted 4-D box of the activation itself, the
+    border zero-filled by the TMA unit -- no im2col buffer in forward, input-gradient
+    (stride 1) or weight-gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gw, gb, kh, kw, stride, pad, act, need_dx=True):
+        x = x.contiguous()
+        N, H, W, Cin = x.shape
+        Cout = w.shape[0]
+        OH, OW = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+        y = torch.empty(N * OH * OW, Cout, device=x.device, dtype=BF)
+        pre = torch.empty_like(y) if act == G.ACT_GELU else None
+        C().conv_gemm(1, 0, x, w, y, N, H, W, Cin, OH, OW, kh, kw, stride, pad, Cout, b, act, pre,
+                      None, 0, None, 1, False)
+        ctx.save_for_backward(x, w, y if act == G.ACT_RELU else pre)
+        ctx.gw, ctx.gb, ctx.act, ctx.need_dx = gw, gb, act, need_dx
+        ctx.geom = (N, Cin, H, W, kh, kw, stride, pad, OH, OW)
+        return y.view(N, OH, OW, Cout)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, aux = ctx.saved_tensors
+        N, Cin, H, W, kh, kw, stride, pad, OH, OW = ctx.geom
+        Cout = w.shape[0]
+        dy = dy.contiguous().view(-1, Cout)
+        rows = dy.shape[0]
+        if ctx.act != G.ACT_NONE:
+            dz = torch.empty_like(dy)
+            C().act_bwd_colsum(dy, aux, dz, ctx.gb, rows, Cout, ctx.act)
+        else:
+            dz = dy
+            if ctx.gb is not None:
+                C().act_bwd_colsum(dy, None, None, ctx.gb, rows, Cout, 0)
+        if ctx.gw is not None:
+            tiles = ((Cout + 127) // 128) * ((kh * kw * Cin + 127) // 128)
+            sk = max(1, min(148 // tiles, (rows // 64) // 2, 32))
+            C().conv_gemm(2, 0, x, dz, ctx.gw, N, H, W, Cin, OH, OW, kh, kw, stride, pad, Cout, None, 0,
+                          None, None, 0, None, sk, sk == 1)
+        dx = None
+        if ctx.needs_input_grad[0] and ctx.need_dx:
+            dx = torch.empty(N, H, W, Cin, device=dy.device, dtype=BF)
+            if stride == 1 and Cout % 64 == 0 and _pix_tile(128, H, W):
+                C().conv_gemm(1, 1, dz, w, dx.view(-1, Cin), N, OH, OW, Cout, H, W, kh, kw, 1, pad, Cin,
+                              None, 0, None, None, 0, None, 1, False)
+            else:
+                dcol = G.gemm(dz, w, b_mn=True)
+                C().col2im(dcol, dx, N, Cin, H, W, kh, kw, stride, pad, OH, OW)
+        return (dx,) + (None,) * 10
+
+
 class Conv2dFn(Function):
     """NHWC convolution = im2col + tcgen05 GEMM (+bias, +activation epilogue)."""
 
@@ -196,6 +268,8 @@ class Conv2dFn(Function):
 
 
 def conv2d(x, w, b, gw, gb, kh, kw, stride=1, pad=0, act=G.ACT_NONE, need_dx=True):
+    if conv_is_implicit(x.shape[1], x.shape[2], x.shape[3], kh, kw, stride, pad, w.shape[1]):
+        return ConvImplicitFn.apply(x, w, b, gw, gb, kh, kw, stride, pad, act, need_dx)
     return Conv2dFn.apply(x, w, b, gw, gb, kh, kw, stride, pad, act, need_dx)
 
 

@@ -40,7 +40,7 @@ def main(argv=None):
     ap.add_argument("--resume", default="")
     ap.add_argument("--no-stage", action="store_true", help="validate straight out of peers' HBM")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"],
-                    help="fp8: block-scaled (MXFP8) forward GEMMs; routes the MLP through the generic engine")
+                    help="fp8: block-scaled (MXFP8) forward GEMMs (the MLP keeps the fused persistent trainer)")
     ap.add_argument("--generic", action="store_true", help="run the MLP through GenericFedEngine")
     a = ap.parse_args(argv)
 
@@ -67,7 +67,7 @@ def main(argv=None):
         shard = tokens_like(world, S, seed=7)[rank]
         test = tokens_like(1, 128, seed=8)[0]
 
-    if a.model == "mlp" and a.dtype == "bf16" and not a.generic:
+    if a.model == "mlp" and not a.generic:
         from .engine.fused import FusedEngine
         eng = FusedEngine(cfg, shard, rank=rank, world=world, device=lr_)
         eng.capture()

@@ -73,6 +73,45 @@ def test_conv2d_fwd_bwd(F, cin, cout, k, stride, pad, hw):
     assert rel(gb, br.grad) < 3e-2
 
 
+@pytest.mark.parametrize("n,cin,cout,k,stride,pad,hw", [
+    (2, 64, 64, 3, 1, 1, 32),     # ResNet stage 1: one pixel tile = 4 image rows
+    (3, 128, 128, 3, 1, 1, 16),   # 8-row tiles, 2 channel blocks per tap
+    (4, 64, 128, 3, 2, 1, 32),    # strided: TMA elementStrides in forward / weight gradient
+    (4, 64, 128, 1, 2, 0, 16),    # 1x1 strided downsample
+    (5, 256, 64, 3, 1, 1, 4),     # tiny images: a pixel tile spans 8 images, 3 of them out of range
+    (6, 64, 192, 3, 1, 1, 8),     # Cout not a multiple of the N tile
+])
+def test_conv2d_implicit_gemm(F, n, cin, cout, k, stride, pad, hw):
+    """The implicit-GEMM path (tap-shifted 4-D TMA boxes, no im2col buffer) against fp32 cuDNN."""
+    from bflc_demo_b200.ops import gemm as G
+    torch.manual_seed(5)
+    assert F.conv_is_implicit(hw, hw, cin, k, k, stride, pad, k * k * cin)
+    x = _leaf(n, hw, hw, cin)
+    kc = k * k * cin
+    w = (torch.randn(cout, kc, device="cuda") * (1.0 / kc ** 0.5)).to(BF)
+    b = torch.randn(cout, device="cuda") * 0.1
+    gw, gb = torch.zeros(cout, kc, device="cuda"), torch.zeros(cout, device="cuda")
+    y = F.conv2d(x, w, b, gw, gb, k, k, stride, pad, G.ACT_RELU)
+    assert type(y.grad_fn).__name__.startswith("ConvImplicitFn")
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.float().view(cout, k, k, cin).permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    yr = torch.relu(TF.conv2d(xr, wr, br, stride=stride, padding=pad))
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert rel(y, yr.permute(0, 2, 3, 1)) < 1e-2
+    assert rel(x.grad, xr.grad.permute(0, 2, 3, 1)) < 3e-2
+    assert rel(gw.view(cout, k, k, cin), wr.grad.permute(0, 2, 3, 1)) < 3e-2
+    assert rel(gb, br.grad) < 3e-2
+    # second backward accumulates into gw (split-K atomics or += epilogue)
+    g1 = gw.clone()
+    x.grad = None
+    y2 = F.conv2d(x, w, b, gw, gb, k, k, stride, pad, G.ACT_RELU)
+    y2.backward(dy)
+    assert rel(gw, 2 * g1) < 1e-2
+
+
 def test_batchnorm_fwd_bwd(F):
     torch.manual_seed(2)
     x = _leaf(6, 8, 8, 32, scale=1.0)
