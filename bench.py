@@ -284,6 +284,16 @@ def main():
         # committee's validation GEMMs (upload + pull + score exchange + FedAvg + publish + skew)
         ph["exposed_comm_us"] = round(max(ph["round_us"] - ph["train_us"] - ph["validate_us"], 0.0), 2)
         extra["phases_us_max_over_ranks"] = ph
+        # the same stamps for end-to-end rounds (inputs streamed from pinned host memory): the
+        # difference to the e2e time per round is what happens before the first / after the last kernel
+        samples = []
+        for i in range(5):
+            sync_all()
+            eng.run_round_e2e()
+            samples.append(eng.read_stamps())
+        drain()
+        med = [sorted(s[k] for s in samples)[len(samples) // 2] for k in keys]
+        extra["phases_us_e2e_round"] = {k: round(v, 2) for k, v in zip(keys, reduce_max(med))}
         if n > 1:
             digs = [None] * n
             dist.all_gather_object(digs, st["model_digest"])

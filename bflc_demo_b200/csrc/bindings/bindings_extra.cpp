@@ -117,6 +117,7 @@ void bind_extra(py::module_& m) {
     d["GemmDynamic"] = sizeof(bflc::GemmDynamic);
     d["FLAG_COUNT"] = (int)bflc::FLAG_COUNT;
     d["kMaxRanks"] = bflc::kMaxRanks;
+    d["kMirrorSeqWord"] = bflc::kMirrorSeqWord;
     d["plan_dyn_off"] = offsetof(bflc::RoundPlan, dyn);
     d["plan_correct_off"] = offsetof(bflc::RoundPlan, correct);
     d["plan_loss_sum_off"] = offsetof(bflc::RoundPlan, loss_sum);
@@ -181,11 +182,14 @@ void bind_extra(py::module_& m) {
   }, py::arg("fed"), py::arg("n_samples"), py::arg("n_loss_terms"), py::arg("byz_mode"), py::arg("byz_scale"),
      py::arg("straggle_us") = 0);
   m.def("fed_consensus_aggregate", [](const py::dict& fd, int n_val, bool weight_by_score,
-                                      bool two_shot, bool use_mc) {
+                                      bool two_shot, bool use_mc, int64_t host_mirror,
+                                      int64_t bump_seq) {
     check(bflc::fed_consensus_aggregate(make_fed(fd), n_val, weight_by_score ? 1 : 0,
-                                        two_shot ? 1 : 0, use_mc ? 1 : 0, cur_stream()),
+                                        two_shot ? 1 : 0, use_mc ? 1 : 0, cur_stream(),
+                                        P<uint32_t>(host_mirror), P<uint32_t>(bump_seq)),
           "fed_consensus_aggregate");
-  });
+  }, py::arg("fed"), py::arg("n_val"), py::arg("weight_by_score"), py::arg("two_shot"),
+     py::arg("use_mc"), py::arg("host_mirror") = 0, py::arg("bump_seq") = 0);
   m.def("fed_pull_candidates", [](const py::dict& fd, at::Tensor stage_shadow, const OptT& stage_master) {
     check(bflc::fed_pull_candidates(make_fed(fd), stage_shadow.data_ptr(),
                                     stage_master.has_value() ? stage_master->data_ptr<float>() : nullptr,

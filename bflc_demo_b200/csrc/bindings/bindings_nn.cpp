@@ -29,6 +29,11 @@ void bind_nn(py::module_& m) {
     check(bflc::col2im_bf16(col.data_ptr(), dx.data_ptr(), N, C, H, W, KH, KW, stride, pad, OH, OW,
                             col.stride(0), st()), "col2im");
   });
+  m.def("upsample_zero", [](at::Tensor dy, at::Tensor up, int N, int H, int W, int OH, int OW, int Cc,
+                            int stride) {
+    check(bflc::upsample_zero_bf16(dy.data_ptr(), up.data_ptr(), N, H, W, OH, OW, Cc, stride, st()),
+          "upsample_zero");
+  });
   m.def("maxpool_fwd", [](at::Tensor x, at::Tensor y, at::Tensor idx, int N, int C, int H, int W,
                           int k, int stride, int pad, int OH, int OW) {
     check(bflc::maxpool2d_fwd(x.data_ptr(), y.data_ptr(), idx.data_ptr<int32_t>(), N, C, H, W, k,

@@ -260,6 +260,9 @@ cudaError_t adam_step(const OptimArgs& a, cudaStream_t s);
 // ------------------------------------------------------- NN support kernels
 cudaError_t im2col_bf16(const void* x, void* col, int N, int C, int H, int W, int KH, int KW,
                         int stride, int pad, int OH, int OW, int64_t ld_col, cudaStream_t s);
+// up[n, s*oh, s*ow, :] = dy[n, oh, ow, :], zeros elsewhere (strided-convolution input gradient)
+cudaError_t upsample_zero_bf16(const void* dy, void* up, int N, int H, int W, int OH, int OW, int C,
+                               int stride, cudaStream_t s);
 cudaError_t col2im_bf16(const void* col, void* dx, int N, int C, int H, int W, int KH, int KW,
                         int stride, int pad, int OH, int OW, int64_t ld_col, cudaStream_t s);
 cudaError_t maxpool2d_fwd(const void* x, void* y, int32_t* idx, int N, int C, int H, int W, int k,
@@ -477,8 +480,15 @@ cudaError_t fed_upload(const FedArgs& f, int n_samples, int n_loss_terms, int by
 // the consensus math, reduce the selected uploads over P2P loads in a fixed order, write
 // the new global model (+bf16, + next round's training buffers), append the BlockRecord,
 // re-elect, epoch++ and release FLAG_DONE.
+// host_mirror (optional, pinned host memory, >= (kMirrorSeqWord + 1) words): the kernel's last
+// block copies the committed RoundState there and then release-stores the new epoch into word
+// kMirrorSeqWord -- the host reads the round's result by polling that word.
+// bump_seq (optional, device): round counter of the host->device input pipeline, incremented
+// once at the very end of the round (prep_inputs_u8_chunks / mlp_round wait for tag *seq + 1).
+constexpr int kMirrorSeqWord = 64;
 cudaError_t fed_consensus_aggregate(const FedArgs& f, int n_val, int weight_by_score,
-                                    int two_shot, int use_multicast, cudaStream_t s);
+                                    int two_shot, int use_multicast, cudaStream_t s,
+                                    uint32_t* host_mirror = nullptr, uint32_t* bump_seq = nullptr);
 
 // committee ranks: pull every candidate's uploaded weights (bf16 shadow, optionally the fp32
 // master) out of the trainers' HBM into local staging [slot z][n_params], each as soon as its

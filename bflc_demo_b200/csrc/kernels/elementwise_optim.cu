@@ -250,7 +250,7 @@ struct PrepArgs {
   // chunked (input pipeline) variant
   int rows_per_chunk, n_chunks;
   const int* in_flags;       // [n_chunks] written by H2D copies (tag of the data now in src)
-  const int* in_seq;         // tag this round expects
+  const int* in_seq;         // rounds fed so far; this round's chunks carry tag *in_seq + 1
   unsigned int* cnt;         // [n_chunks] monotonically increasing CTA arrivals
   unsigned int* ready;       // [n_chunks] completed conversions (rounds)
   unsigned int* err;         // set to 1 when a chunk's tag never arrived (host checks it)
@@ -281,7 +281,10 @@ __global__ void __launch_bounds__(256) k_prep_inputs(PrepArgs a, const int* pred
 __global__ void __launch_bounds__(256) k_prep_chunks(PrepArgs a) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
-  const int want = *reinterpret_cast<const volatile int*>(a.in_seq);
+  // the round's tag = device round counter + 1: the consensus kernel bumps the counter at the
+  // very end of the round (after every reader), the host tags its copies with the same number
+  // -- no host -> device copy of a sequence word in front of the graph
+  const int want = *reinterpret_cast<const volatile int*>(a.in_seq) + 1;
   const int G = (a.K + 31) / 32, n_kb = (a.K + 127) / 128;
   const long long per = static_cast<long long>(a.rows_per_chunk) * G;
   const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;

@@ -210,7 +210,8 @@ __device__ __forceinline__ unsigned long long digest_term(float v, long long idx
 }
 
 __global__ void __launch_bounds__(kFedThreads)
-k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc) {
+k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc,
+            uint32_t* host_mirror, uint32_t* bump_seq) {
   __shared__ ConsShared sh;
   __shared__ bool last;
   ptx::pdl_launch_dependents();
@@ -478,6 +479,21 @@ k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc)
     __threadfence_system();
   }
   __syncthreads();
+  // input pipeline: every reader of this round's tag (input kernel, trainer) is done -- count
+  // the round so the next one expects the next tag
+  if (bump_seq != nullptr && threadIdx.x == 0) *bump_seq = *bump_seq + 1u;
+  if (host_mirror != nullptr) {
+    // result read-back without a copy-engine launch or a stream sync: the committed ledger page
+    // goes to a pinned host page with plain PCIe posted writes, then a release-store of the new
+    // epoch into the word the host is spinning on (engine/fused.py::run_round_e2e)
+    constexpr int kWords = static_cast<int>(sizeof(RoundState) / 4);
+    const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>(st);
+    for (int i = threadIdx.x; i < kWords; i += blockDim.x)
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(host_mirror + i), "r"(src[i]) : "memory");
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) ptx::st_release_sys(host_mirror + kMirrorSeqWord, epoch + 1);
+  }
   // tell every peer that this rank no longer reads epoch `epoch` buffers
   if (threadIdx.x < n)
     ptx::st_release_sys(
@@ -636,12 +652,13 @@ cudaError_t fed_upload(const FedArgs& f, int n_samples, int n_loss_terms, int by
 }
 
 cudaError_t fed_consensus_aggregate(const FedArgs& f, int n_val, int weight_by_score,
-                                    int two_shot, int use_multicast, cudaStream_t s) {
+                                    int two_shot, int use_multicast, cudaStream_t s,
+                                    uint32_t* host_mirror, uint32_t* bump_seq) {
   const long long work = two_shot ? f.lay.n_params / (f.n_ranks > 0 ? f.n_ranks : 1)
                                   : f.lay.n_params;
   note_launch();
   return launch_pdl(k_consensus, dim3(fed_grid(work)), dim3(kFedThreads), 0, s, f, n_val,
-                    weight_by_score, two_shot, use_multicast);
+                    weight_by_score, two_shot, use_multicast, host_mirror, bump_seq);
 }
 
 cudaError_t fed_pull_candidates(const FedArgs& f, void* stage_shadow, float* stage_master,

@@ -17,6 +17,7 @@
 // split-K atomics; a row-wise softmax-cross-entropy epilogue that emits dlogits + loss +
 // #correct; an argmax-accuracy epilogue (the committee score, python-sdk/main.py:182-183).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
@@ -74,6 +75,7 @@ struct KParams {
   int cv_kw, cv_pad, cv_stride;
   int cv_oh, cv_ow;           // pixel grid enumerated by the rows (mode 1) / the reduction (mode 2)
   int cv_c;                   // channels of the viewed activation
+  int stages;                 // smem ring depth of this launch (<= SmemLayout::kStages)
 };
 
 template <int BN>
@@ -132,21 +134,6 @@ __device__ __forceinline__ void tile_store(const float* stg, void* dptr, long lo
     }
   }
 }
-__device__ __forceinline__ void tile_accumulate_f32(const float* stg, void* dptr, long long tile_off,
-                                                    long long ldd, int row_base, int nc, int M,
-                                                    int N, int cr, int cg) {
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int rr = it * 4 + cr;
-    const int row = row_base + rr;
-    const int col = nc + cg;
-    if (row >= M || col >= N) continue;
-    const float4 x = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cg);
-    const float xs[4] = {x.x, x.y, x.z, x.w};
-    float* d = reinterpret_cast<float*>(dptr) + tile_off + static_cast<long long>(row) * ldd + col;
-    for (int k = 0; k < 4; ++k) if (col + k < N) d[k] += xs[k];
-  }
-}
 // global bf16 tile -> staged fp32 tile (zeros outside the matrix)
 __device__ __forceinline__ void tile_load_bf16(float* stg, const void* sptr, long long tile_off,
                                                long long ldd, int row_base, int nc, int M, int N,
@@ -183,18 +170,22 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, (BN == 64 ? 2 : 1))
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const KParams p) {
   using L = SmemLayout<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes);
+  // Ring depth is a launch parameter: short-K problems take a shallow ring so that two CTAs fit
+  // one SM and one CTA's epilogue overlaps the other's main loop.
+  const int n_stages = p.stages;
+  const int tile_bytes = n_stages * L::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + tile_bytes);
   uint64_t* empty_bar = full_bar + L::kStages;
   uint64_t* accum_bar = empty_bar + L::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-  float* stage_base = reinterpret_cast<float*>(smem + L::kTileBytes + L::kBarBytes);
+  float* stage_base = reinterpret_cast<float*>(smem + tile_bytes + L::kBarBytes);
   float* sbias = stage_base + 4 * 32 * kStgLd;
 
   // Programmatic dependent launch: let the next kernel of the stream get scheduled now; this
@@ -220,7 +211,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     ptx::tma_prefetch_desc(&tmA);
     if (p.b_maps_dev == nullptr) ptx::tma_prefetch_desc(&tmB);
     if (p.cv_mode != 0) ptx::tma_prefetch_desc(&tmC);
-    for (int s = 0; s < L::kStages; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
@@ -260,8 +251,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::fence_proxy_async_all();
     }
     for (int i = 0; i < n_kb; ++i) {
-      const int s = i % L::kStages;
-      const uint32_t ph = (i / L::kStages) & 1;
+      const int s = i % n_stages;
+      const uint32_t ph = (i / n_stages) & 1;
       ptx::mbar_wait(&empty_bar[s], ph ^ 1);
       uint8_t* sa = smem + s * L::kStageBytes;
       uint8_t* sb = sa + kABytes;
@@ -340,8 +331,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t ks_a = p.kstep_a >> 4, ks_b = p.kstep_b >> 4;
     const bool fp8 = p.is_fp8 != 0;
     for (int i = 0; i < n_kb; ++i) {
-      const int s = i % L::kStages;
-      const uint32_t ph = (i / L::kStages) & 1;
+      const int s = i % n_stages;
+      const uint32_t ph = (i / n_stages) & 1;
       ptx::mbar_wait(&full_bar[s], ph);
       ptx::tc_fence_after_sync();
       const uint32_t so = static_cast<uint32_t>(s) * (L::kStageBytes >> 4);
@@ -437,7 +428,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (p.split_k > 1)
           tile_store<0, true>(stg, p.d, tile_off, p.ldd, row_base, nc, p.M, p.N, cr, cg, p.vec_ok);
         else if (p.d_dtype == 0)
-          (p.accumulate ? tile_accumulate_f32(stg, p.d, tile_off, p.ldd, row_base, nc, p.M, p.N, cr, cg)
+          // d += tile: one writer per element, so a fire-and-forget red.add is deterministic and
+          // has no load round trip (the read-modify-write form spent 32 dependent L2 latencies,
+          // 16 us, in a 128 x 128 weight-gradient tile)
+          (p.accumulate ? tile_store<0, true>(stg, p.d, tile_off, p.ldd, row_base, nc, p.M, p.N, cr,
+                                              cg, p.vec_ok)
                         : tile_store<0, false>(stg, p.d, tile_off, p.ldd, row_base, nc, p.M, p.N,
                                                cr, cg, p.vec_ok));
         else if (p.d_dtype == 1)
@@ -671,7 +666,8 @@ cudaError_t launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     configured = true;
   }
   note_launch();
-  return launch_pdl(gemm_kernel<BN, EPI>, grid, dim3(kThreads), L::kTotal, stream, ta, tb, tc, kp);
+  const int smem = L::kTotal - (L::kStages - kp.stages) * L::kStageBytes;
+  return launch_pdl(gemm_kernel<BN, EPI>, grid, dim3(kThreads), smem, stream, ta, tb, tc, kp);
 }
 
 }  // namespace
@@ -833,6 +829,17 @@ cudaError_t gemm_sm100(const GemmProblem& p, cudaStream_t stream) {
   if (cv.mode == 2) { kp.lbo_b = 64u * 128u; kp.kstep_b = mn_kstep; }
 
   dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, p.batch * kp.split_k);
+  {
+    // Ring depth: the full ring for long reductions; 3 stages (2 CTAs per SM with the 64-wide
+    // tile) when every CTA only runs a few K blocks and there is more than a wave of tiles.
+    const int full = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    const int kb_cta = (kp.k_blocks + kp.split_k - 1) / kp.split_k;
+    const long long ctas = static_cast<long long>(grid.x) * grid.y * grid.z;
+    static const int force = [] { const char* e = std::getenv("BFLC_GEMM_STAGES"); return e ? std::atoi(e) : 0; }();
+    kp.stages = full;
+    if (BN == 64 && kb_cta <= 40 && ctas > 148) kp.stages = 3;
+    if (force >= 2 && force <= full) kp.stages = force;
+  }
 #define BFLC_LAUNCH(BN_, EPI_) return launch<BN_, EPI_>(ta, tb, tc, kp, grid, stream)
   const int epi = static_cast<int>(p.epi.kind);
   if (epi == 0) {

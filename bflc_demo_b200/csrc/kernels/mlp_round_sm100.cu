@@ -108,7 +108,7 @@ struct Args {
   int chain;                     // 0: P1|P2|P3 as separate phases   3: P1 | fwd2->xent->dh chained
   int epiopt;                    // optimizer applied in the weight-gradient epilogues (no P5)
   unsigned long long* dbg;       // optional %globaltimer stamps [steps][32] written by CTA 0
-  const unsigned int* x_ready;   // optional input pipeline: step s may read x once x_ready[s] >= *round_seq
+  const unsigned int* x_ready;   // optional input pipeline: step s may read x once x_ready[s] >= *round_seq + 1
   const unsigned int* round_seq;
   long long n_params;
   const int* pred;               // whole kernel is a no-op when *pred == 0 (non-trainer rank)
@@ -1078,7 +1078,7 @@ mlp_round_kernel(const __grid_constant__ Maps maps, const Args a) {
         // Once the LAST chunk is seen ready nothing is checked any more.
         int all = 0;
         if (lane == 0) {
-          const unsigned int want = __ldcg(a.round_seq);
+          const unsigned int want = __ldcg(a.round_seq) + 1u;   // bumped by k_consensus at round end
           unsigned int v;
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.x_ready + a.steps - 1) : "memory");
           all = static_cast<int>(v - want) >= 0 ? 1 : 0;

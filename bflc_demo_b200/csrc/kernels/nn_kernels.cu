@@ -76,6 +76,28 @@ __global__ void k_im2col(const bf16* __restrict__ x, bf16* __restrict__ col, int
   }
 }
 
+// Zero-stuffed upsampling of a strided convolution's output gradient: up[n, s*oh, s*ow, :] =
+// dy[n, oh, ow, :], zero elsewhere.  The input gradient of a stride-s convolution is then the
+// stride-1 implicit-GEMM convolution of `up` (ConvView flip mode).  8 channels (16 B) per thread.
+__global__ void k_upsample_zero(const uint4* __restrict__ dy, uint4* __restrict__ up, int N, int H,
+                                int W, int OH, int OW, int C8, int stride) {
+  const long long total = static_cast<long long>(N) * H * W * C8;
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += step) {
+    const int c = static_cast<int>(i % C8);
+    const long long pix = i / C8;
+    const int iw = static_cast<int>(pix % W);
+    const int ih = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    const int oh = ih / stride, ow = iw / stride;
+    if (oh * stride == ih && ow * stride == iw && oh < OH && ow < OW)
+      v = dy[((static_cast<long long>(n) * OH + oh) * OW + ow) * C8 + c];
+    up[i] = v;
+  }
+}
+
 // gather form of the transpose: each dx element sums the col entries it was copied to
 __global__ void k_col2im(const bf16* __restrict__ col, bf16* __restrict__ dx, int N, int C, int H,
                          int W, int KH, int KW, int stride, int pad, int OH, int OW,
@@ -472,6 +494,13 @@ cudaError_t col2im_bf16(const void* col, void* dx, int N, int C, int H, int W, i
   NN_LAUNCH(k_col2im, blocks_for(static_cast<int64_t>(N) * H * W * C),
             reinterpret_cast<const bf16*>(col), reinterpret_cast<bf16*>(dx), N, C, H, W, KH, KW,
             stride, pad, OH, OW, ld_col);
+}
+cudaError_t upsample_zero_bf16(const void* dy, void* up, int N, int H, int W, int OH, int OW, int C,
+                               int stride, cudaStream_t s) {
+  if (C % 8 != 0) return cudaErrorInvalidValue;
+  NN_LAUNCH(k_upsample_zero, blocks_for(static_cast<int64_t>(N) * H * W * (C / 8)),
+            reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(up), N, H, W, OH, OW, C / 8,
+            stride);
 }
 cudaError_t maxpool2d_fwd(const void* x, void* y, int32_t* idx, int N, int C, int H, int W, int k,
                           int stride, int pad, int OH, int OW, cudaStream_t s) {

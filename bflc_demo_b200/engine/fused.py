@@ -32,6 +32,7 @@ from __future__ import annotations
 import os
 
 import struct
+import time
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -256,6 +257,13 @@ class FusedEngine:
                                 and (cfg.batch_size * self.in_dim) % 16 == 0
                                 and os.environ.get("BFLC_INPUT_PIPELINE", "1") != "0"
                                 and os.environ.get("BFLC_MLP_CHAIN", "3") != "1")
+        # result read-back of run_round_e2e: the consensus kernel mirrors the committed ledger page
+        # into this pinned page and release-stores the new epoch into word MIRROR_SEQ; the host
+        # polls it (no copy-engine launch, no stream sync at the end of a round)
+        self.mirror = torch.zeros(128, dtype=torch.int32).pin_memory()
+        self._mirror_np = self.mirror.numpy()
+        self._epoch_known: Optional[int] = None
+        self.mirror_result = os.environ.get("BFLC_RESULT_MIRROR", "1") != "0"
         self.in_flags = torch.zeros(16, device=self.dev, dtype=torch.int32)
         self.in_seq = torch.zeros(1, device=self.dev, dtype=torch.int32)
         self.cast_cnt = torch.zeros(16, device=self.dev, dtype=torch.int32)
@@ -263,8 +271,13 @@ class FusedEngine:
         self.in_err = torch.zeros(1, device=self.dev, dtype=torch.int32)
         self._ev_wq = torch.cuda.Event()
         self.seq_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._seq_np = self.seq_host.numpy()
         self._seq = 0
         self._copy_stream = torch.cuda.Stream(device=self.dev)
+        # constant arguments of the per-round h2d_pipeline call (kept off the per-round Python path)
+        self._pipe_dst, self._pipe_y = self.x_u8.data_ptr(), self.y.data_ptr()
+        self._pipe_chunk = self.cfg.batch_size * self.in_dim
+        self._pipe_flags = (self.in_flags.data_ptr(), self.seq_host.data_ptr(), self._copy_stream.cuda_stream)
         self.launches_per_round = 0
         if world > 1:
             dist.barrier(group=group)
@@ -355,7 +368,9 @@ class FusedEngine:
             else:
                 self._validate_two_gemms(xv, yv, H)
         m.fed_consensus_aggregate(self.fed, self.n_val, cfg.weight_by_score, self.two_shot,
-                                  cfg.use_multicast and self.heap.has_multicast)
+                                  cfg.use_multicast and self.heap.has_multicast,
+                                  self.mirror.data_ptr() if (pipe and self.mirror_result) else 0,
+                                  self.in_seq.data_ptr() if pipe else 0)
         self.launches_per_round = int(m.launch_count() - n0)
 
     def _validate_two_gemms(self, xv, yv, H):
@@ -386,10 +401,12 @@ class FusedEngine:
             # their H2D copies land.  Its only new kernel is warmed up once outside the capture
             # (lazy module loading), without running an extra round.
             with torch.cuda.stream(self.stream):
+                self.in_seq.fill_(-1)       # the kernel waits for tag *in_seq + 1: 0 = the initial tags
                 self.mod.prep_inputs_chunks(self.x_u8, self.x_bf, self.x_q, self.x_sf,
                                             self.cfg.batch_size, self.steps, 1.0 / 255.0,
                                             self.in_flags, self.in_seq, self.cast_cnt, self.x_ready,
                                             self.in_err)
+                self.in_seq.zero_()         # rounds fed so far (bumped by the consensus kernel)
             self.stream.synchronize()
             gp = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gp, stream=self.stream):
@@ -400,6 +417,8 @@ class FusedEngine:
         # the device BlockRecord ring has ring_slots entries and the consensus kernel overwrites
         # slot epoch % ring_slots: drain into the host ledger before records can be lost
         self._rounds += 1
+        if self._epoch_known is not None:
+            self._epoch_known += 1          # every round advances the epoch by exactly one
         if self._rounds - self.drained >= max(self.cfg.ring_slots // 2, 1):
             errs = self.drain_blocks()
             if errs:
@@ -422,42 +441,67 @@ class FusedEngine:
             # launch the round first, then feed it: labels, chunk 0, tag 0, chunk 1, tag 1, ... on
             # the copy stream; step s of the trainer starts when chunk s has been converted, so
             # the copy of the later chunks hides behind the compute of the earlier steps
+            # The copies of round r carry tag r; the device counts fed rounds itself (the consensus
+            # kernel bumps in_seq at the end of every pipelined round), so nothing has to be
+            # copied in front of the graph.
             self._seq += 1
-            self.seq_host[0] = self._seq
-            with torch.cuda.stream(self.stream):
-                self.in_seq.copy_(self.seq_host, non_blocking=True)
-            chunk_bytes = self.cfg.batch_size * self.in_dim
-            args = (hx.data_ptr(), self.x_u8.data_ptr(), chunk_bytes)
-            tail = (hy.data_ptr(), self.y.data_ptr())
-            flags = (self.in_flags.data_ptr(), self.seq_host.data_ptr(), self._copy_stream.cuda_stream)
+            self._seq_np[0] = self._seq
             # launch the round, then feed it (measured: issuing chunk 0 ahead of the graph launch
             # was slower, profiles/run27_*)
             self.run_round(pipe=True)
-            self.mod.h2d_pipeline(*args, 0, self.steps, *tail, hy.numel() * hy.element_size(), *flags)
+            self.mod.h2d_pipeline(hx.data_ptr(), self._pipe_dst, self._pipe_chunk, 0, self.steps,
+                                  hy.data_ptr(), self._pipe_y, hy.numel() * hy.element_size(),
+                                  *self._pipe_flags)
         else:
             with torch.cuda.stream(self.stream):
                 self.x_u8.copy_(hx, non_blocking=True)
                 self.y.copy_(hy, non_blocking=True)
             self.run_round()
+        if self.pipelined_input and self.mirror_result and self.graph_pipe is not None \
+                and self._epoch_known is not None:
+            # the kernel wrote the page into pinned memory; every chunk copy was consumed before
+            # the trainer's last step, so nothing is in flight once the new epoch is visible
+            self._wait_mirror(self._epoch_known)
+            return self.read_state(self.mirror)
         with torch.cuda.stream(self.stream):
             self.out_host.copy_(self.state_bytes, non_blocking=True)
         self.stream.synchronize()
         if self.pipelined_input:
             self._copy_stream.synchronize()
-        return self.read_state(self.out_host)
+        st = self.read_state(self.out_host)
+        self._epoch_known = st["epoch"]
+        return st
+
+    def _wait_mirror(self, want: int):
+        m, n, t0 = self._mirror_np, 0, None
+        seq = int(self.sz["kMirrorSeqWord"])
+        while int(m[seq]) != want:
+            n += 1
+            if (n & 0x3FFF) == 0:
+                now = time.monotonic()
+                if t0 is None:
+                    t0 = now
+                elif now - t0 > 30.0:
+                    raise RuntimeError(f"round result never reached the host mirror page (want epoch {want}, "
+                                       f"have {int(m[seq])})")
 
     @property
     def h2d_bytes_per_round(self) -> int:
-        tags = 4 * (self.steps + 1) if self.pipelined_input else 0   # per-chunk tags + sequence word
+        tags = 4 * self.steps if self.pipelined_input else 0   # one 4-byte tag per chunk
         return self.host_x.numel() * self.host_x.element_size() + self.host_y.numel() * 4 + tags
 
     @property
     def d2h_bytes_per_round(self) -> int:
+        if self.pipelined_input and self.mirror_result:
+            return int(self.sz["RoundState"]) + 4      # ledger page + epoch word, written by the kernel
         return self.out_host.numel()
 
     # ------------------------------------------------------------------ host views
     def read_state(self, buf: Optional[torch.Tensor] = None) -> dict:
-        b = bytes((self.state_bytes.cpu() if buf is None else buf).numpy())
+        if buf is not None and buf is getattr(self, "mirror", None):   # (GenericFedEngine borrows this method)
+            b = self._mirror_np       # buffer protocol: parsed in place, no copy
+        else:
+            b = bytes((self.state_bytes.cpu() if buf is None else buf).numpy())
         epoch, n_ranks, n_comm, n_agg = struct.unpack_from("<4I", b, 0)
         roles = list(struct.unpack_from("<8I", b, 16))[: self.world]
         med = list(struct.unpack_from("<8f", b, 48))[: self.world]

@@ -170,6 +170,25 @@ def conv_is_implicit(H, W, Cin, kh, kw, stride, pad, Kp) -> bool:
             and _pix_tile(128, OH, OW) and _pix_tile(64, OH, OW) and OW * stride <= 256)
 
 
+def _conv_rows_gemm(flip, act_src, w, out, N, GH, GW, Cc, OH, OW, kh, kw, stride, pad, n_out, bias=None,
+                    act=G.ACT_NONE, pre=None):
+    """Mode-1 implicit GEMM (rows = pixels).  Few output tiles but a long reduction (the deep,
+    small-image ResNet layers) would leave most SMs idle and run the rest at the 128 x 64 tile's
+    L2-feed limit: split the taps x channels reduction over CTAs into an fp32 workspace
+    (red.add), then cast -- wide 256-column tiles on every SM."""
+    M, kb = N * OH * OW, kh * kw * Cc // 64
+    tiles = ((M + 127) // 128) * ((n_out + 255) // 256)
+    sk = min(148 // tiles, kb // 4) if tiles <= 74 else 1
+    if sk >= 2 and bias is None and act == G.ACT_NONE and pre is None and n_out % 4 == 0:
+        ws = torch.zeros(M, n_out, device=out.device, dtype=torch.float32)
+        C().conv_gemm(1, flip, act_src, w, ws, N, GH, GW, Cc, OH, OW, kh, kw, stride, pad, n_out, None, 0,
+                      None, None, 0, None, sk, False)
+        C().cast_f32_to_bf16(ws.view(-1), out.view(-1))
+    else:
+        C().conv_gemm(1, flip, act_src, w, out, N, GH, GW, Cc, OH, OW, kh, kw, stride, pad, n_out, bias, act,
+                      pre, None, 0, None, 1, False)
+
+
 class ConvImplicitFn(Function):
     """NHWC convolution as an implicit GEMM: the tcgen05 GEMM's TMA producer fetches each
     (filter tap, 64 channels) K block as a tap-shifted 4-D box of the activation itself, the
@@ -184,8 +203,7 @@ class ConvImplicitFn(Function):
         OH, OW = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
         y = torch.empty(N * OH * OW, Cout, device=x.device, dtype=BF)
         pre = torch.empty_like(y) if act == G.ACT_GELU else None
-        C().conv_gemm(1, 0, x, w, y, N, H, W, Cin, OH, OW, kh, kw, stride, pad, Cout, b, act, pre,
-                      None, 0, None, 1, False)
+        _conv_rows_gemm(0, x, w, y, N, H, W, Cin, OH, OW, kh, kw, stride, pad, Cout, b, act, pre)
         ctx.save_for_backward(x, w, y if act == G.ACT_RELU else pre)
         ctx.gw, ctx.gb, ctx.act, ctx.need_dx = gw, gb, act, need_dx
         ctx.geom = (N, Cin, H, W, kh, kw, stride, pad, OH, OW)
@@ -213,9 +231,13 @@ class ConvImplicitFn(Function):
         dx = None
         if ctx.needs_input_grad[0] and ctx.need_dx:
             dx = torch.empty(N, H, W, Cin, device=dy.device, dtype=BF)
-            if stride == 1 and Cout % 64 == 0 and _pix_tile(128, H, W):
-                C().conv_gemm(1, 1, dz, w, dx.view(-1, Cin), N, OH, OW, Cout, H, W, kh, kw, 1, pad, Cin,
-                              None, 0, None, None, 0, None, 1, False)
+            if Cout % 64 == 0 and _pix_tile(128, H, W):
+                if stride == 1:
+                    g, GH, GW = dz, OH, OW
+                else:   # zero-stuffed dy on the input grid, then the stride-1 form
+                    g, GH, GW = torch.empty(N, H, W, Cout, device=dy.device, dtype=BF), H, W
+                    C().upsample_zero(dz, g, N, H, W, OH, OW, Cout, stride)
+                _conv_rows_gemm(1, g, w, dx.view(-1, Cin), N, GH, GW, Cout, H, W, kh, kw, 1, pad, Cin)
             else:
                 dcol = G.gemm(dz, w, b_mn=True)
                 C().col2im(dcol, dx, N, Cin, H, W, kh, kw, stride, pad, OH, OW)

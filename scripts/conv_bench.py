@@ -46,10 +46,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--layers", type=int, nargs="*", default=None, help="indices into LAYERS")
+    ap.add_argument("--once", action="store_true", help="one eager implicit pass per layer (for ncu)")
     a = ap.parse_args()
     flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
     rows = []
-    for cin, cout, k, stride, pad, hw in LAYERS:
+    for li, (cin, cout, k, stride, pad, hw) in enumerate(LAYERS):
+        if a.layers is not None and li not in a.layers:
+            continue
         n = a.batch
         x = (torch.randn(n, hw, hw, cin, device="cuda") * 0.5).to(BF).requires_grad_(True)
         w = (torch.randn(cout, k * k * cin, device="cuda") * 0.05).to(BF)
@@ -71,6 +75,10 @@ def main():
             y = TF.conv2d(xc, wc, None, stride=stride, padding=pad)
             y.backward(dyc)
 
+        if a.once:
+            ours(); ours()
+            torch.cuda.synchronize()
+            continue
         F._IMPLICIT = True
         t_imp = timed(ours, a.iters, flush)
         F._IMPLICIT = False
