@@ -6,6 +6,8 @@
 
 #include <cstring>
 #include <memory>
+#include <cuda.h>
+
 #include <optional>
 
 #include "bflc_kernels.h"
@@ -371,19 +373,37 @@ void bind_extra(py::module_& m) {
   });
   m.def("h2d_pipeline", [](int64_t host_x, int64_t dev_x, int64_t chunk_bytes, int c_begin, int c_end,
                            int64_t host_y, int64_t dev_y, int64_t y_bytes, int64_t dev_flags,
-                           int64_t host_seq, int64_t stream_ptr) {
-    // chunks [c_begin, c_end); the labels travel with chunk 0 (y_bytes > 0)
+                           int64_t host_seq, int64_t stream_ptr, bool write_value) {
+    // chunks [c_begin, c_end); the labels travel with chunk 0 (y_bytes > 0).  A chunk's tag is a
+    // stream-ordered 32-bit write behind its copy: cuStreamWriteValue32 (a stream memory
+    // operation, no copy-engine descriptor) or, as a fallback, a 4-byte copy of *host_seq.
+    using WriteFn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    static WriteFn wv = [] {
+      void* sym = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+          q != cudaDriverEntryPointSuccess)
+        sym = nullptr;
+      return reinterpret_cast<WriteFn>(sym);
+    }();
     cudaStream_t s = reinterpret_cast<cudaStream_t>(static_cast<uintptr_t>(stream_ptr));
+    const uint32_t tag = static_cast<uint32_t>(*P<const int32_t>(host_seq));
     if (y_bytes > 0)
       check(cudaMemcpyAsync(P<void>(dev_y), P<const void>(host_y), (size_t)y_bytes, cudaMemcpyHostToDevice, s),
             "h2d labels");
     for (int c = c_begin; c < c_end; ++c) {
       check(cudaMemcpyAsync(P<char>(dev_x) + c * chunk_bytes, P<const char>(host_x) + c * chunk_bytes,
                             (size_t)chunk_bytes, cudaMemcpyHostToDevice, s), "h2d chunk");
-      check(cudaMemcpyAsync(P<int32_t>(dev_flags) + c, P<const void>(host_seq), 4, cudaMemcpyHostToDevice, s),
-            "h2d tag");
+      bool done = false;
+      if (write_value && wv != nullptr)
+        done = wv(reinterpret_cast<CUstream>(s), static_cast<CUdeviceptr>(dev_flags + 4 * c), tag, 0u) == CUDA_SUCCESS;
+      if (!done)
+        check(cudaMemcpyAsync(P<int32_t>(dev_flags) + c, P<const void>(host_seq), 4, cudaMemcpyHostToDevice, s),
+              "h2d tag");
     }
-  });
+  }, py::arg("host_x"), py::arg("dev_x"), py::arg("chunk_bytes"), py::arg("c_begin"), py::arg("c_end"),
+     py::arg("host_y"), py::arg("dev_y"), py::arg("y_bytes"), py::arg("dev_flags"), py::arg("host_seq"),
+     py::arg("stream_ptr"), py::arg("write_value") = true);
   m.def("cast_u8_to_bf16", [](at::Tensor src, at::Tensor dst, double scale) {
     check(bflc::cast_u8_to_bf16(src.data_ptr<uint8_t>(), dst.data_ptr(), src.numel(), (float)scale,
                                 cur_stream()),

@@ -67,6 +67,11 @@ def initial_roles(cfg: FLConfig) -> List[int]:
     return roles
 
 
+# RoundState (csrc/include/bflc_kernels.h): epoch, n_ranks, n_comm, n_aggregate, role[8],
+# last_median[8], selected_mask, global_loss, model_digest, blocks_appended, n_needed
+_ROUND_STATE = struct.Struct("<4I8I8fIfQII")
+
+
 class FusedEngine:
     def __init__(self, cfg: FLConfig, shard: Shard, *, rank: int = 0, world: int = 1,
                  device: int = 0, group=None, in_dim: Optional[int] = None):
@@ -79,6 +84,7 @@ class FusedEngine:
         self.mod = C()
         sz = self.mod.struct_sizes()
         self.sz = sz
+        assert sz["RoundState"] == _ROUND_STATE.size, "RoundState layout changed: update _ROUND_STATE"
 
         # ---- model + heap --------------------------------------------------------------
         x0 = shard.x.reshape(len(shard), -1)
@@ -278,6 +284,8 @@ class FusedEngine:
         self._pipe_dst, self._pipe_y = self.x_u8.data_ptr(), self.y.data_ptr()
         self._pipe_chunk = self.cfg.batch_size * self.in_dim
         self._pipe_flags = (self.in_flags.data_ptr(), self.seq_host.data_ptr(), self._copy_stream.cuda_stream)
+        self._prefeed = os.environ.get("BFLC_E2E_PREFEED", "1") == "1"
+        self._tag_wv = os.environ.get("BFLC_E2E_TAGS", "writevalue") != "memcpy"
         self.launches_per_round = 0
         if world > 1:
             dist.barrier(group=group)
@@ -448,10 +456,17 @@ class FusedEngine:
             self._seq_np[0] = self._seq
             # launch the round, then feed it (measured: issuing chunk 0 ahead of the graph launch
             # was slower, profiles/run27_*)
-            self.run_round(pipe=True)
-            self.mod.h2d_pipeline(hx.data_ptr(), self._pipe_dst, self._pipe_chunk, 0, self.steps,
-                                  hy.data_ptr(), self._pipe_y, hy.numel() * hy.element_size(),
-                                  *self._pipe_flags)
+            yb = hy.numel() * hy.element_size()
+            if self._prefeed:   # labels + chunk 0 travel while the graph launch is in progress
+                self.mod.h2d_pipeline(hx.data_ptr(), self._pipe_dst, self._pipe_chunk, 0, 1,
+                                      hy.data_ptr(), self._pipe_y, yb, *self._pipe_flags, self._tag_wv)
+                self.run_round(pipe=True)
+                self.mod.h2d_pipeline(hx.data_ptr(), self._pipe_dst, self._pipe_chunk, 1, self.steps,
+                                      0, 0, 0, *self._pipe_flags, self._tag_wv)
+            else:
+                self.run_round(pipe=True)
+                self.mod.h2d_pipeline(hx.data_ptr(), self._pipe_dst, self._pipe_chunk, 0, self.steps,
+                                      hy.data_ptr(), self._pipe_y, yb, *self._pipe_flags, self._tag_wv)
         else:
             with torch.cuda.stream(self.stream):
                 self.x_u8.copy_(hx, non_blocking=True)
@@ -499,7 +514,11 @@ class FusedEngine:
     # ------------------------------------------------------------------ host views
     def read_state(self, buf: Optional[torch.Tensor] = None) -> dict:
         if buf is not None and buf is getattr(self, "mirror", None):   # (GenericFedEngine borrows this method)
-            b = self._mirror_np       # buffer protocol: parsed in place, no copy
+            # hot path of run_round_e2e: one precompiled unpack straight out of the pinned page
+            f = _ROUND_STATE.unpack_from(self._mirror_np, 0)
+            w = self.world
+            return dict(epoch=f[0], roles=list(f[4:4 + w]), median=list(f[12:12 + w]), selected_mask=f[20],
+                        global_loss=f[21], model_digest=f[22])
         else:
             b = bytes((self.state_bytes.cpu() if buf is None else buf).numpy())
         epoch, n_ranks, n_comm, n_agg = struct.unpack_from("<4I", b, 0)
