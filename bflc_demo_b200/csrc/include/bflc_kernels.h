@@ -92,12 +92,14 @@ struct GemmProblem {
 
 // cuTensorMapEncodeTiled is a driver call and needs a context current on the calling thread;
 // worker threads (e.g. PyTorch's autograd thread) may never have bound the primary context
-// (observed: CUDA_ERROR_INVALID_CONTEXT).  Bind it once per thread -- never again, because
-// cudaFree is illegal while a stream capture is active.
+// (observed: CUDA_ERROR_INVALID_CONTEXT).  Bind it once per thread with cudaSetDevice (legal while
+// a stream capture is active -- cudaFree(nullptr), the usual idiom, invalidates the capture when
+// a thread makes its first GEMM call inside one, e.g. autograd's worker during graph capture).
 inline void bind_context_once() {
   static thread_local bool bound = false;
   if (!bound) {
-    (void)cudaFree(nullptr);
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) (void)cudaSetDevice(dev);
     bound = true;
   }
 }

@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(256) k_quantize_mlp_blob(BlobArgs a) {
 
 #define BFLC_LAUNCH_1D(kernel, nvec, ...)                       \
   do {                                                          \
+    (void)cudaGetLastError(); /* drop a stale error of this thread */ \
     kernel<<<grid_for(nvec), kBlock, 0, s>>>(__VA_ARGS__);      \
     note_launch();                                              \
     return cudaGetLastError();                                  \

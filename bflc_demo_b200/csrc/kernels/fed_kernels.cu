@@ -684,6 +684,7 @@ cudaError_t fed_pull_blobs(const FedArgs& f, long long off0, long long off1, lon
 }
 
 cudaError_t fed_wait_trained(const FedArgs& f, cudaStream_t s) {
+  (void)cudaGetLastError();
   k_wait_trained<<<1, 32, 0, s>>>(f);
   note_launch();
   return cudaGetLastError();

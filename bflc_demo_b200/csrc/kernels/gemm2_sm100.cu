@@ -316,6 +316,7 @@ cudaError_t gemm2_sm100(const GemmProblem& p, cudaStream_t stream) {
   const int tiles = kp.m_pairs * kp.n_tiles;
   const int pairs = tiles < 74 ? tiles : 74;
   dim3 grid(2 * pairs, 1, 1);
+  (void)cudaGetLastError();
   gemm2_kernel<<<grid, kThreads, kSmemTotal, stream>>>(ta, tb, kp);
   note_launch();
   return cudaGetLastError();

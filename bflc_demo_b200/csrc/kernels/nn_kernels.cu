@@ -469,6 +469,7 @@ __global__ void k_act_bwd_colsum(const bf16* __restrict__ dy, const bf16* __rest
 cudaError_t act_bwd_colsum(const void* dy, const void* aux, void* dz, float* colsum, int64_t rows,
                            int C, int mode, cudaStream_t s) {
   dim3 g((C + 31) / 32, static_cast<unsigned>(rows / 64 > 128 ? 128 : (rows / 64 > 0 ? rows / 64 : 1)));
+  (void)cudaGetLastError();
   k_act_bwd_colsum<<<g, kT, 0, s>>>(reinterpret_cast<const bf16*>(dy),
                                     reinterpret_cast<const bf16*>(aux), reinterpret_cast<bf16*>(dz),
                                     colsum, rows, C, mode);
@@ -478,6 +479,7 @@ cudaError_t act_bwd_colsum(const void* dy, const void* aux, void* dz, float* col
 
 #define NN_LAUNCH(kernel, grid, ...)            \
   do {                                          \
+    (void)cudaGetLastError(); /* drop a stale error of this thread */ \
     kernel<<<grid, kT, 0, s>>>(__VA_ARGS__);    \
     note_launch();                              \
     return cudaGetLastError();                  \
@@ -534,6 +536,7 @@ cudaError_t batchnorm_fwd(const void* x, void* y, const float* gamma, const floa
     e = cudaMemsetAsync(rstd, 0, sizeof(float) * C, s);
     if (e != cudaSuccess) return e;
     dim3 g((C + 31) / 32, static_cast<unsigned>(rows / 64 > 64 ? 64 : (rows / 64 > 0 ? rows / 64 : 1)));
+    (void)cudaGetLastError();
     k_bn_stats<<<g, kT, 0, s>>>(reinterpret_cast<const bf16*>(x), mean, rstd, rows, C);
     note_launch();
     k_bn_finalize<<<(C + 127) / 128, 128, 0, s>>>(mean, rstd, run_mean, run_var, rows, C, eps,
@@ -552,6 +555,7 @@ cudaError_t batchnorm_bwd(const void* dy, const void* x, const void* y, const fl
   // must be isolated, so reduce into them only when they are zero on entry (the optimizer zeroes
   // the gradient buffer every step) -- documented contract.
   dim3 g((C + 31) / 32, static_cast<unsigned>(rows / 64 > 64 ? 64 : (rows / 64 > 0 ? rows / 64 : 1)));
+  (void)cudaGetLastError();
   k_bn_bwd_reduce<<<g, kT, 0, s>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x),
                                    reinterpret_cast<const bf16*>(y), mean, rstd, dgamma, dbeta, rows,
                                    C, relu);

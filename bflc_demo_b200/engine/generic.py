@@ -178,6 +178,21 @@ class GenericFedEngine:
             dist.barrier(group=self.group)
         if not self.cfg.cuda_graph:
             return
+        # A rank that was committee in the warm-up round has never run the training body (and a
+        # trainer never the validation forward): do both once, eagerly, on saved-and-restored
+        # state, so that no first-use initialisation (lazy module loading, per-thread context
+        # binding of autograd's worker, buffer caches) happens inside a capture.
+        with torch.cuda.stream(self.stream):
+            state = [t for t in (self.work_master, self.work_shadow, self.grad, self.m, self.v) if t is not None]
+            keep = [t.clone() for t in state]
+            plan = self.plan_bytes.clone()
+            self.local_training()
+            self.net.correct(self.bound, self.x[: self.n_val], self.y[: self.n_val])
+            for t, k in zip(state, keep):
+                t.copy_(k)
+            self.plan_bytes.copy_(plan)
+        torch.cuda.synchronize()
+        del keep, plan
         try:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self.stream):

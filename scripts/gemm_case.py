@@ -1,4 +1,6 @@
 """One GEMM bring-up case per process (a device trap poisons the context). Prints a JSON line."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 import json, sys, time
 import torch
 from bflc_demo_b200.ops import gemm as G

@@ -6,6 +6,7 @@
 tag=$1; shift
 out=gpurun_out/$tag
 mkdir -p "$out"
+export PYTHONPATH=$PWD:$PYTHONPATH
 nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$out/smi.csv" 2>&1
 i=0
 for cmd in "$@"; do

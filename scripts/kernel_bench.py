@@ -1,5 +1,7 @@
 """Hot-cache, event-timed microbenchmarks of the individual kernels of one MLP training step
 (and of a whole captured step), to separate launch overhead from execution time."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 import json, sys
 import torch
 from bflc_demo_b200.ops import gemm as G

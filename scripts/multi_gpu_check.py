@@ -16,6 +16,8 @@ Checks:
               uploads read out of the trainers' HBM, ascending rank order, fp32 fma) in PyTorch and
               compares it with the device result -- bf16 and fp8 engines
 """
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 import json
 import os
 import sys

@@ -1,5 +1,7 @@
 """Multi-GPU substrate probe (torchrun): symmetric heap modes, P2P read bandwidth from inside a
 kernel, NVLS multicast store, flag latency.  Prints one JSON line from rank 0."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 import json, os, sys, time
 import torch, torch.distributed as dist
 from bflc_demo_b200._native import C
