@@ -250,7 +250,8 @@ k_consensus(FedArgs f, int n_val, int weight_by_score, int two_shot, int use_mc,
       for (int z = 0; z < plan->n_cand; ++z)
         row[cand_of[z]] =
             static_cast<float>(plan->correct[z]) / static_cast<float>(n_val > 0 ? n_val : 1);
-      __threadfence_system();
+      // the row was written by THIS lane: the sys-scope release store below orders it, no
+      // separate membar.sys (which also waited for every other outstanding write of the SM)
       ptx::st_release_sys(at<uint32_t>(f.peers.base[r], f.lay.flags_off) + FLAG_SCORED + f.rank,
                           epoch + 1);
     }

@@ -146,10 +146,20 @@ def main():
             }
             if byz_ranks:
                 bz = byz_ranks[0]
+                as_tr = [b for b in blocks if bz in b["admitted"]]
                 line["byzantine_check"] = {
-                    "rank": bz, "rounds_as_trainer": sum(bz in b["admitted"] for b in blocks),
+                    "rank": bz, "rounds_as_trainer": len(as_tr),
+                    "times_selected": sum(bz in b["selected"] for b in as_tr),
                     "ever_selected": any(bz in b["selected"] for b in blocks),
-                    "ever_elected": any(b["role_after"][bz] == 2 for b in blocks)}
+                    # with committee >= trainers every trainer is re-elected by construction
+                    "ever_elected": any(b["role_after"][bz] == 2 for b in blocks),
+                    "election_is_structural": cfg.committee_size >= cfg.n_trainers,
+                    # per round the Byzantine rank trained: its median score vs the honest trainers'
+                    # (block.median is per admitted trainer, in admission order)
+                    "median_byz_vs_honest": [
+                        [round(b["median"][b["admitted"].index(bz)], 4),
+                         [round(m, 4) for t, m in zip(b["admitted"], b["median"]) if t != bz]]
+                        for b in as_tr][:12]}
             print(json.dumps(line), flush=True)
         del eng
         torch.cuda.empty_cache()
