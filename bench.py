@@ -151,11 +151,26 @@ def main():
 
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
+    _start = torch.zeros(1, dtype=torch.int64, device="cuda") if n > 1 else None
+    _ALIGN = os.environ.get("BFLC_BENCH_ALIGN", "1") != "0"
+
     def sync_all():
+        """Barrier + synchronize on every rank; then the ranks leave together.  An NCCL barrier
+        releases the processes several (up to ~20) microseconds apart, and with a step of ~250 us
+        that host-side skew lands 1:1 in the max-over-ranks time of whoever started first (it waits
+        for the late ranks' uploads).  All ranks run on one node, so CLOCK_MONOTONIC is common: agree
+        on an instant a little in the future and spin until it -- outside every timed interval."""
         torch.cuda.synchronize()
         if n > 1:
             dist.barrier()
-            torch.cuda.synchronize()
+            if not _ALIGN:
+                torch.cuda.synchronize()
+                return
+            _start[0] = time.monotonic_ns() + 300_000
+            dist.all_reduce(_start, op=dist.ReduceOp.MAX)
+            tgt = int(_start.item())          # (also synchronizes the device)
+            while time.monotonic_ns() < tgt:
+                pass
 
     def reduce_max(vals):
         t = torch.tensor(vals, device="cuda", dtype=torch.float64)

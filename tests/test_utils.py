@@ -81,3 +81,37 @@ def test_param_spec_offsets_are_tma_aligned():
     flat2 = torch.empty(mlp_spec().total)
     mlp_spec().init_(flat2, seed=3)
     assert torch.equal(flat, flat2)                  # identical genesis on every rank
+
+
+def test_implicit_conv_eligibility_and_pixel_tiles():
+    """Host-side geometry of the implicit-GEMM convolution (ops/nn.py mirrors
+    csrc/kernels/gemm_sm100.cu::conv_pixel_tile): a pixel tile is whole image rows."""
+    from bflc_demo_b200.ops import nn as F
+    assert F._pix_tile(128, 32, 32) and F._pix_tile(64, 32, 32)      # 4 / 2 rows of one image
+    assert F._pix_tile(128, 16, 16) and F._pix_tile(128, 8, 8)       # 8 rows; two whole 8x8 images
+    assert F._pix_tile(128, 4, 4) and F._pix_tile(64, 4, 4)          # 8 / 4 whole 4x4 images
+    assert not F._pix_tile(128, 28, 28)                              # 128 % 28 != 0
+    assert not F._pix_tile(128, 12, 16)                              # 8 rows do not divide 12
+    assert not F._pix_tile(64, 7, 128)                               # a row is wider than the tile
+    # ResNet-18 body layers are eligible; the stem (Cin = 3) and LeNet (Cin = 3 / 6, 5x5) are not
+    assert F.conv_is_implicit(32, 32, 64, 3, 3, 1, 1, 9 * 64)
+    assert F.conv_is_implicit(32, 32, 64, 3, 3, 2, 1, 9 * 64)
+    assert F.conv_is_implicit(16, 16, 128, 1, 1, 2, 0, 128)
+    assert not F.conv_is_implicit(32, 32, 3, 3, 3, 1, 1, 32)
+    assert not F.conv_is_implicit(14, 14, 6, 5, 5, 1, 0, 152)
+    prev = F.set_precision("mx8")                                    # fp8 forward keeps the im2col path
+    try:
+        assert not F.conv_is_implicit(32, 32, 64, 3, 3, 1, 1, 9 * 64)
+    finally:
+        F.set_precision(prev)
+
+
+def test_round_state_mirror_layout_matches_the_native_struct():
+    """run_round_e2e parses the pinned mirror page with one precompiled struct."""
+    from bflc_demo_b200._native import C
+    from bflc_demo_b200.engine.fused import _ROUND_STATE
+    sz = C().struct_sizes()
+    assert _ROUND_STATE.size == sz["RoundState"]
+    assert sz["state_epoch_off"] == 0 and sz["state_role_off"] == 16
+    assert sz["state_global_loss_off"] == 84 and sz["state_digest_off"] == 88
+    assert sz["kMirrorSeqWord"] * 4 >= sz["RoundState"]
