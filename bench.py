@@ -333,7 +333,7 @@ def main():
             # reference); the comparator is OUR NCCL+cuBLAS build of the same round, timed by this
             # same invocation (key "baseline"): vs_baseline = value / baseline.value
             "vs_baseline": (K / (dev_ms / 1e3)) / base["value"] if base else None,
-            "dtype": "mxfp8" if args.dtype == "fp8" else "bf16", "data": "synthetic (class-conditional FEMNIST-like 28x28 uint8, 62 classes; random-init weights)",
+            "dtype": "mxfp8" if (args.dtype == "fp8" and args.impl == "fused") else "bf16", "data": "synthetic (class-conditional FEMNIST-like 28x28 uint8, 62 classes; random-init weights)",
             "impl": args.impl if args.impl == "fused" else "nccl-baseline (ours, not a reference build)",
             "config": {"model": f"mlp_784x{args.hidden}x62", "global_batch": trainers * eng.S,
                        "seq_len": None, "parallelism": f"fed-dp{n} (committee {cfg.committee_size}, "
