@@ -195,11 +195,9 @@ def main():
                 sync_all()
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
-                with torch.cuda.stream(eng.stream):
-                    e0.record()
-                fn(i)
-                with torch.cuda.stream(eng.stream):
-                    e1.record()
+                e0.record(eng.stream)      # (no stream context manager: its Python cost would sit
+                fn(i)                      #  between the event and the launch, inside the interval)
+                e1.record(eng.stream)
                 e1.synchronize()
                 out.append(e0.elapsed_time(e1))
             return out

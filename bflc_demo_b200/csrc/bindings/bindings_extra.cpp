@@ -371,6 +371,14 @@ void bind_extra(py::module_& m) {
                                       reinterpret_cast<unsigned int*>(err.data_ptr()), cur_stream()),
           "prep_inputs_u8_chunks");
   });
+  // cudaGraphLaunch of an instantiated graph (torch.cuda.CUDAGraph.raw_cuda_graph_exec()) on a
+  // given stream: the per-round launch without the stream-guard / generator bookkeeping of
+  // CUDAGraph.replay() on the Python path.
+  m.def("graph_launch", [](int64_t exec_ptr, int64_t stream_ptr) {
+    check(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(static_cast<uintptr_t>(exec_ptr)),
+                          reinterpret_cast<cudaStream_t>(static_cast<uintptr_t>(stream_ptr))),
+          "cudaGraphLaunch");
+  });
   m.def("h2d_pipeline", [](int64_t host_x, int64_t dev_x, int64_t chunk_bytes, int c_begin, int c_end,
                            int64_t host_y, int64_t dev_y, int64_t y_bytes, int64_t dev_flags,
                            int64_t host_seq, int64_t stream_ptr, bool write_value) {

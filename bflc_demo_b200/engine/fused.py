@@ -253,6 +253,7 @@ class FusedEngine:
         self._rounds = 0
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_pipe: Optional[torch.cuda.CUDAGraph] = None
+        self._exec: Dict[int, int] = {}
         self.stream = torch.cuda.Stream(device=self.dev)
         self._side = torch.cuda.Stream(device=self.dev)
         self._side2 = torch.cuda.Stream(device=self.dev)
@@ -420,6 +421,16 @@ class FusedEngine:
             with torch.cuda.graph(gp, stream=self.stream):
                 self._enqueue_round(pipe=True)
             self.graph_pipe = gp
+        # raw executable handles for the per-round launch (the captured rounds use no torch RNG, so
+        # CUDAGraph.replay()'s generator prologue has nothing to do)
+        self._stream_ptr = self.stream.cuda_stream
+        if os.environ.get("BFLC_RAW_GRAPH_LAUNCH", "1") != "0":
+            for gg in (self.graph, self.graph_pipe):
+                try:
+                    if gg is not None:
+                        self._exec[id(gg)] = int(gg.raw_cuda_graph_exec())
+                except Exception:      # older torch: fall back to replay()
+                    pass
 
     def run_round(self, pipe: bool = False):
         # the device BlockRecord ring has ring_slots entries and the consensus kernel overwrites
@@ -433,8 +444,12 @@ class FusedEngine:
                 raise RuntimeError(f"host/device ledgers disagree: {errs[:2]}")
         g = self.graph_pipe if (pipe and self.graph_pipe is not None) else self.graph
         if g is not None:
-            with torch.cuda.stream(self.stream):
-                g.replay()
+            ex = self._exec.get(id(g))
+            if ex:      # cudaGraphLaunch straight on the engine stream (no guard, no replay bookkeeping)
+                self.mod.graph_launch(ex, self._stream_ptr)
+            else:
+                with torch.cuda.stream(self.stream):
+                    g.replay()
         else:
             with torch.cuda.stream(self.stream):
                 self._enqueue_round(pipe=pipe)
