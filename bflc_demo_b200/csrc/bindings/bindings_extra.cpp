@@ -192,12 +192,16 @@ void bind_extra(py::module_& m) {
           "fed_consensus_aggregate");
   }, py::arg("fed"), py::arg("n_val"), py::arg("weight_by_score"), py::arg("two_shot"),
      py::arg("use_mc"), py::arg("host_mirror") = 0, py::arg("bump_seq") = 0);
-  m.def("fed_pull_candidates", [](const py::dict& fd, at::Tensor stage_shadow, const OptT& stage_master) {
+  m.def("fed_pull_candidates", [](const py::dict& fd, at::Tensor stage_shadow, const OptT& stage_master,
+                                  const OptT& ranges) {
+    // ranges: int64 [n][2] device tensor {first float4, float4 count} -- the fp32 parts to pull
+    const long long* rp = ranges.has_value() ? reinterpret_cast<const long long*>(ranges->data_ptr<int64_t>())
+                                             : nullptr;
     check(bflc::fed_pull_candidates(make_fed(fd), stage_shadow.data_ptr(),
                                     stage_master.has_value() ? stage_master->data_ptr<float>() : nullptr,
-                                    cur_stream()),
+                                    cur_stream(), rp, ranges.has_value() ? (int)ranges->size(0) : 0),
           "fed_pull_candidates");
-  });
+  }, py::arg("fed"), py::arg("stage_shadow"), py::arg("stage_master"), py::arg("ranges") = py::none());
   m.def("fed_wait_trained", [](const py::dict& fd) {
     check(bflc::fed_wait_trained(make_fed(fd), cur_stream()), "fed_wait_trained");
   });

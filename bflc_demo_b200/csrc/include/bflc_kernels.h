@@ -495,8 +495,10 @@ cudaError_t fed_consensus_aggregate(const FedArgs& f, int n_val, int weight_by_s
 // committee ranks: pull every candidate's uploaded weights (bf16 shadow, optionally the fp32
 // master) out of the trainers' HBM into local staging [slot z][n_params], each as soon as its
 // trainer's flag is up.  stage_master may be null.
+// `ranges` (optional, device, [n_ranges][2] = {first float4, float4 count}): pull only these
+// parts of the fp32 master -- the 1-D parameters a forward pass reads in fp32.
 cudaError_t fed_pull_candidates(const FedArgs& f, void* stage_shadow, float* stage_master,
-                                cudaStream_t s);
+                                cudaStream_t s, const long long* ranges = nullptr, int n_ranges = 0);
 // committee ranks, fp8 MLP: pull each candidate's blob (nbytes at heap offset off0/off1 by
 // epoch parity) into stage + slot * nbytes as soon as its trainer's flag is up
 cudaError_t fed_pull_blobs(const FedArgs& f, long long off0, long long off1, long long nbytes,

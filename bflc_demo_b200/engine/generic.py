@@ -133,9 +133,27 @@ class GenericFedEngine:
                                 self.work_shadow, self.m, self.v, cfg.learning_rate, 0.0, 0.9,
                                 0.999, 1e-8, i + 1, self.opt_step_ptr, 0, True)
 
+    def _vector_ranges(self) -> torch.Tensor:
+        """fp32 parts of an update that a forward pass reads from the master copy: every 1-D
+        parameter (biases, norm scales / shifts, running statistics); matrices are consumed from
+        the bf16 copy.  Coalesced {first float4, float4 count} pairs for ``fed_pull_candidates`` --
+        for BERT-base this is 0.1 % of the 437 MB master."""
+        runs = []
+        for e in self.net.spec.entries:
+            if len(e.shape) != 1:
+                continue
+            lo, hi = e.offset // 4, (e.offset + e.shape[0] + 3) // 4
+            if runs and runs[-1][1] >= lo:
+                runs[-1][1] = max(runs[-1][1], hi)
+            else:
+                runs.append([lo, hi])
+        t = torch.tensor([[lo, hi - lo] for lo, hi in runs], dtype=torch.int64).reshape(-1, 2)
+        return t.to(self.dev)
+
     def _ensure_stage(self):
         if self._stage is None:
             P = self.n_params
+            self._ranges = self._vector_ranges()
             self._stage = (torch.empty(self.world, P, device=self.dev, dtype=torch.bfloat16),
                            torch.empty(self.world, P, device=self.dev, dtype=torch.float32))
             self._stage_bounds = [self.net.bind(self._stage[1][z], self._stage[0][z], None)
@@ -149,7 +167,8 @@ class GenericFedEngine:
         sequence is identical every round and therefore capturable."""
         xv, yv = self.x[: self.n_val], self.y[: self.n_val]
         self._ensure_stage()
-        self.mod.fed_pull_candidates(self.fed, self._stage[0], self._stage[1])
+        self.mod.fed_pull_candidates(self.fed, self._stage[0], self._stage[1],
+                                     self._ranges if self._ranges.numel() else None)
         for z in range(self.n_cand):
             cnt = self.net.correct(self._stage_bounds[z], xv, yv)
             self.val_correct[z:z + 1].copy_(cnt)

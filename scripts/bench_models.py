@@ -113,7 +113,11 @@ def main():
         agg = torch.tensor([agg_us], device="cuda", dtype=torch.float64)
         digs = [st["model_digest"]]
         all_errs = [errs]
+        pkeys = sorted(stamps[0])
+        pmed = torch.tensor([sorted(s_[k] for s_ in stamps)[len(stamps) // 2] for k in pkeys],
+                            device="cuda", dtype=torch.float64)
         if world > 1:
+            dist.all_reduce(pmed, op=dist.ReduceOp.MAX)
             dist.all_reduce(agg, op=dist.ReduceOp.MAX)
             digs = [None] * world
             dist.all_gather_object(digs, st["model_digest"])
@@ -140,6 +144,7 @@ def main():
                 "replicas_bit_identical": len(set(digs)) == 1,
                 "ledger_mismatches": [e for e in all_errs if e][:2], "chain_ok": eng.host_ledger.verify_chain(),
                 "clocks": clocks,
+                "phases_us_max_over_ranks": {k: round(v, 1) for k, v in zip(pkeys, pmed.tolist())},
                 "fedavg": {"aggregate_publish_us_max_over_ranks": round(float(agg.item()), 1),
                            "nvlink_bytes_per_rank": int(nv_bytes), "roofline_us_at_770GBs": round(roof_us, 1),
                            "fraction_of_nvlink_roofline": round(roof_us / max(float(agg.item()), 1e-9), 3)},
