@@ -92,7 +92,10 @@ class GenericFedEngine:
 
         self.x = net.preprocess(shard.x.to(self.dev))
         self.y = shard.y.to(self.dev, torch.int32)
-        self.two_shot = cfg.two_shot if cfg.two_shot is not None else (P * 4 > (64 << 20) and world > 1)
+        # same rule as the fused engine: big updates always, and from 8 ranks up any update (eight
+        # ranks each pulling every selected upload contend with the committee's pulls)
+        self.two_shot = (cfg.two_shot if cfg.two_shot is not None
+                         else world > 1 and (P * 4 > (64 << 20) or world >= 8))
         self.byz = 1 if rank in cfg.byzantine_ranks else 0
         self.straggle_us = cfg.straggler_delay_us if rank in cfg.straggler_ranks else 0
         self._peer_bounds = {}
