@@ -210,6 +210,12 @@ def main():
 
         for i in range(W):
             round_e2e(i)
+        if n > 1:
+            # a few more untimed rounds through the exact timed paths (barrier, flush, events) so
+            # that every rank's launch path is warm before the first timed round: the first
+            # multi-GPU run on a fresh box otherwise shows the ranks' launches further apart
+            timed(round_only, 8)
+            timed(round_e2e, 4)
         sync_all()
         sampler = ClockSampler(local_rank) if (rank == 0 and want_clocks) else None
         if sampler:
