@@ -132,6 +132,8 @@ void bind_extra(py::module_& m) {
     d["plan_round_seq_off"] = offsetof(bflc::RoundPlan, round_seq);
     d["plan_opt_total_off"] = offsetof(bflc::RoundPlan, opt_total);
     d["plan_cand_blob_off"] = offsetof(bflc::RoundPlan, cand_blob);
+    d["plan_cand_src_off"] = offsetof(bflc::RoundPlan, cand_src);
+    d["plan_pull_cnt_off"] = offsetof(bflc::RoundPlan, pull_cnt);
     d["state_epoch_off"] = offsetof(bflc::RoundState, epoch);
     d["state_role_off"] = offsetof(bflc::RoundState, role);
     d["state_global_loss_off"] = offsetof(bflc::RoundState, global_loss);
@@ -153,7 +155,7 @@ void bind_extra(py::module_& m) {
   // ------------------------------------------------------------ fed kernels
   m.def("fed_plan_round", [](const py::dict& fd, std::vector<std::pair<int64_t, bool>> layers,
                              int steps_per_round, bool staged, int64_t blob_stage_ptr, int64_t blob_bytes,
-                             std::vector<int64_t> upq_off) {
+                             std::vector<int64_t> upq_off, bool fused_pull) {
     bflc::FedArgs f = make_fed(fd);
     bflc::PlanLayer pl[bflc::kMaxPlanLayers];
     TORCH_CHECK((int)layers.size() <= bflc::kMaxPlanLayers, "too many plan layers");
@@ -167,12 +169,14 @@ void bind_extra(py::module_& m) {
       TORCH_CHECK(upq_off.size() == 2, "upq_off: heap offsets of the two parity upload blobs");
       pb.stage = P<uint8_t>(blob_stage_ptr); pb.bytes = blob_bytes;
       pb.upq_off[0] = upq_off[0]; pb.upq_off[1] = upq_off[1];
+      pb.fused_pull = fused_pull ? 1 : 0;
     }
     check(bflc::fed_plan_round(f, pl, (int)layers.size(), steps_per_round, staged ? 1 : 0, cur_stream(),
                                blobs ? &pb : nullptr),
           "fed_plan_round");
   }, py::arg("fed"), py::arg("layers"), py::arg("steps_per_round"), py::arg("staged"),
-     py::arg("blob_stage_ptr") = 0, py::arg("blob_bytes") = 0, py::arg("upq_off") = std::vector<int64_t>{});
+     py::arg("blob_stage_ptr") = 0, py::arg("blob_bytes") = 0, py::arg("upq_off") = std::vector<int64_t>{},
+     py::arg("fused_pull") = false);
   m.def("fed_pull_blobs", [](const py::dict& fd, int64_t off0, int64_t off1, int64_t nbytes, at::Tensor stage) {
     check(bflc::fed_pull_blobs(make_fed(fd), off0, off1, nbytes, stage.data_ptr(), cur_stream()), "fed_pull_blobs");
   });
@@ -295,7 +299,8 @@ void bind_extra(py::module_& m) {
   // committee validation of every candidate in one launch (fwd1 -> relu -> fwd2 -> argmax)
   m.def("mlp_val", [](at::Tensor x, at::Tensor labels, at::Tensor correct, at::Tensor maps,
                       int64_t dyn1_ptr, int64_t dyn2_ptr, int n_val, int in_dim, int hidden,
-                      int n_classes, int max_cand, const OptT& x_sf, int64_t cand_blob_ptr) {
+                      int n_classes, int max_cand, const OptT& x_sf, int64_t cand_blob_ptr,
+                      int64_t cand_src_ptr, int64_t pull_cnt_ptr, int64_t blob_bytes, int64_t stamps_ptr) {
     bflc::MlpValArgs r;
     r.n_val = n_val; r.in_dim = in_dim; r.hidden = hidden; r.n_classes = n_classes;
     r.max_cand = max_cand;
@@ -309,11 +314,19 @@ void bind_extra(py::module_& m) {
       r.fp8 = true;
       r.x_sf = x_sf->data_ptr<uint8_t>();
       r.cand_blob = P<const uint8_t* const>(cand_blob_ptr);
+      if (cand_src_ptr != 0) {   // fused gather of the candidate blobs inside the kernel
+        r.cand_src = P<const uint8_t* const>(cand_src_ptr);
+        r.pull_cnt = P<unsigned int>(pull_cnt_ptr);
+        r.blob_bytes = blob_bytes;
+        r.stamps = P<unsigned long long>(stamps_ptr);
+      }
     }
     check(bflc::mlp_val_sm100(r, cur_stream()), "mlp_val_sm100");
   }, py::arg("x"), py::arg("labels"), py::arg("correct"), py::arg("maps"), py::arg("dyn1_ptr"),
      py::arg("dyn2_ptr"), py::arg("n_val"), py::arg("in_dim"), py::arg("hidden"), py::arg("n_classes"),
-     py::arg("max_cand"), py::arg("x_sf") = py::none(), py::arg("cand_blob_ptr") = 0);
+     py::arg("max_cand"), py::arg("x_sf") = py::none(), py::arg("cand_blob_ptr") = 0,
+     py::arg("cand_src_ptr") = 0, py::arg("pull_cnt_ptr") = 0, py::arg("blob_bytes") = 0,
+     py::arg("stamps_ptr") = 0);
   m.def("quantize_mlp_blob", [](at::Tensor master, std::vector<int64_t> offs, int in_dim, int hidden,
                                 int n_classes, at::Tensor blob) {
     TORCH_CHECK(offs.size() == 4, "offs = element offsets of w1, b1, w2, b2");

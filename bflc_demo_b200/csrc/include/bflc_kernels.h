@@ -204,6 +204,14 @@ struct MlpValArgs {
   bool fp8 = false;
   const uint8_t* x_sf = nullptr;
   const uint8_t* const* cand_blob = nullptr;   // device array [max_cand]
+  // fused gather ("QueryAllUpdates" inside the validation kernel): when cand_src is set, the
+  // CTAs of candidate z first copy z's blob out of the trainer's HBM (cand_src[z], P2P loads,
+  // 1/gridDim.x each) into the local slot cand_blob[z], meet on pull_cnt[z], then validate from
+  // the local copy -- no separate pull kernel.  Needs gridDim.x <= 128 (co-residency).
+  const uint8_t* const* cand_src = nullptr;    // device array [max_cand] (RoundPlan::cand_src)
+  unsigned int* pull_cnt = nullptr;            // device array [max_cand], zeroed by the plan kernel
+  long long blob_bytes = 0;
+  unsigned long long* stamps = nullptr;        // optional RoundPlan::t_stamp (pull begin / end)
 };
 cudaError_t mlp_val_sm100(const MlpValArgs& r, cudaStream_t stream);
 
@@ -354,6 +362,8 @@ struct RoundPlan {
   uint32_t parity;
   GemmDynamic dyn[kMaxPlanLayers];
   const uint8_t* cand_blob[kMaxRanks];  // fp8 MLP: candidate z's Mx8MlpLayout blob (staging slot or peer)
+  const uint8_t* cand_src[kMaxRanks];   // fused gather: the trainer's upload blob the slot is filled from
+  unsigned int pull_cnt[kMaxRanks];     // fused gather: CTAs of candidate z that finished their share
   unsigned int correct[kMaxRanks];  // validation hits per candidate slot (accuracy epilogue)
   float loss_sum;                   // local-training loss accumulator (xent epilogue)
   unsigned int train_correct;
@@ -466,6 +476,7 @@ struct PlanLayer {
 // upload blob at heap offset upq_off[parity])
 struct PlanBlobs {
   uint8_t* stage = nullptr; long long bytes = 0; long long upq_off[2] = {0, 0};
+  int fused_pull = 0;   // staged slots are filled by the validation kernel itself (MlpValArgs::cand_src)
 };
 cudaError_t fed_plan_round(const FedArgs& f, const PlanLayer* layers, int n_layers,
                            int steps_per_round, int staged, cudaStream_t s,

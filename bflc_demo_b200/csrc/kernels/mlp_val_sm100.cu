@@ -60,7 +60,16 @@ struct ValArgs {
   const int* pred;
   // fp8
   const uint8_t* x_sf; const uint8_t* const* cand_blob; Mx8MlpLayout ql;
+  // fused gather of the candidate blobs (see MlpValArgs)
+  const uint8_t* const* cand_src; unsigned int* pull_cnt; long long blob_bytes;
+  unsigned long long* stamps;
 };
+
+__device__ __forceinline__ void val_stamp(unsigned long long* stamps, int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  atomicMax(stamps + slot, t);
+}
 
 template <bool FP8>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -106,6 +115,41 @@ mlp_val_kernel(const __grid_constant__ CUtensorMap tmX, const ValArgs v) {
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   const uint32_t base_lo = ptx::smem_u32(smem) >> 4;
   const uint8_t* blob = FP8 ? v.cand_blob[z] : nullptr;
+
+  if (FP8 && v.cand_src != nullptr) {
+    // ---- fused gather (reference: QueryAllUpdates, CommitteePrecompiled.cpp:299-311).  The
+    // gridDim.x CTAs that validate candidate z each copy 1/gridDim.x of z's blob out of the
+    // trainer's HBM with 16-byte P2P loads as soon as its FLAG_TRAINED is up, publish their share
+    // (device-scope fence + counter), wait for the others' shares and only then start the TMA /
+    // bulk loads of the local copy.  Every candidate crosses NVLink once per committee rank, and
+    // there is no pull kernel in front of the validation.
+    if (threadIdx.x == 0 && v.stamps != nullptr && blockIdx.x == 0 && z == 0) val_stamp(v.stamps, STAMP_PULL_BEGIN);
+    if (threadIdx.x == 0 && v.dyn1->wait_flag[z] != nullptr)
+      ptx::wait_flag_ge(v.dyn1->wait_flag[z], v.dyn1->wait_value);
+    __syncthreads();
+    const float4* src = reinterpret_cast<const float4*>(v.cand_src[z]);
+    float4* dst = reinterpret_cast<float4*>(const_cast<uint8_t*>(blob));
+    const long long n16 = v.blob_bytes >> 4;
+    const long long per = (n16 + gridDim.x - 1) / gridDim.x;
+    const long long lo = per * blockIdx.x, hi = lo + per < n16 ? lo + per : n16;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = ptx::ld_peer_f4(src + i);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      atomicAdd(v.pull_cnt + z, 1u);
+      unsigned long long spins = 0;
+      unsigned int have;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(v.pull_cnt + z) : "memory");
+        if (have >= gridDim.x) break;
+        __nanosleep(20);
+      } while (++spins < (1ull << 26));
+      if (have < gridDim.x) __trap();   // a sibling CTA never arrived: co-residency assumption broken
+      if (v.stamps != nullptr && blockIdx.x == 0) val_stamp(v.stamps, STAMP_PULL_END);
+    }
+    __syncthreads();
+    ptx::fence_proxy_async_all();   // the others' generic-proxy stores -> this CTA's TMA / bulk loads
+  }
 
   if (warp == 0) {
     if (v.dyn1->wait_flag[z] != nullptr) {   // candidate z's trainer has published its upload
@@ -313,6 +357,14 @@ cudaError_t mlp_val_sm100(const MlpValArgs& r, cudaStream_t stream) {
   v.labels = r.labels; v.correct = r.correct;
   v.pred = r.pred ? r.pred : current_predicate();
   v.x_sf = r.x_sf; v.cand_blob = r.cand_blob; v.ql = mx8_mlp_layout(r.in_dim, r.hidden);
+  if (r.cand_src != nullptr) {
+    // every CTA of a candidate must be able to run while its siblings spin on the counter
+    if (!r.fp8 || r.pull_cnt == nullptr || r.blob_bytes <= 0 || r.blob_bytes % 16 != 0 ||
+        (r.n_val + kBM - 1) / kBM > 128)
+      return cudaErrorInvalidValue;
+    v.cand_src = r.cand_src; v.pull_cnt = r.pull_cnt; v.blob_bytes = r.blob_bytes;
+    v.stamps = r.stamps;
+  }
   static bool configured[2] = {false, false};
   if (!configured[r.fp8 ? 1 : 0]) {
     e = r.fp8 ? cudaFuncSetAttribute(mlp_val_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kValSmem)

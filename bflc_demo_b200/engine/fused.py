@@ -245,6 +245,16 @@ class FusedEngine:
         self.first_k = (not cfg.solo) and cfg.needed_updates < cfg.n_trainers
         if self.first_k and not self.staged:
             raise ValueError("needed_updates < trainers (first-K-wins admission) needs stage_candidates=True")
+        # Hot path 1 as ONE kernel (opt-in, BFLC_FUSED_PULL=1): the validation CTAs gather the
+        # candidates' MXFP8 blobs out of the trainers' HBM themselves (mlp_val_sm100.cu).  Correct
+        # (multi_gpu_check fused / fedavg / byzantine) but measured 4 us per round SLOWER than the
+        # separate pull kernel at 2 GPUs (249.7 vs 244.3 us, profiles/r2/bench_n2_fused_pull_ab_*.log):
+        # k_pull_blob is already resident and spinning on the trainers' flags when they arrive and
+        # its tail overlaps the validation kernel's prologue (PDL), while the in-kernel gather adds
+        # a P2P round trip plus a counter barrier to every validation CTA.  Default: separate pull.
+        # first-K mode always keeps the pull kernel (slot -> trainer is only known from the tickets).
+        self.fused_pull = (self.fp8 and self.staged and not self.first_k and (self.n_val + 127) // 128 <= 128
+                           and os.environ.get("BFLC_FUSED_PULL", "0") == "1")
         self.fused_step = bool(cfg.fused_step) and self.trainer.fused_ok(self.steps)
         # UploadLocalUpdate inside the trainer's last optimizer epilogue (needs E_OPT)
         self.fused_upload = self.fused_step and os.environ.get("BFLC_MLP_EPIOPT", "1") != "0"
@@ -325,7 +335,7 @@ class FusedEngine:
             self._ev_join.record(self._side)
         if self.fp8:
             m.fed_plan_round(self.fed, self.plan_layers, self.steps, self.staged,
-                             self.cand_q.data_ptr(), self.blob_bytes, self.upq_off)
+                             self.cand_q.data_ptr(), self.blob_bytes, self.upq_off, self.fused_pull)
         else:
             m.fed_plan_round(self.fed, self.plan_layers, self.steps, self.staged)
         if not pipe:
@@ -355,7 +365,9 @@ class FusedEngine:
             m.fed_upload(self.fed, self.S, self.steps * B, self.byz, cfg.byzantine_scale, self.straggle_us)
         # committee validation: grouped GEMMs whose B operands are the trainers' uploads
         if self.staged:
-            if self.fp8:
+            if self.fused_pull:
+                pass        # QueryAllUpdates happens inside the validation kernel (fused gather)
+            elif self.fp8:
                 m.fed_pull_blobs(self.fed, self.upq_off[0], self.upq_off[1], self.blob_bytes, self.cand_q)
             else:
                 m.fed_pull_candidates(self.fed, self.cand_shadow, None)
@@ -365,7 +377,9 @@ class FusedEngine:
             m.mlp_val(self.x_q[: self.n_val], self.y[: self.n_val], self.val_correct, self.b_maps,
                       self.dyn_ptr[0], self.dyn_ptr[1], self.n_val, self.in_dim, H,
                       self.spec.by_name["w2"].shape[0], self.world, self.x_sf,
-                      self.plan_ptr + self.sz["plan_cand_blob_off"])
+                      self.plan_ptr + self.sz["plan_cand_blob_off"],
+                      *((self.plan_ptr + self.sz["plan_cand_src_off"], self.plan_ptr + self.sz["plan_pull_cnt_off"],
+                         self.blob_bytes, self.plan_ptr + self.sz["plan_stamps_off"]) if self.fused_pull else ()))
             m.set_predicate(0)
         else:
             xv, yv = self.x_bf[: self.n_val], self.y[: self.n_val]
