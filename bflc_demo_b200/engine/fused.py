@@ -12,7 +12,8 @@ page (role bits), not by launch topology.
                                        (csrc/kernels/mlp_round_sm100.cu; per-GEMM launches +
                                        fed_upload with ``fused_step=False``: models/mlp.py)
     [committee] fed_pull_*             QueryAllUpdates: each candidate's weights cross NVLink once
-                                       (fp8: one 227 KB blob per candidate)
+                                       (fp8: one 227 KB blob per candidate); BFLC_FUSED_PULL=1 moves
+                                       this gather into the validation kernel itself
                 mlp_val                validation of every candidate in one launch (or two grouped
                                        GEMMs whose TMA pulls the trainers' HBM directly)
     fed_consensus_aggregate            UploadScores + Aggregate + QueryGlobalModel

@@ -44,6 +44,7 @@ def main():
     from bflc_demo_b200.engine.fused import FusedEngine
 
     def run_fused(rounds=6, **kw):
+        kw.setdefault("dtype", os.environ.get("BFLC_CHECK_DTYPE", "bf16"))   # fp8: MXFP8 trainer + blobs
         cfg = FLConfig.for_world(world, hidden=256, batch_size=128, samples_per_client=512,
                                  learning_rate=0.05, **kw)
         shard = femnist_like(world, 512, seed=3, only=rank)[0]

@@ -17,10 +17,11 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _run(which):
+def _run(which, **extra_env):
     n = min(torch.cuda.device_count(), 8)
     n = 8 if n >= 8 else (4 if n >= 4 else 2)
-    env = dict(os.environ, PYTHONPATH=ROOT + ":" + os.environ.get("PYTHONPATH", ""), BFLC_NO_AUTOBUILD="1")
+    env = dict(os.environ, PYTHONPATH=ROOT + ":" + os.environ.get("PYTHONPATH", ""), BFLC_NO_AUTOBUILD="1",
+               **extra_env)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                           f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port",
                           str(_free_port()), os.path.join(ROOT, "scripts", "multi_gpu_check.py"), *which],
@@ -50,6 +51,18 @@ def test_fedavg_result_equals_weighted_mean_of_uploads():
         assert r["errs"] == [] and r["n_selected"] >= 1
         assert r["worst_rel"] < 1e-6, r          # (bit_exact is reported; fp64 emulation of fma can
                                                  #  double-round a rare element by one ulp)
+
+
+def test_gather_fused_into_the_validation_kernel():
+    """BFLC_FUSED_PULL=1: no pull kernel -- the validation CTAs copy the candidates' MXFP8 blobs out
+    of the trainers' HBM themselves (mlp_val_sm100.cu).  Same protocol results, and the FedAvg check
+    still holds bit for bit."""
+    n, res = _run(["fused", "fedavg"], BFLC_FUSED_PULL="1", BFLC_CHECK_DTYPE="fp8")
+    f = res["fused"]
+    assert f["errs"] == [] and f["identical_digest"] and f["identical_chain"] and f["chain_ok"]
+    assert all(e == 7 for e in f["epochs"]) and f["loss"][-1] < f["loss"][0]
+    r = res["fedavg"]["fp8"]
+    assert r["errs"] == [] and r["worst_rel"] < 1e-6, r
 
 
 def test_first_k_admission_drops_the_straggler():
