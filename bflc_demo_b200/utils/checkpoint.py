@@ -96,6 +96,12 @@ def load_checkpoint(path: str, eng) -> dict:
     _set_plan_counters(eng, blob.get("opt_total", 0), max(cur_seq, int(blob.get("round_seq", 0))))
     eng.drained = epoch
     eng._rounds = epoch
+    # host-side caches of the ledger page are stale now: the e2e path re-learns the epoch with one
+    # synchronous read, the generic engine re-reads its role table
+    if hasattr(eng, "_epoch_known"):
+        eng._epoch_known = None
+    if hasattr(eng, "_st"):
+        eng._st = None
     torch.cuda.synchronize()
     if eng.world > 1:
         dist.barrier(group=eng.group)

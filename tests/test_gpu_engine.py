@@ -73,6 +73,14 @@ def test_checkpoint_resume_continues_the_chain(tmp_path):
     blocks = b.host_ledger.blocks()
     assert len(blocks) == 6 and blocks[4]["prev_hash"] == last_hash and b.host_ledger.verify_chain()
     assert b.read_state()["epoch"] == 6
+    # the end-to-end path after a restore that happened AFTER capture (run.py's order): its cached
+    # epoch must be re-learnt, then the pinned mirror page takes over again
+    c = FusedEngine(cfg, shard, rank=0, world=1, device=0)
+    c.capture()
+    c.run_round_e2e()
+    load_checkpoint(str(tmp_path / "ck.pt"), c)
+    assert [c.run_round_e2e()["epoch"] for _ in range(3)] == [5, 6, 7]
+    assert c.drain_blocks() == [] and c.host_ledger.verify_chain()
 
 
 def test_generic_engine_lenet_solo_and_tracing():
