@@ -32,6 +32,23 @@ from ..parallel.symm import SymmetricHeap
 from .fused import ROLE_COMM, ROLE_TRAINER, FusedEngine, initial_roles
 
 
+def vector_ranges(spec) -> torch.Tensor:
+    """fp32 parts of an update that a forward pass reads from the master copy: every 1-D
+    parameter (biases, norm scales / shifts, running statistics); matrices are consumed from
+    the bf16 copy.  Coalesced {first float4, float4 count} pairs for ``fed_pull_candidates`` --
+    for BERT-base this is 0.1 % of the 437 MB master.  int64 [n, 2] on the CPU."""
+    runs = []
+    for e in spec.entries:
+        if len(e.shape) != 1:
+            continue
+        lo, hi = e.offset // 4, (e.offset + e.shape[0] + 3) // 4
+        if runs and runs[-1][1] >= lo:
+            runs[-1][1] = max(runs[-1][1], hi)
+        else:
+            runs.append([lo, hi])
+    return torch.tensor([[lo, hi - lo] for lo, hi in runs], dtype=torch.int64).reshape(-1, 2)
+
+
 class GenericFedEngine:
     read_state = FusedEngine.read_state
     drain_blocks = FusedEngine.drain_blocks
@@ -137,21 +154,7 @@ class GenericFedEngine:
                                 0.999, 1e-8, i + 1, self.opt_step_ptr, 0, True)
 
     def _vector_ranges(self) -> torch.Tensor:
-        """fp32 parts of an update that a forward pass reads from the master copy: every 1-D
-        parameter (biases, norm scales / shifts, running statistics); matrices are consumed from
-        the bf16 copy.  Coalesced {first float4, float4 count} pairs for ``fed_pull_candidates`` --
-        for BERT-base this is 0.1 % of the 437 MB master."""
-        runs = []
-        for e in self.net.spec.entries:
-            if len(e.shape) != 1:
-                continue
-            lo, hi = e.offset // 4, (e.offset + e.shape[0] + 3) // 4
-            if runs and runs[-1][1] >= lo:
-                runs[-1][1] = max(runs[-1][1], hi)
-            else:
-                runs.append([lo, hi])
-        t = torch.tensor([[lo, hi - lo] for lo, hi in runs], dtype=torch.int64).reshape(-1, 2)
-        return t.to(self.dev)
+        return vector_ranges(self.net.spec).to(self.dev)
 
     def _ensure_stage(self):
         if self._stage is None:

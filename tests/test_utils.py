@@ -115,3 +115,30 @@ def test_round_state_mirror_layout_matches_the_native_struct():
     assert sz["state_epoch_off"] == 0 and sz["state_role_off"] == 16
     assert sz["state_global_loss_off"] == 84 and sz["state_digest_off"] == 88
     assert sz["kMirrorSeqWord"] * 4 >= sz["RoundState"]
+
+
+def test_vector_ranges_cover_exactly_the_1d_parameters():
+    """The committee pulls the bf16 copy of a candidate plus only these fp32 ranges
+    (engine/generic.py::vector_ranges -> fed_pull_candidates)."""
+    from bflc_demo_b200.engine.generic import vector_ranges
+    from bflc_demo_b200.models.nets import build_model
+    for name, kw in (("lenet5", {}), ("resnet18", {}), ("bert", {"layers": 2})):
+        spec = build_model(name, 10, **kw).spec
+        r = vector_ranges(spec)
+        assert r.dtype == torch.int64 and r.shape[1] == 2 and (r[:, 1] > 0).all()
+        lo, hi = r[:, 0] * 4, (r[:, 0] + r[:, 1]) * 4
+        assert (lo[1:] > hi[:-1]).all()                      # sorted, coalesced, disjoint
+        covered = torch.zeros(spec.total + 8, dtype=torch.bool)
+        for a, b in zip(lo.tolist(), hi.tolist()):
+            assert b <= spec.total + 3
+            covered[a:b] = True
+        for e in spec.entries:
+            seg = covered[e.offset:e.offset + e.numel]
+            if len(e.shape) == 1:
+                assert seg.all(), e.name                     # every 1-D parameter is pulled in fp32
+            else:
+                # a matrix is never pulled in fp32, except for the <= 3 elements a rounded-up
+                # neighbouring range may touch at its very start (alignment padding makes that 0)
+                assert int(seg.sum()) == 0, e.name
+        frac = float((hi - lo).sum()) / spec.total
+        assert frac < 0.02 if name != "lenet5" else frac < 0.1
